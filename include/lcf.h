@@ -1,0 +1,200 @@
+/*
+ * lcf.h -- C ABI of liblcf_b200.so, the B200 (sm_100a) implementation of the
+ * lightcurve_fitting MCMC hot path.
+ *
+ * The reference (griffin-h/lightcurve_fitting) is pure Python and has no FFI; the
+ * boundary it exposes for this path is a set of Python call signatures.  Each entry
+ * point below names the reference interface it replaces (file:line relative to
+ * /root/reference/lightcurve_fitting/).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only: opaque handles, int/int64/double scalars, caller-owned host
+ *     buffers (C-contiguous).  No torch / numpy types cross this boundary.
+ *   - every function returns 0 on success, <0 on error; lcf_last_error() returns a
+ *     thread-local message.
+ *   - handles are not thread-safe; each handle owns one CUDA stream.
+ *   - there is NO CPU fallback: every compute entry point fails with LCF_ERR_CUDA when
+ *     no sm_100-class device is usable.
+ */
+#ifndef LCF_H
+#define LCF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCF_ABI_VERSION 1
+
+/* error codes */
+#define LCF_OK            0
+#define LCF_ERR_ARG      -1   /* invalid argument                                     */
+#define LCF_ERR_CUDA     -2   /* CUDA runtime / no device                             */
+#define LCF_ERR_NAN      -3   /* log-posterior evaluated to NaN (emcee: ValueError)   */
+#define LCF_ERR_STATE    -4   /* call sequence error (e.g. run before set_state)      */
+#define LCF_ERR_NWALKERS -5   /* nwalkers < 2*ndim (emcee RedBlueMove: RuntimeError)  */
+
+/* model ids: models.py classes */
+#define LCF_MODEL_SHOCKCOOLING       1   /* models.py:301-353  */
+#define LCF_MODEL_SHOCKCOOLING2      2   /* models.py:356-411  */
+#define LCF_MODEL_SHOCKCOOLING3      3   /* models.py:433-496  */
+#define LCF_MODEL_SHOCKCOOLING4      4   /* models.py:507-632  */
+#define LCF_MODEL_COMPANIONSHOCKING  5   /* models.py:848-918  */
+#define LCF_MODEL_COMPANIONSHOCKING2 6   /* models.py:921-980  */
+#define LCF_MODEL_COMPANIONSHOCKING3 7   /* models.py:983-1045 */
+#define LCF_MODEL_BLACKBODY_SED      8   /* bolometric.py:154-164 with spectrum=planck_fast */
+
+/* prior kinds: models.py:1048-1098 */
+#define LCF_PRIOR_UNIFORM    0
+#define LCF_PRIOR_LOGUNIFORM 1
+#define LCF_PRIOR_GAUSSIAN   2
+
+#define LCF_PRECISION_FP64 0   /* parity mode: rtol 1e-9 vs the reference arithmetic */
+#define LCF_PRECISION_FP32 1   /* throughput mode: rtol 1e-4                          */
+
+#define LCF_MAX_NDIM 12
+#define LCF_NMODEL_CONSTS 16
+
+/* per-filter role bits (CompanionShocking*, models.py:811-815, 913-916) */
+#define LCF_ROLE_KASEN_RU  1   /* filt.char == 'U': shock component times r_U         */
+#define LCF_ROLE_SIFTO_RR  2   /* filt.char == 'r': SiFTO times r_r                   */
+#define LCF_ROLE_SIFTO_RI  4   /* filt.char == 'i': SiFTO times r_i                   */
+#define LCF_ROLE_DT_U      8   /* filter is filtdict['U']: SiFTO epoch offset dt_U    */
+#define LCF_ROLE_DT_I     16   /* filter is filtdict['i']: SiFTO epoch offset dt_i    */
+
+typedef struct lcf_problem  lcf_problem;    /* one light curve / SED epoch + model + priors   */
+typedef struct lcf_ensemble lcf_ensemble;   /* walker ensemble resident in HBM                */
+typedef struct lcf_batch    lcf_batch;      /* many independent (problem, ensemble) pairs     */
+
+/*
+ * Problem description.  All arrays are host pointers, copied by lcf_problem_create.
+ *
+ * Filter bank (replaces Filter.trans / Filter.synthesize, filters.py:181-214, 288-310):
+ *   for filter f the samples k in [bank_offsets[f], bank_offsets[f+1]) carry
+ *     bank_alpha[k] = c1 * nu_k * (1+z)                      [kK]   (exp argument = alpha / T)
+ *     bank_w[k]     = c2 * nu'_k^3 * min(1, nu_c/nu'_k) * T_norm_per_freq_k * trapz_weight_k
+ *                     (times 10^(-0.4*ebv*kappa_k) for a fixed ebv)
+ *     bank_kappa[k] = A_F99(lambda'_k; a_v = 3.1) per unit E(B-V)  (only read by ShockCooling3)
+ *   so that  synthesize(planck_fast, T, R) == R^2 * sum_k bank_w[k] / (exp(bank_alpha[k]/T) - 1).
+ *
+ * Points (replaces lc['MJD'], lc['filter'], lc[q], lc['d'+q]; models.py:116-119):
+ *   must be grouped by filter: point_filter[] non-decreasing.
+ */
+typedef struct {
+    int32_t model_id;
+    int32_t precision;
+    int32_t ndim;             /* model parameters (+1 when use_sigma)                         */
+    int32_t use_sigma;        /* models.py:128-133                                            */
+    int32_t sigma_type;       /* 0 = 'relative' (sigma_units = dy), 1 = 'absolute' (median dy) */
+    int32_t npoints;
+    int32_t nfilters;
+    int32_t reserved0;
+    double  sigma_unit_abs;   /* np.median(dy) when sigma_type == 1                           */
+    double  model_consts[LCF_NMODEL_CONSTS];
+                              /* BaseShockCooling: A, a, alpha, epsilon_1, epsilon_2, L_0, T_0,
+                                 Tph_to_Tcol (models.py:195-224); others: unused               */
+    const int32_t *bank_offsets;  /* [nfilters+1] */
+    const double  *bank_alpha;    /* [bank_offsets[nfilters]] */
+    const double  *bank_w;
+    const double  *bank_kappa;    /* may be NULL unless model_id == SHOCKCOOLING3 */
+    const int32_t *filter_role;   /* [nfilters] LCF_ROLE_* bits; may be NULL */
+    /* SiFTO cubic splines (models.py:701-717): uniform knots x0 + i*dx, i in [0, n_knots);
+       sifto_coef[f][i][0..3] = scipy PPoly coefficients (highest power first) of interval i */
+    int32_t       sifto_nknots;
+    int32_t       reserved1;
+    double        sifto_x0, sifto_dx;
+    const double *sifto_coef;     /* [nfilters][sifto_nknots-1][4]; NULL unless CompanionShocking* */
+    const double  *t;             /* [npoints] */
+    const int32_t *point_filter;  /* [npoints] index into the bank */
+    const double  *y;             /* [npoints] */
+    const double  *dy;            /* [npoints] */
+    /* priors (models.py:1048-1098) */
+    const int32_t *prior_kind;    /* [ndim] */
+    const double  *prior_min;     /* [ndim] strict bounds */
+    const double  *prior_max;
+    const double  *prior_mean;    /* Gaussian only */
+    const double  *prior_std;
+} lcf_problem_desc;
+
+int         lcf_abi_version(void);
+const char *lcf_last_error(void);
+int         lcf_device_count(void);          /* number of usable CUDA devices (0 on a CPU box) */
+int         lcf_set_device(int device);
+
+int  lcf_problem_create(const lcf_problem_desc *desc, lcf_problem **out);
+void lcf_problem_destroy(lcf_problem *p);
+
+/* Model.__call__(t, f, *params) pointwise (models.py:86-91, 1161-1162): nsets parameter
+   vectors of length n_model_params -> out[nsets][npoints].                                 */
+int lcf_model_eval(lcf_problem *p, int64_t nsets, const double *params, double *out);
+
+/* Model.log_likelihood(lc, p, use_sigma, sigma_type) (models.py:93-136): params[nsets][ndim] */
+int lcf_log_likelihood(lcf_problem *p, int64_t nsets, const double *params, double *out);
+
+/* log_posterior closure (fitting.py:121-128, bolometric.py:154-164).  *nan_count receives the
+   number of NaN results (the reference's emcee raises ValueError on any).                    */
+int lcf_log_posterior(lcf_problem *p, int64_t nsets, const double *params, double *out, int64_t *nan_count);
+
+/* emcee.EnsembleSampler(nwalkers, ndim, log_posterior) with the default StretchMove(a=2)
+   (fitting.py:130, bolometric.py:167).  rank/world shard one ensemble across GPUs: this
+   process proposes/evaluates/accepts only its slice of each half-ensemble (world=1: all). */
+int  lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int rank, int world,
+                         lcf_ensemble **out);
+void lcf_ensemble_destroy(lcf_ensemble *e);
+/* sampler.run_mcmc(initial, ...) first evaluates log_prob(initial): coords[nwalkers][ndim];
+   log_prob may be NULL (computed on device).  Returns LCF_ERR_NAN like emcee.              */
+int  lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *log_prob);
+int  lcf_ensemble_get_state(lcf_ensemble *e, double *coords, double *log_prob);
+/* sampler.reset(): forget the stored chain and acceptance counts, keep the position.       */
+int  lcf_ensemble_reset(lcf_ensemble *e);
+/* nsteps stretch-move iterations with device counter-based RNG (Philox4x32-10 keyed by
+   (seed, iteration, half, walker)); store != 0 appends to the HBM-resident chain.          */
+int  lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store);
+/* the same iterations driven by caller-supplied draws, in emcee's order:
+   split[s][w] in {0,1}; for each step the Ns0 entries for split 0 (ascending walker index)
+   then the Ns1 entries for split 1: z (stretch factors), partner (index into the
+   complementary set, ascending walker order), logu (log of the acceptance uniform).        */
+int  lcf_ensemble_run_replay(lcf_ensemble *e, int64_t nsteps, int store, const int32_t *split,
+                             const double *z, const int32_t *partner, const double *logu);
+/* one half-step only (multi-GPU drivers interleave the all-gather between half-steps)      */
+int  lcf_ensemble_half_step(lcf_ensemble *e, int half, int store);
+int  lcf_ensemble_end_step(lcf_ensemble *e, int store);
+int64_t lcf_ensemble_nstored(lcf_ensemble *e);
+int  lcf_ensemble_get_chain(lcf_ensemble *e, double *chain /* [nstored][nwalkers][ndim] */);
+int  lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob /* [nstored][nwalkers] */);
+int  lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted /* [nwalkers] */);
+/* device-side view for the multi-GPU exchange (torch.distributed wraps these raw pointers):
+   coords are stored colour-major: rows [0, n0) even walkers, [n0, nwalkers) odd walkers.    */
+int  lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream,
+                              int64_t *n0, int64_t *own_begin /* [2] */, int64_t *own_count /* [2] */);
+int  lcf_ensemble_sync(lcf_ensemble *e);
+/* device time (ms) spent in the last lcf_ensemble_run* call, measured with CUDA events on the
+   handle's stream; kernel launches issued by that call.                                    */
+int  lcf_ensemble_last_timing(lcf_ensemble *e, double *ms, int64_t *launches);
+
+/* Batched independent ensembles: one CTA per (problem, ensemble); the whole burn-in +
+   sampling chain runs inside ONE launch (calculate_bolometric's per-epoch loop
+   bolometric.py:735-798; survey-scale light-curve batches).  All problems must share
+   model_id / precision / ndim / use_sigma.                                                 */
+int  lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nwalkers, uint64_t seed,
+                      lcf_batch **out);
+void lcf_batch_destroy(lcf_batch *b);
+int  lcf_batch_set_state(lcf_batch *b, const double *coords /* [nproblems][nwalkers][ndim] */);
+/* run nburn unstored + nsteps stored iterations for every problem                           */
+int  lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps);
+int  lcf_batch_get_chain(lcf_batch *b, double *chain /* [nproblems][nsteps][nwalkers][ndim] */);
+int  lcf_batch_get_log_prob(lcf_batch *b, double *log_prob /* [nproblems][nsteps][nwalkers] */);
+int  lcf_batch_get_accepted(lcf_batch *b, int64_t *accepted /* [nproblems][nwalkers] */);
+int  lcf_batch_get_status(lcf_batch *b, int32_t *status /* [nproblems]: 0 ok, LCF_ERR_NAN */);
+int  lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches);
+
+/* launch-shape overrides for tuning (0 = heuristic): walkers per CTA (power of two <= 32)
+   and warps per CTA.                                                                       */
+int  lcf_set_tuning(int walkers_per_cta, int warps_per_cta);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCF_H */

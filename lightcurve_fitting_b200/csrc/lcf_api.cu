@@ -1,0 +1,1016 @@
+// lcf_api.cu -- host side of liblcf_b200.so: the C ABI declared in include/lcf.h.
+//
+// Everything here is plumbing around the kernels in lcf_device.cuh: argument checks,
+// folding of physical constants / unit scales into the packed filter bank (FP64 on the
+// host), device buffers, launch-shape heuristics, CUDA-event timing.  There is no CPU
+// implementation of the hot path in this library.
+#include "../../include/lcf.h"
+#include "lcf_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lcf;
+
+namespace {
+
+thread_local std::string g_err;
+int g_tune_wpb = 0, g_tune_nw = 0;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(LCF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// physical constants, computed with the same libm calls as the reference's astropy expressions
+// (models.py:10-12, 1101-1102): CODATA 2018 / IAU 2015.
+struct Consts {
+    double kB, c3, c4;
+    Consts() {
+        const double h = 6.62607015e-34, k = 1.380649e-23, c = 299792458.0, e = 1.602176634e-19;
+        const double sigma = 2. * std::pow(M_PI, 5) * std::pow(k, 4) / (15. * std::pow(h, 3) * std::pow(c, 2));
+        const double Rsun = 6.957e8, au = 1.495978707e11;
+        const double Mpc = 1e6 * (au * 648000. / M_PI);
+        kB = k / e * 1e3;
+        c3 = std::pow(4. * M_PI * (sigma * 1e7 * std::pow(Rsun, 2) * 1e12), -0.5) / 1000.;
+        c4 = 1. / (4. * M_PI * std::pow(Mpc, 2.));
+    }
+};
+const Consts &consts() {
+    static Consts c;
+    return c;
+}
+
+template <typename T> int upload(const std::vector<T> &h, void **d) {
+    *d = nullptr;
+    size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(d, bytes));
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int model_nparams(int model) {
+    switch (model) {
+        case 1: return 5;
+        case 2: return 4;
+        case 3: return 7;
+        case 4: return 5;
+        case 5: return 8;
+        case 6: return 7;
+        case 7: return 7;
+        case 8: return 2;
+        default: return -1;
+    }
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------
+// handles
+// -----------------------------------------------------------------------------------------
+struct lcf_problem {
+    ProblemDev dev;
+    int precision = 0;
+    std::vector<void *> allocs;                 // every device allocation, freed on destroy
+    std::vector<int> h_point_filter;            // grouped by filter
+    TileDev tiles[6];                           // per wpb_log2
+    bool tiles_built[6] = {false, false, false, false, false, false};
+    int device = 0;
+    ~lcf_problem() {
+        for (void *p : allocs) cudaFree(p);
+    }
+};
+
+struct lcf_ensemble {
+    lcf_problem *p = nullptr;
+    long long W = 0, n0 = 0, n1 = 0;
+    int D = 0, rank = 0, world = 1;
+    long long own_begin[2] = {0, 0}, own_count[2] = {0, 0};
+    unsigned long long seed = 0;
+    long long iteration = 0;                    // RNG counter, never reset
+    double *d_coords = nullptr, *d_logp = nullptr;
+    unsigned long long *d_acc = nullptr;
+    int *d_nan = nullptr;
+    double *d_chain = nullptr, *d_lnp = nullptr;
+    long long cap = 0, nstored = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool has_state = false;
+    double last_ms = 0.;
+    long long last_launches = 0;
+    ~lcf_ensemble() {
+        cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct lcf_batch {
+    std::vector<lcf_problem *> probs;
+    long long W = 0, n0 = 0, nprob = 0, nsteps_stored = 0, iteration = 0;
+    int D = 0, model = 0, precision = 0, wpb_log2 = 0, nw = 0;
+    size_t smem = 0;
+    unsigned long long seed = 0;
+    ProblemDev *d_probs = nullptr;
+    TileDev *d_tiles = nullptr;
+    double *d_coords = nullptr, *d_logp = nullptr, *d_chain = nullptr, *d_lnp = nullptr;
+    unsigned long long *d_acc = nullptr;
+    int *d_status = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool has_state = false, need_init_logp = true;
+    double last_ms = 0.;
+    long long last_launches = 0;
+    ~lcf_batch() {
+        cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
+        cudaFree(d_acc); cudaFree(d_status);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// -----------------------------------------------------------------------------------------
+// kernel dispatch
+// -----------------------------------------------------------------------------------------
+typedef void (*PassKernel)(const ProblemDev, const TileDev, const MoveDev);
+typedef void (*ChainKernel)(const BatchDev);
+
+template <typename R> PassKernel pass_kernel_for(int model) {
+    switch (model) {
+        case 1: return k_pass<1, R>;
+        case 2: return k_pass<2, R>;
+        case 3: return k_pass<3, R>;
+        case 4: return k_pass<4, R>;
+        case 5: return k_pass<5, R>;
+        case 6: return k_pass<6, R>;
+        case 7: return k_pass<7, R>;
+        case 8: return k_pass<8, R>;
+    }
+    return nullptr;
+}
+template <typename R> ChainKernel chain_kernel_for(int model) {
+    switch (model) {
+        case 1: return k_chain<1, R>;
+        case 2: return k_chain<2, R>;
+        case 3: return k_chain<3, R>;
+        case 4: return k_chain<4, R>;
+        case 5: return k_chain<5, R>;
+        case 6: return k_chain<6, R>;
+        case 7: return k_chain<7, R>;
+        case 8: return k_chain<8, R>;
+    }
+    return nullptr;
+}
+
+size_t smem_bytes(const lcf_problem *p, int wpb, int nw) {
+    if (p->precision == LCF_PRECISION_FP32)
+        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3).total;
+    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3).total;
+}
+
+constexpr size_t kSmemMax = 227 * 1024;
+
+int build_tiles(lcf_problem *p, int l) {
+    if (p->tiles_built[l]) return 0;
+    const int ppt = 32 >> l;
+    std::vector<int4> t;
+    const int N = p->dev.npoints;
+    int i = 0;
+    while (i < N) {
+        int f = p->h_point_filter[i], j = i;
+        while (j < N && p->h_point_filter[j] == f) ++j;
+        for (int s = i; s < j; s += ppt) t.push_back(make_int4(s, std::min(ppt, j - s), f, 0));
+        i = j;
+    }
+    void *d = nullptr;
+    int rc = upload(t, &d);
+    if (rc) return rc;
+    p->allocs.push_back(d);
+    p->tiles[l].tiles = reinterpret_cast<const int4 *>(d);
+    p->tiles[l].ntiles = (int)t.size();
+    p->tiles_built[l] = true;
+    return 0;
+}
+
+// launch-shape heuristic: walkers per CTA (2^l) and warps per CTA
+int choose_shape(lcf_problem *p, long long Ns, int *l_out, int *nw_out, size_t *smem_out) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    int l = 5;
+    if (g_tune_wpb > 0) {
+        l = 0;
+        while ((1 << l) < g_tune_wpb && l < 5) ++l;
+    } else {
+        // enough CTAs to cover the SMs a few times over, otherwise trade walkers/CTA for CTAs
+        while (l > 0 && (Ns + (1 << l) - 1) / (1 << l) < 2LL * sms) --l;
+    }
+    while (l > 0 && smem_bytes(p, 1 << l, 16) > kSmemMax / 2) --l;   // keep >= 2 CTAs/SM when the table is big
+    while (l > 0 && smem_bytes(p, 1 << l, 16) > kSmemMax) --l;
+    int rc = build_tiles(p, l);
+    if (rc) return rc;
+    int nw = g_tune_nw > 0 ? g_tune_nw : 8;
+    long long ngroups = (Ns + (1 << l) - 1) / (1 << l);
+    if (g_tune_nw <= 0) {
+        if (ngroups >= 16LL * sms) nw = 4;          // plenty of CTAs: small CTAs balance better
+        if (ngroups < 2LL * sms) nw = 16;           // few CTAs: spread the points over more warps
+    }
+    nw = std::max(1, std::min(nw, std::min(16, p->tiles[l].ntiles)));
+    size_t sm = smem_bytes(p, 1 << l, nw);
+    if (sm > kSmemMax)
+        return fail(LCF_ERR_ARG, "filter bank needs %zu bytes of shared memory (> %zu): too many transmission samples", sm,
+                    kSmemMax);
+    *l_out = l;
+    *nw_out = nw;
+    *smem_out = sm;
+    return 0;
+}
+
+int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long long *launches) {
+    MoveDev mv = mv_in;
+    if (mv.Ns <= 0) return 0;
+    int l, nw;
+    size_t smem;
+    int rc = choose_shape(p, mv.Ns, &l, &nw, &smem);
+    if (rc) return rc;
+    mv.wpb_log2 = l;
+    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
+    if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ngroups = (mv.Ns + (1 << l) - 1) / (1 << l);
+    long long grid = std::min<long long>(ngroups, 1LL << 30);
+    k<<<(unsigned)grid, nw * 32, smem, stream>>>(p->dev, p->tiles[l], mv);
+    CUDA_TRY(cudaGetLastError());
+    if (launches) ++*launches;
+    return 0;
+}
+
+int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(LCF_ERR_CUDA, "no CUDA device available (%s); liblcf_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+template <typename R>
+int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale) {
+    const int F = d->nfilters, N = d->npoints;
+    const int ns = d->bank_offsets[F];
+    const int ns_pad = (ns + 1) & ~1;                        // TMA bulk copies move multiples of 16 bytes
+    typedef typename Vec2<R>::type R2;
+    const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
+    std::vector<R2> bank(ns_pad);
+    std::vector<R> kap(ns_pad, (R)0), famin(F);
+    for (int k = 0; k < ns_pad; ++k) {
+        if (k < ns) {
+            bank[k].x = (R)(d->bank_alpha[k] * kLog2e);
+            bank[k].y = (R)(d->bank_w[k] * wfac);
+            if (d->bank_kappa) kap[k] = (R)(d->bank_kappa[k] * 0.4 * 3.3219280948873623479);   // 0.4*log2(10)
+        } else {
+            bank[k].x = (R)1;
+            bank[k].y = (R)0;
+        }
+    }
+    for (int f = 0; f < F; ++f) {
+        double m = INFINITY;
+        for (int k = d->bank_offsets[f]; k < d->bank_offsets[f + 1]; ++k) m = std::min(m, d->bank_alpha[k] * kLog2e);
+        famin[f] = (R)m;
+    }
+    std::vector<R> y(N), e1(N), e2(N);
+    for (int i = 0; i < N; ++i) {
+        y[i] = (R)(d->y[i] / scale);
+        if (d->use_sigma) {
+            double dys = d->dy[i] / scale;
+            double su = (d->sigma_type == 0 ? d->dy[i] : d->sigma_unit_abs) / scale;
+            e1[i] = (R)(dys * dys);
+            e2[i] = (R)(su * su);
+        } else {
+            e1[i] = (R)(scale / d->dy[i]);
+            e2[i] = (R)0;
+        }
+    }
+    void *dp;
+    int rc;
+    ProblemDev &P = p->dev;
+    if ((rc = upload(bank, &dp))) return rc;  p->allocs.push_back(dp); P.bank = dp;
+    if ((rc = upload(kap, &dp))) return rc;   p->allocs.push_back(dp); P.kappa = dp;
+    if ((rc = upload(famin, &dp))) return rc; p->allocs.push_back(dp); P.famin = dp;
+    if ((rc = upload(y, &dp))) return rc;     p->allocs.push_back(dp); P.y = dp;
+    if ((rc = upload(e1, &dp))) return rc;    p->allocs.push_back(dp); P.e1 = dp;
+    if ((rc = upload(e2, &dp))) return rc;    p->allocs.push_back(dp); P.e2 = dp;
+    P.nsamples = ns_pad;
+    if (d->sifto_coef && d->sifto_nknots >= 2) {
+        const int nint = d->sifto_nknots - 1;
+        typedef typename Vec4<R>::type R4;
+        std::vector<R4> spl((size_t)F * nint);
+        for (size_t i = 0; i < spl.size(); ++i) {
+            spl[i].x = (R)(d->sifto_coef[4 * i + 0] / scale);
+            spl[i].y = (R)(d->sifto_coef[4 * i + 1] / scale);
+            spl[i].z = (R)(d->sifto_coef[4 * i + 2] / scale);
+            spl[i].w = (R)(d->sifto_coef[4 * i + 3] / scale);
+        }
+        if ((rc = upload(spl, &dp))) return rc;
+        p->allocs.push_back(dp);
+        P.spl = dp;
+        P.spl_nint = nint;
+        P.spl_x0 = d->sifto_x0;
+        P.spl_dx = d->sifto_dx;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------------------
+extern "C" {
+
+int lcf_abi_version(void) { return LCF_ABI_VERSION; }
+const char *lcf_last_error(void) { return g_err.c_str(); }
+
+int lcf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lcf_set_device(int device) {
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+int lcf_set_tuning(int walkers_per_cta, int warps_per_cta) {
+    if (walkers_per_cta < 0 || walkers_per_cta > 32 || (walkers_per_cta & (walkers_per_cta - 1)))
+        return fail(LCF_ERR_ARG, "walkers_per_cta must be 0 or a power of two <= 32");
+    if (warps_per_cta < 0 || warps_per_cta > 16) return fail(LCF_ERR_ARG, "warps_per_cta must be in [0, 16]");
+    g_tune_wpb = walkers_per_cta;
+    g_tune_nw = warps_per_cta;
+    return 0;
+}
+
+int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
+    if (!d || !out) return fail(LCF_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int nm = model_nparams(d->model_id);
+    if (nm < 0) return fail(LCF_ERR_ARG, "unknown model id %d", d->model_id);
+    if (d->precision != LCF_PRECISION_FP64 && d->precision != LCF_PRECISION_FP32) return fail(LCF_ERR_ARG, "bad precision");
+    if (d->ndim != nm + (d->use_sigma ? 1 : 0))
+        return fail(LCF_ERR_ARG, "ndim = %d but model %d takes %d parameters%s", d->ndim, d->model_id, nm,
+                    d->use_sigma ? " + sigma" : "");
+    if (d->ndim > LCF_MAX_NDIM) return fail(LCF_ERR_ARG, "ndim too large");
+    if (d->sigma_type != 0 && d->sigma_type != 1)
+        return fail(LCF_ERR_ARG, "sigma_type must either be \"relative\" or \"absolute\"");   // models.py:126
+    if (d->npoints <= 0 || d->nfilters <= 0) return fail(LCF_ERR_ARG, "empty light curve or filter bank");
+    if (!d->bank_offsets || !d->bank_alpha || !d->bank_w || !d->t || !d->point_filter || !d->y || !d->dy || !d->prior_kind ||
+        !d->prior_min || !d->prior_max)
+        return fail(LCF_ERR_ARG, "null array in problem description");
+    if (d->model_id == LCF_MODEL_SHOCKCOOLING3 && !d->bank_kappa) return fail(LCF_ERR_ARG, "ShockCooling3 needs bank_kappa");
+    if (d->model_id >= 5 && d->model_id <= 7 && (!d->sifto_coef || !d->filter_role || d->sifto_nknots < 2))
+        return fail(LCF_ERR_ARG, "CompanionShocking models need the SiFTO spline table and filter roles");
+    if (d->bank_offsets[0] != 0) return fail(LCF_ERR_ARG, "bank_offsets[0] must be 0");
+    for (int f = 0; f < d->nfilters; ++f)
+        if (d->bank_offsets[f + 1] < d->bank_offsets[f] + 2) return fail(LCF_ERR_ARG, "filter %d has fewer than 2 samples", f);
+    for (int i = 0; i < d->npoints; ++i) {
+        if (d->point_filter[i] < 0 || d->point_filter[i] >= d->nfilters) return fail(LCF_ERR_ARG, "point_filter out of range");
+        if (i && d->point_filter[i] < d->point_filter[i - 1]) return fail(LCF_ERR_ARG, "points must be grouped by filter");
+    }
+    int rc = check_device();
+    if (rc) return rc;
+
+    lcf_problem *p = new lcf_problem();
+    cudaGetDevice(&p->device);
+    p->precision = d->precision;
+    ProblemDev &P = p->dev;
+    memset(&P, 0, sizeof(P));
+    P.model = d->model_id;
+    P.ndim = d->ndim;
+    P.nmodel = nm;
+    P.use_sigma = d->use_sigma ? 1 : 0;
+    P.npoints = d->npoints;
+    P.nfilters = d->nfilters;
+    P.kB = consts().kB;
+    P.c3sq = consts().c3 * consts().c3;
+    for (int i = 0; i < 16; ++i) P.mc[i] = d->model_consts[i];
+    for (int i = 0; i < d->ndim; ++i) {
+        P.prior.kind[i] = d->prior_kind[i];
+        P.prior.pmin[i] = d->prior_min[i];
+        P.prior.pmax[i] = d->prior_max[i];
+        P.prior.mean[i] = d->prior_mean ? d->prior_mean[i] : 0.;
+        P.prior.std[i] = d->prior_std ? d->prior_std[i] : 1.;
+    }
+    // FP32 unit scale: the median uncertainty, so residuals, sigmas and model values are O(1..1e3)
+    double scale = 1.;
+    if (d->precision == LCF_PRECISION_FP32) {
+        std::vector<double> v;
+        for (int i = 0; i < d->npoints; ++i)
+            if (std::isfinite(d->dy[i]) && d->dy[i] > 0.) v.push_back(d->dy[i]);
+        if (!v.empty()) {
+            std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+            scale = v[v.size() / 2];
+        }
+    }
+    P.scale = scale;
+    double ct = 0.;
+    if (d->use_sigma) {
+        ct = d->npoints * (std::log(2. * M_PI) + 2. * std::log(scale));
+    } else {
+        for (int i = 0; i < d->npoints; ++i) ct += std::log(2. * M_PI * (d->dy[i] * d->dy[i]));   // models.py:135
+    }
+    P.const_term = ct;
+    p->h_point_filter.assign(d->point_filter, d->point_filter + d->npoints);
+
+    void *dp;
+    std::vector<int> foff(d->bank_offsets, d->bank_offsets + d->nfilters + 1);
+    std::vector<int> role(d->nfilters, 0);
+    if (d->filter_role) role.assign(d->filter_role, d->filter_role + d->nfilters);
+    std::vector<double> t(d->t, d->t + d->npoints);
+    if ((rc = upload(foff, &dp))) { delete p; return rc; }
+    p->allocs.push_back(dp); P.foff = reinterpret_cast<const int *>(dp);
+    if ((rc = upload(role, &dp))) { delete p; return rc; }
+    p->allocs.push_back(dp); P.frole = reinterpret_cast<const int *>(dp);
+    if ((rc = upload(t, &dp))) { delete p; return rc; }
+    p->allocs.push_back(dp); P.t = reinterpret_cast<const double *>(dp);
+    rc = (d->precision == LCF_PRECISION_FP32) ? build_problem_arrays<float>(d, p, scale) : build_problem_arrays<double>(d, p, scale);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+void lcf_problem_destroy(lcf_problem *p) { delete p; }
+
+static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, const double *params, double *out, size_t out_per_set,
+                       long long *nan_count) {
+    if (!p || !params || !out) return fail(LCF_ERR_ARG, "null argument");
+    if (nsets <= 0) return 0;
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(p->device));
+    double *d_q = nullptr, *d_out = nullptr;
+    int *d_nan = nullptr;
+    CUDA_TRY(cudaMalloc(&d_q, sizeof(double) * nsets * ncols));
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * nsets * out_per_set));
+    CUDA_TRY(cudaMalloc(&d_nan, sizeof(int)));
+    CUDA_TRY(cudaMemcpy(d_q, params, sizeof(double) * nsets * ncols, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(d_nan, 0, sizeof(int)));
+    if (mode == MODE_MODEL) CUDA_TRY(cudaMemset(d_out, 0, sizeof(double) * nsets * out_per_set));
+    MoveDev mv;
+    memset(&mv, 0, sizeof(mv));
+    mv.mode = mode;
+    mv.Ns = nsets;
+    mv.qin = d_q;
+    mv.out = d_out;
+    mv.nanflag = d_nan;
+    rc = launch_pass(p, mv, 0, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(LCF_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) {
+        cudaMemcpy(out, d_out, sizeof(double) * nsets * out_per_set, cudaMemcpyDeviceToHost);
+        int h_nan = 0;
+        cudaMemcpy(&h_nan, d_nan, sizeof(int), cudaMemcpyDeviceToHost);
+        if (nan_count) *nan_count = h_nan;
+    }
+    cudaFree(d_q); cudaFree(d_out); cudaFree(d_nan);
+    return rc;
+}
+
+int lcf_model_eval(lcf_problem *p, int64_t nsets, const double *params, double *out) {
+    if (!p) return fail(LCF_ERR_ARG, "null problem");
+    return eval_common(p, MODE_MODEL, nsets, p->dev.nmodel, params, out, (size_t)p->dev.npoints, nullptr);
+}
+int lcf_log_likelihood(lcf_problem *p, int64_t nsets, const double *params, double *out) {
+    if (!p) return fail(LCF_ERR_ARG, "null problem");
+    return eval_common(p, MODE_LOGLIKE, nsets, p->dev.ndim, params, out, 1, nullptr);
+}
+int lcf_log_posterior(lcf_problem *p, int64_t nsets, const double *params, double *out, int64_t *nan_count) {
+    if (!p) return fail(LCF_ERR_ARG, "null problem");
+    long long nc = 0;
+    int rc = eval_common(p, MODE_LOGPOST, nsets, p->dev.ndim, params, out, 1, &nc);
+    if (nan_count) *nan_count = nc;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// ensemble
+// ---------------------------------------------------------------------------------------
+int lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int rank, int world, lcf_ensemble **out) {
+    if (!p || !out) return fail(LCF_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (nwalkers < 2) return fail(LCF_ERR_ARG, "need at least 2 walkers");
+    if (nwalkers < 2LL * p->dev.ndim)
+        return fail(LCF_ERR_NWALKERS, "It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.");
+    if (world < 1 || rank < 0 || rank >= world) return fail(LCF_ERR_ARG, "bad rank/world");
+    if (nwalkers >= (1LL << 31)) return fail(LCF_ERR_ARG, "too many walkers");
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(p->device));
+    lcf_ensemble *e = new lcf_ensemble();
+    e->p = p;
+    e->W = nwalkers;
+    e->D = p->dev.ndim;
+    e->n0 = (nwalkers + 1) / 2;
+    e->n1 = nwalkers - e->n0;
+    e->rank = rank;
+    e->world = world;
+    e->seed = seed;
+    for (int h = 0; h < 2; ++h) {           // contiguous slice of each colour block
+        long long n = h ? e->n1 : e->n0;
+        long long per = (n + world - 1) / world;
+        long long b = std::min(n, per * rank), en = std::min(n, per * (rank + 1));
+        e->own_begin[h] = b;
+        e->own_count[h] = en - b;
+    }
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&e->d_coords, sizeof(double) * e->W * e->D)) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_logp, sizeof(double) * e->W)) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_acc, sizeof(unsigned long long) * e->W)) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_nan, sizeof(int))) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess) {
+        delete e;
+        return fail(LCF_ERR_CUDA, "ensemble allocation failed: %s", cudaGetErrorString(ce));
+    }
+    cudaMemset(e->d_acc, 0, sizeof(unsigned long long) * e->W);
+    cudaMemset(e->d_nan, 0, sizeof(int));
+    *out = e;
+    return 0;
+}
+
+void lcf_ensemble_destroy(lcf_ensemble *e) { delete e; }
+
+static inline long long phys_row(const lcf_ensemble *e, long long j) { return (j & 1) ? e->n0 + (j >> 1) : (j >> 1); }
+
+static int check_nan(lcf_ensemble *e) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, e->d_nan, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (h) {
+        cudaMemsetAsync(e->d_nan, 0, sizeof(int), e->stream);
+        return fail(LCF_ERR_NAN, "Probability function returned NaN");
+    }
+    return 0;
+}
+
+int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *log_prob) {
+    if (!e || !coords) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    const int D = e->D;
+    std::vector<double> hc((size_t)e->W * D), hl(e->W);
+    for (long long j = 0; j < e->W; ++j) {
+        long long r = phys_row(e, j);
+        for (int d = 0; d < D; ++d) {
+            double v = coords[j * D + d];
+            if (std::isinf(v)) return fail(LCF_ERR_ARG, "At least one parameter value was infinite");   // emcee check
+            if (std::isnan(v)) return fail(LCF_ERR_ARG, "At least one parameter value was NaN");
+            hc[r * D + d] = v;
+        }
+        if (log_prob) hl[r] = log_prob[j];
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->d_coords, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, e->stream));
+    if (log_prob) {
+        CUDA_TRY(cudaMemcpyAsync(e->d_logp, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    } else {
+        MoveDev mv;
+        memset(&mv, 0, sizeof(mv));
+        mv.mode = MODE_LOGPOST;
+        mv.Ns = e->W;
+        mv.qin = e->d_coords;
+        mv.out = e->d_logp;
+        mv.nanflag = e->d_nan;
+        int rc = launch_pass(e->p, mv, e->stream, nullptr);
+        if (rc) return rc;
+        rc = check_nan(e);
+        if (rc) return rc;
+    }
+    e->has_state = true;
+    return 0;
+}
+
+int lcf_ensemble_get_state(lcf_ensemble *e, double *coords, double *log_prob) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (!e->has_state) return fail(LCF_ERR_STATE, "ensemble has no state");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    const int D = e->D;
+    std::vector<double> hc((size_t)e->W * D), hl(e->W);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(hc.data(), e->d_coords, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hl.data(), e->d_logp, sizeof(double) * hl.size(), cudaMemcpyDeviceToHost));
+    for (long long j = 0; j < e->W; ++j) {
+        long long r = phys_row(e, j);
+        if (coords) for (int d = 0; d < D; ++d) coords[j * D + d] = hc[r * D + d];
+        if (log_prob) log_prob[j] = hl[r];
+    }
+    return 0;
+}
+
+int lcf_ensemble_reset(lcf_ensemble *e) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    e->nstored = 0;
+    CUDA_TRY(cudaMemsetAsync(e->d_acc, 0, sizeof(unsigned long long) * e->W, e->stream));
+    return 0;
+}
+
+static int ensure_capacity(lcf_ensemble *e, long long need) {
+    if (need <= e->cap) return 0;
+    long long ncap = std::max(need, e->cap * 2);
+    double *nc = nullptr, *nl = nullptr;
+    CUDA_TRY(cudaMalloc(&nc, sizeof(double) * ncap * e->W * e->D));
+    CUDA_TRY(cudaMalloc(&nl, sizeof(double) * ncap * e->W));
+    if (e->nstored) {
+        CUDA_TRY(cudaMemcpyAsync(nc, e->d_chain, sizeof(double) * e->nstored * e->W * e->D, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(nl, e->d_lnp, sizeof(double) * e->nstored * e->W, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(e->d_chain);
+    cudaFree(e->d_lnp);
+    e->d_chain = nc;
+    e->d_lnp = nl;
+    e->cap = ncap;
+    return 0;
+}
+
+static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
+    memset(&mv, 0, sizeof(mv));
+    mv.coords = e->d_coords;
+    mv.logp = e->d_logp;
+    mv.accepted = e->d_acc;
+    mv.nanflag = e->d_nan;
+    mv.W = e->W;
+    mv.n0 = e->n0;
+    mv.mode = MODE_MOVE;
+    mv.Ns = e->own_count[half];
+    mv.act_base = (half ? e->n0 : 0) + e->own_begin[half];
+    mv.Nc = half ? e->n0 : e->n1;
+    mv.comp_base = half ? 0 : e->n0;
+    mv.seed = e->seed;
+    mv.ctr = (unsigned int)(2 * e->iteration + half);
+    if (store) {
+        mv.chain_step = e->d_chain + e->nstored * e->W * e->D;
+        mv.lnp_step = e->d_lnp + e->nstored * e->W;
+    }
+}
+
+int lcf_ensemble_half_step(lcf_ensemble *e, int half, int store) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
+    if (half != 0 && half != 1) return fail(LCF_ERR_ARG, "half must be 0 or 1");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    if (store) {
+        int rc = ensure_capacity(e, e->nstored + 1);
+        if (rc) return rc;
+    }
+    MoveDev mv;
+    fill_move(e, half, store, mv);
+    return launch_pass(e->p, mv, e->stream, &e->last_launches);
+}
+
+int lcf_ensemble_end_step(lcf_ensemble *e, int store) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    e->iteration += 1;
+    if (store) e->nstored += 1;
+    return 0;
+}
+
+int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    if (store) {
+        int rc = ensure_capacity(e, e->nstored + nsteps);
+        if (rc) return rc;
+    }
+    e->last_launches = 0;
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    for (long long s = 0; s < nsteps; ++s) {
+        for (int half = 0; half < 2; ++half) {
+            MoveDev mv;
+            fill_move(e, half, store, mv);
+            int rc = launch_pass(e->p, mv, e->stream, &e->last_launches);
+            if (rc) return rc;
+        }
+        e->iteration += 1;
+        if (store) e->nstored += 1;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->last_ms = ms;
+    return check_nan(e);
+}
+
+int lcf_ensemble_run_replay(lcf_ensemble *e, int64_t nsteps, int store, const int32_t *split, const double *z,
+                            const int32_t *partner, const double *logu) {
+    if (!e || !split || !z || !partner || !logu) return fail(LCF_ERR_ARG, "null argument");
+    if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
+    if (e->world != 1) return fail(LCF_ERR_ARG, "replay mode is single-GPU");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    const long long W = e->W;
+    if (store) {
+        int rc = ensure_capacity(e, e->nstored + nsteps);
+        if (rc) return rc;
+    }
+    // physical rows of the split-0 walkers (ascending walker index) then of the split-1 walkers, per step
+    std::vector<int> rows((size_t)nsteps * W), ns0(nsteps);
+    for (long long s = 0; s < nsteps; ++s) {
+        long long k = 0;
+        for (int sp = 0; sp < 2; ++sp) {
+            for (long long j = 0; j < W; ++j) {
+                int v = split[s * W + j];
+                if (v != 0 && v != 1) return fail(LCF_ERR_ARG, "split labels must be 0 or 1");
+                if (v == sp) rows[s * W + k++] = (int)phys_row(e, j);
+            }
+            if (sp == 0) ns0[s] = (int)k;
+        }
+        if (ns0[s] == 0 || ns0[s] == W) return fail(LCF_ERR_ARG, "degenerate split");
+    }
+    int *d_rows = nullptr, *d_part = nullptr;
+    double *d_z = nullptr, *d_lu = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rows, sizeof(int) * nsteps * W));
+    CUDA_TRY(cudaMalloc(&d_part, sizeof(int) * nsteps * W));
+    CUDA_TRY(cudaMalloc(&d_z, sizeof(double) * nsteps * W));
+    CUDA_TRY(cudaMalloc(&d_lu, sizeof(double) * nsteps * W));
+    CUDA_TRY(cudaMemcpy(d_rows, rows.data(), sizeof(int) * nsteps * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_part, partner, sizeof(int) * nsteps * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_z, z, sizeof(double) * nsteps * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_lu, logu, sizeof(double) * nsteps * W, cudaMemcpyHostToDevice));
+    e->last_launches = 0;
+    int rc = 0;
+    cudaEventRecord(e->ev0, e->stream);
+    for (long long s = 0; s < nsteps && !rc; ++s) {
+        for (int half = 0; half < 2 && !rc; ++half) {
+            MoveDev mv;
+            fill_move(e, half, store, mv);
+            const long long off = s * W + (half ? ns0[s] : 0);
+            mv.Ns = half ? W - ns0[s] : ns0[s];
+            mv.Nc = W - mv.Ns;
+            mv.act_rows = d_rows + off;
+            mv.comp_rows = d_rows + s * W + (half ? 0 : ns0[s]);
+            mv.zin = d_z + off;
+            mv.rin = d_part + off;
+            mv.luin = d_lu + off;
+            rc = launch_pass(e->p, mv, e->stream, &e->last_launches);
+        }
+        e->iteration += 1;
+        if (store) e->nstored += 1;
+    }
+    cudaEventRecord(e->ev1, e->stream);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->last_ms = ms;
+    cudaFree(d_rows); cudaFree(d_part); cudaFree(d_z); cudaFree(d_lu);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(LCF_ERR_CUDA, "replay failed: %s", cudaGetErrorString(ce));
+    return check_nan(e);
+}
+
+int64_t lcf_ensemble_nstored(lcf_ensemble *e) { return e ? e->nstored : 0; }
+
+int lcf_ensemble_get_chain(lcf_ensemble *e, double *chain) {
+    if (!e || !chain) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->nstored) CUDA_TRY(cudaMemcpy(chain, e->d_chain, sizeof(double) * e->nstored * e->W * e->D, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob) {
+    if (!e || !log_prob) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->nstored) CUDA_TRY(cudaMemcpy(log_prob, e->d_lnp, sizeof(double) * e->nstored * e->W, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted) {
+    if (!e || !accepted) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(accepted, e->d_acc, sizeof(unsigned long long) * e->W, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream, int64_t *n0, int64_t *own_begin,
+                             int64_t *own_count) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (d_coords) *d_coords = e->d_coords;
+    if (d_log_prob) *d_log_prob = e->d_logp;
+    if (stream) *stream = e->stream;
+    if (n0) *n0 = e->n0;
+    if (own_begin) { own_begin[0] = e->own_begin[0]; own_begin[1] = e->own_begin[1]; }
+    if (own_count) { own_count[0] = e->own_count[0]; own_count[1] = e->own_count[1]; }
+    return 0;
+}
+int lcf_ensemble_sync(lcf_ensemble *e) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return check_nan(e);
+}
+int lcf_ensemble_last_timing(lcf_ensemble *e, double *ms, int64_t *launches) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (ms) *ms = e->last_ms;
+    if (launches) *launches = e->last_launches;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// batch
+// ---------------------------------------------------------------------------------------
+int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nwalkers, uint64_t seed, lcf_batch **out) {
+    if (!problems || !out || nproblems <= 0) return fail(LCF_ERR_ARG, "bad argument");
+    *out = nullptr;
+    lcf_problem *p0 = problems[0];
+    if (!p0) return fail(LCF_ERR_ARG, "null problem");
+    for (long long i = 0; i < nproblems; ++i) {
+        lcf_problem *p = problems[i];
+        if (!p) return fail(LCF_ERR_ARG, "null problem");
+        if (p->dev.model != p0->dev.model || p->precision != p0->precision || p->dev.ndim != p0->dev.ndim ||
+            p->dev.use_sigma != p0->dev.use_sigma || p->device != p0->device)
+            return fail(LCF_ERR_ARG, "all problems of a batch must share model, precision, ndim, use_sigma and device");
+    }
+    if (nwalkers < 2LL * p0->dev.ndim)
+        return fail(LCF_ERR_NWALKERS, "It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.");
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(p0->device));
+    lcf_batch *b = new lcf_batch();
+    b->probs.assign(problems, problems + nproblems);
+    b->nprob = nproblems;
+    b->W = nwalkers;
+    b->n0 = (nwalkers + 1) / 2;
+    b->D = p0->dev.ndim;
+    b->model = p0->dev.model;
+    b->precision = p0->precision;
+    b->seed = seed;
+    // shape: walkers per CTA pass = smallest power of two covering a half-ensemble (<= 32)
+    int l = 0;
+    if (g_tune_wpb > 0) { while ((1 << l) < g_tune_wpb && l < 5) ++l; }
+    else { while ((1 << l) < b->n0 && l < 5) ++l; }
+    size_t smem = 0;
+    int max_tiles = 1;
+    for (;;) {
+        smem = 0;
+        for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 16));
+        if (smem <= kSmemMax / 2 || l == 0) break;
+        --l;
+    }
+    std::vector<ProblemDev> hp(nproblems);
+    std::vector<TileDev> ht(nproblems);
+    for (long long i = 0; i < nproblems; ++i) {
+        if ((rc = build_tiles(b->probs[i], l))) { delete b; return rc; }
+        hp[i] = b->probs[i]->dev;
+        ht[i] = b->probs[i]->tiles[l];
+        max_tiles = std::max(max_tiles, ht[i].ntiles);
+    }
+    int nw = g_tune_nw > 0 ? g_tune_nw : std::min(8, max_tiles);
+    nw = std::max(1, std::min(nw, 16));
+    smem = 0;
+    for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw));
+    if (smem > kSmemMax) { delete b; return fail(LCF_ERR_ARG, "filter bank does not fit in shared memory"); }
+    b->wpb_log2 = l;
+    b->nw = nw;
+    b->smem = smem;
+    void *dp;
+    if ((rc = upload(hp, &dp))) { delete b; return rc; }
+    b->d_probs = reinterpret_cast<ProblemDev *>(dp);
+    if ((rc = upload(ht, &dp))) { delete b; return rc; }
+    b->d_tiles = reinterpret_cast<TileDev *>(dp);
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&b->d_coords, sizeof(double) * nproblems * b->W * b->D)) != cudaSuccess ||
+        (ce = cudaMalloc(&b->d_logp, sizeof(double) * nproblems * b->W)) != cudaSuccess ||
+        (ce = cudaMalloc(&b->d_acc, sizeof(unsigned long long) * nproblems * b->W)) != cudaSuccess ||
+        (ce = cudaMalloc(&b->d_status, sizeof(int) * nproblems)) != cudaSuccess ||
+        (ce = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (ce = cudaEventCreate(&b->ev0)) != cudaSuccess || (ce = cudaEventCreate(&b->ev1)) != cudaSuccess) {
+        delete b;
+        return fail(LCF_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(ce));
+    }
+    cudaMemset(b->d_acc, 0, sizeof(unsigned long long) * nproblems * b->W);
+    cudaMemset(b->d_status, 0, sizeof(int) * nproblems);
+    *out = b;
+    return 0;
+}
+
+void lcf_batch_destroy(lcf_batch *b) { delete b; }
+
+int lcf_batch_set_state(lcf_batch *b, const double *coords) {
+    if (!b || !coords) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    const int D = b->D;
+    const long long W = b->W;
+    std::vector<double> hc((size_t)b->nprob * W * D);
+    for (long long p = 0; p < b->nprob; ++p)
+        for (long long j = 0; j < W; ++j) {
+            long long r = (j & 1) ? b->n0 + (j >> 1) : (j >> 1);
+            for (int d = 0; d < D; ++d) hc[(p * W + r) * D + d] = coords[(p * W + j) * D + d];
+        }
+    CUDA_TRY(cudaMemcpy(b->d_coords, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice));
+    b->has_state = true;
+    b->need_init_logp = true;
+    return 0;
+}
+
+int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
+    if (!b) return fail(LCF_ERR_ARG, "null argument");
+    if (!b->has_state) return fail(LCF_ERR_STATE, "batch has no initial state");
+    if (nburn < 0 || nsteps < 0) return fail(LCF_ERR_ARG, "negative step count");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    cudaFree(b->d_chain); cudaFree(b->d_lnp);
+    b->d_chain = nullptr; b->d_lnp = nullptr;
+    CUDA_TRY(cudaMalloc(&b->d_chain, std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W * b->D)));
+    CUDA_TRY(cudaMalloc(&b->d_lnp, std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W)));
+    CUDA_TRY(cudaMemsetAsync(b->d_acc, 0, sizeof(unsigned long long) * b->nprob * b->W, b->stream));
+    BatchDev B;
+    memset(&B, 0, sizeof(B));
+    B.probs = b->d_probs; B.tiles = b->d_tiles;
+    B.coords = b->d_coords; B.logp = b->d_logp; B.accepted = b->d_acc; B.status = b->d_status;
+    B.chain = b->d_chain; B.lnp = b->d_lnp;
+    B.W = b->W; B.n0 = b->n0; B.nproblems = b->nprob;
+    B.nburn = nburn; B.nsteps = nsteps; B.iter0 = b->iteration;
+    B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.init_logp = b->need_init_logp ? 1 : 0;
+    ChainKernel k = (b->precision == LCF_PRECISION_FP32) ? chain_kernel_for<float>(b->model) : chain_kernel_for<double>(b->model);
+    if (!k) return fail(LCF_ERR_ARG, "unknown model");
+    if (b->smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    k<<<(unsigned)b->nprob, b->nw * 32, b->smem, b->stream>>>(B);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    b->last_ms = ms;
+    b->last_launches = 1;
+    b->iteration += nburn + nsteps;
+    b->nsteps_stored = nsteps;
+    b->need_init_logp = false;
+    return 0;
+}
+
+int lcf_batch_get_chain(lcf_batch *b, double *chain) {
+    if (!b || !chain) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    if (b->nsteps_stored)
+        CUDA_TRY(cudaMemcpy(chain, b->d_chain, sizeof(double) * b->nprob * b->nsteps_stored * b->W * b->D, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_batch_get_log_prob(lcf_batch *b, double *log_prob) {
+    if (!b || !log_prob) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    if (b->nsteps_stored)
+        CUDA_TRY(cudaMemcpy(log_prob, b->d_lnp, sizeof(double) * b->nprob * b->nsteps_stored * b->W, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_batch_get_accepted(lcf_batch *b, int64_t *accepted) {
+    if (!b || !accepted) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    CUDA_TRY(cudaMemcpy(accepted, b->d_acc, sizeof(unsigned long long) * b->nprob * b->W, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_batch_get_status(lcf_batch *b, int32_t *status) {
+    if (!b || !status) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    std::vector<int> h(b->nprob);
+    CUDA_TRY(cudaMemcpy(h.data(), b->d_status, sizeof(int) * b->nprob, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < b->nprob; ++i) status[i] = h[i] ? LCF_ERR_NAN : 0;
+    return 0;
+}
+int lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches) {
+    if (!b) return fail(LCF_ERR_ARG, "null argument");
+    if (ms) *ms = b->last_ms;
+    if (launches) *launches = b->last_launches;
+    return 0;
+}
+
+}  // extern "C"

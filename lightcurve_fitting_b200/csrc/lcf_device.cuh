@@ -1,0 +1,721 @@
+// lcf_device.cuh -- device code of the fused log-posterior + stretch-move kernels (sm_100a).
+//
+// Work decomposition:
+//   CTA      = one group of WPB walkers of the active half-ensemble (WPB = 2^k <= 32)
+//   lane     = (walker-in-group wl = lane % WPB, point slot = lane / WPB); a lane serves the
+//              SAME walker for the whole kernel, so the per-walker model constants live in
+//              registers and the chi-square partial sums need no atomics
+//   tile     = 32/WPB photometry points that share one filter (points are grouped by filter
+//              on the host), so every lane of a warp walks the same transmission curve and the
+//              shared-memory reads of (alpha_k, w_k) are pure broadcasts
+//   warp     = strides over the tiles of the light curve
+// The packed filter bank is staged into shared memory once per CTA with a 1-D TMA bulk copy
+// (cp.async.bulk + mbarrier).  Inner loop per Planck sample (FP32 mode):
+//   FMUL x=a_k*invT ; MUFU.EX2 ; FADD -1 ; MUFU.RCP ; FFMA acc+=w_k*r
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace lcf {
+
+constexpr int kMaxDim = 12;
+constexpr int kNumWC = 8;  // per-walker model constants held in registers
+
+enum Mode : int { MODE_MOVE = 0, MODE_LOGPOST = 1, MODE_LOGLIKE = 2, MODE_MODEL = 3 };
+
+struct PriorDev {
+    int kind[kMaxDim];
+    double pmin[kMaxDim], pmax[kMaxDim], mean[kMaxDim], std[kMaxDim];
+};
+
+// Device view of one problem.  `real` arrays are float (FP32 mode) or double (FP64 mode).
+struct ProblemDev {
+    int model, ndim, nmodel, use_sigma;
+    int npoints, nfilters, nsamples, spl_nint;
+    const void *bank;      // real2[nsamples]: (alpha*log2(e), w/scale)
+    const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
+    const void *famin;     // real[nfilters]: min_k bank.x                    (FP32 slow-path guard)
+    const int *foff;       // [nfilters+1]
+    const int *frole;      // [nfilters]
+    const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
+    const double *t;       // [npoints]
+    const void *y;         // real[npoints]  y/scale
+    const void *e1;        // real[npoints]  use_sigma ? (dy/scale)^2 : scale/dy
+    const void *e2;        // real[npoints]  (sigma_units/scale)^2            (use_sigma only)
+    double spl_x0, spl_dx;
+    double const_term;     // sum_i log(2 pi dy_i^2)  or  N*(log 2 pi + 2 log scale)
+    double scale;          // FP32 unit scale (1 in FP64 mode)
+    double kB, c3sq;       // models.py:10-11 constants (host computed)
+    double mc[16];         // model constants
+    PriorDev prior;
+};
+
+struct TileDev {           // one tile table per WPB
+    const int4 *tiles;     // (first point, count, filter, 0)
+    int ntiles;
+};
+
+struct MoveDev {
+    double *coords;                  // [W][D] colour-major rows
+    double *logp;                    // [W]
+    unsigned long long *accepted;    // [W] indexed by logical walker
+    int *nanflag;
+    long long W, n0;                 // n0 = rows of colour 0
+    int mode, wpb_log2;
+    // active set: physical row = act_rows ? act_rows[i] : act_base + i,  i in [0, Ns)
+    long long Ns, act_base;
+    const int *act_rows;
+    long long Nc, comp_base;
+    const int *comp_rows;
+    // injected draws (replay mode), indexed by i; NULL -> Philox
+    const double *zin;
+    const int *rin;
+    const double *luin;
+    unsigned long long seed;
+    unsigned int ctr;                // 2*iteration + half
+    // evaluation modes
+    const double *qin;               // [Ns][D]  (nmodel columns in MODE_MODEL)
+    double *out;                     // [Ns] or [Ns][npoints]
+    // chain write-back for this iteration (NULL = not stored), logical walker order
+    double *chain_step;              // [W][D]
+    double *lnp_step;                // [W]
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP), MUFU approximations
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+template <typename R> struct Mth;
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static __device__ __forceinline__ float lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static __device__ __forceinline__ float rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float nan() { return __int_as_float(0x7fffffff); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
+    static __device__ __forceinline__ double lg2(double x) { return log2(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <typename R> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<double> { typedef double2 type; };
+template <typename R> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<double> { typedef double4 type; };
+
+constexpr double kLog2e = 1.4426950408889634074;
+constexpr double kLn2 = 0.69314718055994530942;
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (walker, ctr, 0, 0), key = seed
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// power() of models.py:42-48: zero for any non-positive (or NaN) base
+__device__ __forceinline__ double pw(double b, double e) { return b > 0. ? pow(b, e) : 0.; }
+
+// log-prior of one parameter (models.py:1055-1098): strict bounds, -inf outside
+__device__ __forceinline__ double prior_logp(const PriorDev &pr, int d, double p) {
+    if (!(pr.pmin[d] < p && p < pr.pmax[d])) return -Mth<double>::inf();
+    switch (pr.kind[d]) {
+        case 1: return -log(p);
+        case 2: { double u = (p - pr.mean[d]) / pr.std[d]; return -0.5 * (u * u); }
+        default: return 0.;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-walker constants (FP64, one thread per walker) -- the model front ends
+//   wc[] meaning per model family is documented next to point_model() below
+// ---------------------------------------------------------------------------------------
+struct WalkerSetup {
+    double wc[kNumWC];
+    double t0;     // explosion epoch (t_exp)
+    double t1;     // SiFTO t_peak (CompanionShocking*)
+};
+
+
+template <int MODEL>
+__device__ inline void setup_walker(const ProblemDev &P, const double *p, WalkerSetup &s) {
+    const double *mc = P.mc;
+    for (int i = 0; i < kNumWC; ++i) s.wc[i] = 0.;
+    s.t0 = 0.; s.t1 = 0.;
+    const double c3sq = P.c3sq, k_kB = P.kB;
+    if (MODEL == 1 || MODEL == 3) {
+        // BaseShockCooling.temperature_radius, models.py:260-269 (kappa = 1)
+        // mc: A, a, alpha, eps1, eps2, L_0, T_0, Tph_to_Tcol
+        double v = p[0], Menv = p[1], f = p[2], Rr = p[3];
+        double texp = (MODEL == 3) ? p[6] : p[4];
+        double KT = mc[6] * pw(v * v / f, mc[3]) * pow(Rr, 0.25) * mc[7] / k_kB;
+        double KL = c3sq * mc[5] * pw(v / f, -mc[4]) * v * v * Rr * mc[0];
+        if (MODEL == 3) KL = KL / (p[4] * p[4]);          // flux = c4*lum/dist^2 (c4 folded into the bank)
+        double ttr = 19.5 * pow(Menv / v, 0.5);
+        double base = mc[1] / ttr;                        // (a t / t_tr) > 0  <=>  a/t_tr > 0 for t > 0
+        s.wc[0] = KT; s.wc[1] = KL;
+        s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        if (MODEL == 3) s.wc[3] = p[5];                   // E(B-V)
+        s.t0 = texp;
+    } else if (MODEL == 2) {
+        // ShockCooling2.evaluate, models.py:403-407
+        double base = mc[1] / p[2];
+        s.wc[0] = p[0];
+        s.wc[1] = c3sq * p[1] * 1e42;
+        s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.t0 = p[3];
+    } else if (MODEL == 4) {
+        // ShockCooling4.temperature_radius, models.py:584-587 (kappa = 1)
+        // mc: A, a, alpha, L_br_0, T_col_br_0, t_br_0, t_tr_0
+        double v = p[0], Menv = p[1], f = p[2], Rr = p[3];
+        double t_br = mc[5] * pow(Rr, 1.26) * pow(v, -1.13) * pow(f, -0.13);
+        double L_br = mc[3] * pow(Rr, 0.78) * pow(v, 2.11) * pow(f, 0.11);
+        // models.py:586 as written: v_s ** 0.58 ** f_rho_M ** 0.03 is right-associative
+        double T_br = mc[4] * pow(Rr, -0.32) * pow(v, pow(0.58, pow(f, 0.03)));
+        double t_tr = mc[6] * sqrt(Menv / v);
+        double base = mc[1] / t_tr;
+        s.wc[0] = T_br / k_kB;
+        s.wc[1] = c3sq * L_br;
+        s.wc[2] = (t_br > 0.) ? -log2(t_br) : Mth<double>::nan();   // log2(ttilde) = log2(t) + wc2
+        s.wc[3] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.t0 = p[4];
+    } else if (MODEL == 5 || MODEL == 6 || MODEL == 7) {
+        // BaseCompanionShocking.temperature_radius, models.py:752-754 (kappa = 1)
+        double a13 = p[1];
+        double Mv7 = (MODEL == 7) ? 1. : p[2];
+        double cK = pow(a13, 36.) * Mv7;
+        s.wc[0] = 25. * pw(cK, 1. / 144.);                 // T = wc0 * t^(-74/144)
+        double rk = 2.7 * pw(Mv7, 1. / 9.);
+        s.wc[1] = rk * rk;                                  // R^2 = wc1 * t^(14/9)
+        s.wc[2] = 1.;
+        if (MODEL == 7) {                                   // models.py:1042-1043
+            double th = p[2] * (3.14159265358979323846 / 180.);
+            s.wc[2] = (0.5 * cos(th) + 0.5) * (0.14 * (th * th) - 0.4 * th + 1.);
+        }
+        s.wc[3] = p[4];                                     // stretch
+        if (MODEL == 5) { s.wc[4] = p[5]; s.wc[5] = p[6]; s.wc[6] = p[7]; }   // r_r, r_i, r_U
+        else            { s.wc[4] = p[5]; s.wc[5] = p[6]; }                   // dt_U, dt_i
+        s.t0 = p[0];
+        s.t1 = p[3];
+    } else if (MODEL == 8) {
+        // planck_fast(nu, T, R), models.py:1127-1128
+        s.wc[0] = (p[0] > 0.) ? 1. / p[0] : 0.;             // power(T, -1)
+        s.wc[1] = p[1] * p[1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Planck x transmission sums:  S(invT) = sum_k w_k / (2^(a_k invT) - 1)
+// ---------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R planck_term_safe(R a, R invT) {
+    // power(exp(x) - 1, -1) semantics (models.py:1128): 0 when exp(x)-1 is 0 or inf
+    if (sizeof(R) == 4) {
+        float d = expm1f((float)(a * invT) * (float)kLn2);
+        return (d > 0.f) ? (R)(1.f / d) : (R)0;
+    } else {
+        double d = exp2((double)(a * invT)) - 1.0;
+        return (d > 0.) ? (R)(1.0 / d) : (R)0;
+    }
+}
+
+// one blackbody.  `tab`: optional per-walker weight table (ShockCooling3: w_k * E_k), stride `ts`.
+template <typename R, bool TAB>
+__device__ __forceinline__ R planck_sum(const typename Vec2<R>::type *__restrict__ b, int K, R invT, bool slow,
+                                        const R *__restrict__ tab, int ts) {
+    R acc0 = 0, acc1 = 0;
+    if (sizeof(R) == 4 && !slow) {
+        int k = 0;
+#pragma unroll 4
+        for (; k + 1 < K; k += 2) {
+            typename Vec2<R>::type s0 = b[k], s1 = b[k + 1];
+            R w0 = TAB ? tab[k * ts] : s0.y, w1 = TAB ? tab[(k + 1) * ts] : s1.y;
+            R e0 = Mth<R>::ex2(s0.x * invT), e1 = Mth<R>::ex2(s1.x * invT);
+            acc0 = fma(w0, Mth<R>::rcp(e0 - (R)1), acc0);
+            acc1 = fma(w1, Mth<R>::rcp(e1 - (R)1), acc1);
+        }
+        if (k < K) {
+            typename Vec2<R>::type s0 = b[k];
+            R w0 = TAB ? tab[k * ts] : s0.y;
+            acc0 = fma(w0, Mth<R>::rcp(Mth<R>::ex2(s0.x * invT) - (R)1), acc0);
+        }
+    } else {
+        for (int k = 0; k < K; ++k) {
+            typename Vec2<R>::type s0 = b[k];
+            R w0 = TAB ? tab[k * ts] : s0.y;
+            acc0 = fma(w0, planck_term_safe<R>(s0.x, invT), acc0);
+        }
+    }
+    return acc0 + acc1;
+}
+
+// two blackbodies sharing the curve (ShockCooling4: T and 0.74 T), models.py:629-630
+template <typename R>
+__device__ __forceinline__ void planck_sum2(const typename Vec2<R>::type *__restrict__ b, int K, R invTa, R invTb, bool slow,
+                                            R &Sa, R &Sb) {
+    R a0 = 0, b0 = 0;
+    if (sizeof(R) == 4 && !slow) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            typename Vec2<R>::type s = b[k];
+            R ea = Mth<R>::ex2(s.x * invTa), eb = Mth<R>::ex2(s.x * invTb);
+            a0 = fma(s.y, Mth<R>::rcp(ea - (R)1), a0);
+            b0 = fma(s.y, Mth<R>::rcp(eb - (R)1), b0);
+        }
+    } else {
+        for (int k = 0; k < K; ++k) {
+            typename Vec2<R>::type s = b[k];
+            a0 = fma(s.y, planck_term_safe<R>(s.x, invTa), a0);
+            b0 = fma(s.y, planck_term_safe<R>(s.x, invTb), b0);
+        }
+    }
+    Sa = a0; Sb = b0;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-lane walker state in registers
+// ---------------------------------------------------------------------------------------
+template <typename R> struct LaneWalker {
+    R wc[kNumWC];
+    double t0, t1;
+};
+
+// SiFTO cubic spline (models.py:717, 817-826): NaN outside the knots -> 0
+template <typename R>
+__device__ __forceinline__ R sifto_eval(const ProblemDev &P, int f, R tau) {
+    const R x0 = (R)P.spl_x0, dx = (R)P.spl_dx;
+    const R xn = x0 + dx * (R)P.spl_nint;
+    if (!(tau >= x0 && tau <= xn)) return (R)0;
+    int i = (int)floor((tau - x0) / dx);
+    i = min(max(i, 0), P.spl_nint - 1);
+    R h = tau - (x0 + dx * (R)i);
+    typename Vec4<R>::type c = reinterpret_cast<const typename Vec4<R>::type *>(P.spl)[(size_t)f * P.spl_nint + i];
+    R v = ((c.x * h + c.y) * h + c.z) * h + c.w;
+    return (v != v) ? (R)0 : v;
+}
+
+// Model value at one photometry point for one walker (scaled units).
+//   SW family (1,2,3): wc0 = K_T, wc1 = K_L, wc2 = log2(a/t_tr) | -inf, (3: wc3 = E(B-V))
+//        T = K_T t^eps_T ; L = K_L t^eps_L exp(-(a t/t_tr)^alpha) ; yhat = L/T^4 * S(1/T)
+//   SC4: wc0 = T_col_br/k_B, wc1 = c3^2 L_br, wc2 = -log2(t_br), wc3 = log2(a/t_tr)
+//   CS*: wc0, wc1 Kasen T/R^2 coefficients, wc2 Kasen factor, wc3 stretch, wc4.. r_r,r_i,r_U | dt_U,dt_i
+//   SED: wc0 = 1/T, wc1 = R^2
+template <int MODEL, typename R>
+__device__ __forceinline__ R point_model(const ProblemDev &P, const LaneWalker<R> &w, const typename Vec2<R>::type *bank,
+                                         const int *s_foff, int f, double tp, const R *tab, int ts) {
+    typedef Mth<R> M;
+    const int k0 = s_foff[f], K = s_foff[f + 1] - k0;
+    const typename Vec2<R>::type *b = bank + k0;
+    const R amin = reinterpret_cast<const R *>(P.famin)[f];
+    if (MODEL == 8) {
+        R invT = w.wc[0];
+        if (!(invT > (R)0)) return w.wc[1] * (R)0;
+        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
+        return w.wc[1] * planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
+    }
+    R dt = (R)(tp - w.t0);
+    R yk = (R)0;
+    if (MODEL >= 1 && MODEL <= 3) {
+        if (!(dt > (R)0)) return (w.wc[0] * w.wc[1]) * (R)0;   // t <= t_exp: zero (NaN constants propagate)
+        const R epsT = (R)(2. * P.mc[3] - 0.5), epsL = (R)(-2. * P.mc[4]), alpha = (R)P.mc[2];
+        R lt = M::lg2(dt);
+        R T = w.wc[0] * M::ex2(epsT * lt);
+        R sup = (w.wc[2] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[2]))) : (R)1;
+        R L = w.wc[1] * M::ex2(epsL * lt) * sup;
+        if (L < (R)0) return M::nan();                          // L ** 0.5 (models.py:268)
+        if (!(T > (R)0)) return (T != T) ? M::nan() : L * (R)0;
+        R invT = M::rcp(T);
+        R i2 = invT * invT;
+        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
+        R S = (MODEL == 3) ? planck_sum<R, true>(b, K, invT, slow, tab + (size_t)k0 * ts, ts)
+                           : planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
+        return L * (i2 * i2) * S;
+    }
+    if (MODEL == 4) {
+        if (!(dt > (R)0)) return (w.wc[0] * w.wc[1]) * (R)0;
+        const R A = (R)P.mc[0], alpha = (R)P.mc[2];
+        R l0 = M::lg2(dt);
+        R lt = l0 + w.wc[2];                                    // log2(ttilde); NaN when t_br invalid
+        R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (l0 + w.wc[3]))) : (R)1;
+        R L = w.wc[1] * (M::ex2((R)(-4. / 3.) * lt) + A * sup * M::ex2((R)(-0.17) * lt));
+        R T = w.wc[0] * M::mn((R)0.97 * M::ex2((R)(-1. / 3.) * lt), M::ex2((R)(-0.45) * lt));
+        if (L < (R)0) return M::nan();
+        if (!(T > (R)0)) return (T != T) ? M::nan() : L * (R)0;
+        R invT = M::rcp(T);
+        R i2 = invT * invT;
+        R R2 = L * (i2 * i2);
+        R invTb = invT * (R)(1. / 0.74);
+        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
+        R Sa, Sb;
+        planck_sum2<R>(b, K, invT, invTb, slow, Sa, Sb);
+        // min(B(T,R), B(0.74 T, 0.74^-2 R)), models.py:629-631
+        return M::mn(R2 * Sa, R2 * (R)(1. / (0.74 * 0.74 * 0.74 * 0.74)) * Sb);
+    }
+    // CompanionShocking family
+    const int role = P.frole[f];
+    if (dt > (R)0) {
+        R lt = M::lg2(dt);
+        R T = w.wc[0] * M::ex2((R)(-74. / 144.) * lt);
+        R R2 = w.wc[1] * M::ex2((R)(14. / 9.) * lt);
+        if (T > (R)0) {
+            R invT = M::rcp(T);
+            bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
+            yk = R2 * planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
+        } else if (T != T) {
+            yk = M::nan();
+        }
+    }
+    R tw = (R)(tp - w.t1);                                      // t_wrt_peak, models.py:816
+    R ys;
+    if (MODEL == 5) {
+        ys = sifto_eval<R>(P, f, tw / w.wc[3]);
+        R kf = (role & 1) ? w.wc[6] : (R)1;
+        R sf = (role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1);
+        return yk * kf + ys * sf;                               // models.py:915
+    }
+    R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
+    ys = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
+    return yk * w.wc[2] + ys;                                   // models.py:979, 1044
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory carve-up (dynamic), identical for the half-step and the chain kernels
+// ---------------------------------------------------------------------------------------
+template <typename R> struct SmemLayout {
+    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
+    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
+        size_t o = 0;
+        off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
+        off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;          o = (o + 15) & ~(size_t)15;
+        off_foff = o; o += (size_t)(nfilters + 1) * sizeof(int);                  o = (o + 15) & ~(size_t)15;
+        off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
+        off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
+        off_q = o;    o += (size_t)wpb * ndim * sizeof(double);
+        off_lp = o;   o += (size_t)wpb * sizeof(double);
+        off_z = o;    o += (size_t)wpb * sizeof(double);
+        off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
+        off_flag = o; o += (size_t)wpb * sizeof(int);                             o = (o + 15) & ~(size_t)15;
+        off_bar = o;  o += 16;
+        total = o;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// One half-step (or one evaluation pass) for the walker group `g` of the active set.
+// Called by every thread of the CTA.  `staged` tells whether the bank is already in smem.
+// ---------------------------------------------------------------------------------------
+template <int MODEL, typename R>
+__device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
+                                           unsigned char *smem, const SmemLayout<R> &L, uint32_t bar_parity, bool need_stage) {
+    typedef typename Vec2<R>::type R2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int wpb = 1 << Mv.wpb_log2;
+    const int D = P.ndim;
+    R2 *s_bank = reinterpret_cast<R2 *>(smem + L.off_bank);
+    R *s_tab = reinterpret_cast<R *>(smem + L.off_tab);
+    int *s_foff = reinterpret_cast<int *>(smem + L.off_foff);
+    R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
+    double *s_t = reinterpret_cast<double *>(smem + L.off_t);
+    double *s_q = reinterpret_cast<double *>(smem + L.off_q);
+    double *s_lp = reinterpret_cast<double *>(smem + L.off_lp);
+    double *s_z = reinterpret_cast<double *>(smem + L.off_z);
+    double *s_part = reinterpret_cast<double *>(smem + L.off_part);
+    int *s_flag = reinterpret_cast<int *>(smem + L.off_flag);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+
+    // ---- phase 0: stage the packed filter bank with one TMA bulk copy -------------------
+    if (need_stage) {
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)((size_t)P.nsamples * sizeof(R2));
+            mbar_expect_tx(s_bar, bytes);
+            tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
+        }
+        for (int i = tid; i <= P.nfilters; i += blockDim.x) s_foff[i] = P.foff[i];
+    }
+
+    // ---- phase 1: proposal + prior + model front end, one thread per walker -------------
+    if (tid < wpb) {
+        const long long i = g * wpb + tid;
+        int flag = 1;                                    // 1 = skip likelihood
+        double lp = 0.;
+        if (i < Mv.Ns) {
+            double q[kMaxDim];
+            if (Mv.mode == MODE_MOVE) {
+                const long long row = Mv.act_rows ? (long long)Mv.act_rows[i] : Mv.act_base + i;
+                const long long j = (row < Mv.n0) ? 2 * row : 2 * (row - Mv.n0) + 1;   // logical walker
+                double z;
+                long long pr;
+                if (Mv.zin) {
+                    z = Mv.zin[i];
+                    pr = Mv.rin[i];
+                } else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)j, Mv.ctr, (uint32_t)(j >> 32), 0u, (uint32_t)Mv.seed, (uint32_t)(Mv.seed >> 32), r);
+                    double u = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
+                    double a = u + 1.;                   // ((a-1) u + 1)^2 / a with a = 2
+                    z = a * a * 0.5;
+                    pr = (long long)(((unsigned long long)r[2] * (unsigned long long)Mv.Nc) >> 32);
+                }
+                const long long crow = Mv.comp_rows ? (long long)Mv.comp_rows[pr] : Mv.comp_base + pr;
+                const double *s = Mv.coords + row * D, *c = Mv.coords + crow * D;
+                for (int d = 0; d < D; ++d)              // q = c - (c - s) z, numpy op order, no FMA
+                    q[d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), z));
+                s_z[tid] = z;                            // kept for the accept test
+            } else {
+                const int nq = (Mv.mode == MODE_MODEL) ? P.nmodel : D;
+                for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * nq + d];
+                for (int d = nq; d < D; ++d) q[d] = 0.;
+            }
+            for (int d = 0; d < D; ++d) s_q[tid * D + d] = q[d];
+            if (Mv.mode == MODE_MOVE || Mv.mode == MODE_LOGPOST)
+                for (int d = 0; d < D; ++d) lp += prior_logp(P.prior, d, q[d]);
+            if (!isinf(lp)) {                            // fitting.py:125: prior -inf skips the likelihood
+                flag = 0;
+                WalkerSetup ws;
+                setup_walker<MODEL>(P, q, ws);
+                if (P.use_sigma) ws.wc[7] = q[D - 1] * q[D - 1];
+                for (int k = 0; k < kNumWC; ++k) s_wc[tid * kNumWC + k] = (R)ws.wc[k];
+                s_t[tid * 2] = ws.t0;
+                s_t[tid * 2 + 1] = ws.t1;
+            }
+        }
+        s_lp[tid] = lp;
+        s_flag[tid] = flag;
+    }
+    __syncthreads();
+    if (need_stage) mbar_wait(s_bar, bar_parity);
+
+    // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33)
+    if (MODEL == 3) {
+        const R *kap = reinterpret_cast<const R *>(P.kappa);
+        const int n = P.nsamples * wpb;
+        for (int idx = tid; idx < n; idx += blockDim.x) {
+            int k = idx >> Mv.wpb_log2, wl = idx & (wpb - 1);
+            R ebv = s_wc[wl * kNumWC + 3];
+            s_tab[idx] = s_bank[k].y * Mth<R>::ex2(-ebv * kap[k]);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: tiles ------------------------------------------------------------------
+    const int wl = lane & (wpb - 1), slot = lane >> Mv.wpb_log2;
+    const long long iw = g * wpb + wl;
+    const bool skip = s_flag[wl] != 0;
+    LaneWalker<R> lw;
+#pragma unroll
+    for (int k = 0; k < kNumWC; ++k) lw.wc[k] = s_wc[wl * kNumWC + k];
+    lw.t0 = s_t[wl * 2];
+    lw.t1 = s_t[wl * 2 + 1];
+    const R *py = reinterpret_cast<const R *>(P.y);
+    const R *pe1 = reinterpret_cast<const R *>(P.e1);
+    const R *pe2 = reinterpret_cast<const R *>(P.e2);
+    R chi = 0;
+    for (int tile = warp; tile < TL.ntiles; tile += nw) {
+        const int4 tl = TL.tiles[tile];
+        if (!skip && slot < tl.y) {
+            const int pi = tl.x + slot;
+            R yhat = point_model<MODEL, R>(P, lw, s_bank, s_foff, tl.z, P.t[pi], s_tab + wl, wpb);
+            if (Mv.mode == MODE_MODEL) {
+                Mv.out[iw * P.npoints + pi] = (double)yhat * P.scale;
+            } else if (P.use_sigma) {
+                R s2 = pe1[pi] + lw.wc[7] * pe2[pi];                 // models.py:130
+                R r = py[pi] - yhat;
+                chi += Mth<R>::lg2(s2) * (R)kLn2 + r * r * Mth<R>::rcp(s2);
+            } else {
+                R r = (py[pi] - yhat) * pe1[pi];                      // models.py:135
+                chi = fma(r, r, chi);
+            }
+        }
+    }
+    if (Mv.mode == MODE_MODEL) { __syncthreads(); return; }
+
+    // ---- phase 3: reduce, accept, write back ----------------------------------------------
+    double chid = (double)chi;
+    for (int off = 16; off >= wpb; off >>= 1) chid += __shfl_xor_sync(0xffffffffu, chid, off);
+    if (lane < wpb) s_part[warp * wpb + lane] = chid;
+    __syncthreads();
+    if (tid < wpb) {
+        const long long i = g * wpb + tid;
+        if (i < Mv.Ns) {
+            double lp = s_lp[tid];
+            double nlp = lp;
+            if (!s_flag[tid]) {
+                double tot = 0.;
+                for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid];
+                nlp = lp + (-0.5 * (P.const_term + tot));
+            }
+            if (Mv.mode != MODE_MOVE) {
+                Mv.out[i] = nlp;
+                if (nlp != nlp) atomicAdd(Mv.nanflag, 1);
+            } else {
+                const long long row = Mv.act_rows ? (long long)Mv.act_rows[i] : Mv.act_base + i;
+                const long long j = (row < Mv.n0) ? 2 * row : 2 * (row - Mv.n0) + 1;
+                double logu;
+                if (Mv.luin) {
+                    logu = Mv.luin[i];
+                } else {
+                    uint32_t r[4];
+                    philox4x32_10((uint32_t)j, Mv.ctr, (uint32_t)(j >> 32), 0u, (uint32_t)Mv.seed, (uint32_t)(Mv.seed >> 32), r);
+                    logu = log(((double)r[3] + 0.5) * (1.0 / 4294967296.0));
+                }
+                if (nlp != nlp) atomicAdd(Mv.nanflag, 1);           // emcee: "Probability function returned NaN"
+                const double old = Mv.logp[row];
+                const double lnpdiff = (double)(D - 1) * log(s_z[tid]) + nlp - old;
+                const bool acc = lnpdiff > logu;
+                double *crd = Mv.coords + row * D;
+                if (acc) {
+                    for (int d = 0; d < D; ++d) crd[d] = s_q[tid * D + d];
+                    Mv.logp[row] = nlp;
+                    Mv.accepted[j] += 1ull;
+                }
+                if (Mv.chain_step) {
+                    for (int d = 0; d < D; ++d) Mv.chain_step[j * D + d] = acc ? s_q[tid * D + d] : crd[d];
+                    Mv.lnp_step[j] = acc ? nlp : old;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
+// ---------------------------------------------------------------------------------------
+template <int MODEL, typename R>
+__global__ void __launch_bounds__(512) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wpb = 1 << Mv.wpb_log2;
+    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
+    uint32_t parity = 0;
+    bool first = true;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        group_pass<MODEL, R>(P, TL, Mv, g, smem, L, parity, first);
+        first = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel B: batched independent ensembles.  One CTA per (problem, ensemble); the whole chain
+// (burn-in + sampling) runs inside one launch with CTA-level barriers between half-steps.
+// ---------------------------------------------------------------------------------------
+struct BatchDev {
+    const ProblemDev *probs;         // [nproblems]
+    const TileDev *tiles;            // [nproblems]
+    double *coords;                  // [nproblems][W][D] colour-major
+    double *logp;                    // [nproblems][W]
+    unsigned long long *accepted;    // [nproblems][W]
+    int *status;                     // [nproblems] NaN counters
+    double *chain;                   // [nproblems][nsteps][W][D]
+    double *lnp;                     // [nproblems][nsteps][W]
+    long long W, n0, nproblems;
+    long long nburn, nsteps, iter0;
+    unsigned long long seed;
+    int wpb_log2, init_logp;
+};
+
+template <int MODEL, typename R>
+__global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ ProblemDev sP;
+    __shared__ TileDev sT;
+    const long long prob = blockIdx.x;
+    {
+        const int *src = reinterpret_cast<const int *>(B.probs + prob);
+        int *dst = reinterpret_cast<int *>(&sP);
+        for (int i = threadIdx.x; i < (int)(sizeof(ProblemDev) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) sT = B.tiles[prob];
+    }
+    __syncthreads();
+    const int wpb = 1 << B.wpb_log2;
+    SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    const int D = sP.ndim;
+    MoveDev Mv;
+    Mv.coords = B.coords + prob * B.W * D;
+    Mv.logp = B.logp + prob * B.W;
+    Mv.accepted = B.accepted + prob * B.W;
+    Mv.nanflag = B.status + prob;
+    Mv.W = B.W; Mv.n0 = B.n0;
+    Mv.wpb_log2 = B.wpb_log2;
+    Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
+    Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
+    Mv.seed = B.seed ^ ((unsigned long long)(prob + 1) * 0x9E3779B97F4A7C15ull);
+    Mv.qin = nullptr; Mv.out = nullptr;
+    bool first = true;
+    if (B.init_logp) {                                   // log-prob of the initial positions
+        Mv.mode = MODE_LOGPOST;
+        Mv.Ns = B.W; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0;
+        Mv.qin = Mv.coords; Mv.out = Mv.logp;
+        Mv.chain_step = nullptr; Mv.lnp_step = nullptr; Mv.ctr = 0;
+        const long long ng = (B.W + wpb - 1) / wpb;
+        for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, 0, first); first = false; }
+        Mv.qin = nullptr; Mv.out = nullptr;
+    }
+    Mv.mode = MODE_MOVE;
+    const long long n1 = B.W - B.n0;
+    for (long long it = 0; it < B.nburn + B.nsteps; ++it) {
+        const bool store = it >= B.nburn;
+        Mv.chain_step = store ? B.chain + ((prob * B.nsteps + (it - B.nburn)) * B.W) * D : nullptr;
+        Mv.lnp_step = store ? B.lnp + (prob * B.nsteps + (it - B.nburn)) * B.W : nullptr;
+        for (int half = 0; half < 2; ++half) {
+            Mv.ctr = (unsigned int)(2 * (B.iter0 + it) + half);
+            Mv.Ns = half ? n1 : B.n0;
+            Mv.act_base = half ? B.n0 : 0;
+            Mv.Nc = half ? B.n0 : n1;
+            Mv.comp_base = half ? 0 : B.n0;
+            const long long ng = (Mv.Ns + wpb - 1) / wpb;
+            for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, 0, first); first = false; }
+        }
+    }
+}
+
+}  // namespace lcf

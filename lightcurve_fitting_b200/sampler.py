@@ -1,0 +1,183 @@
+"""Device-resident affine-invariant ensemble sampler with the ``emcee.EnsembleSampler`` surface the
+reference relies on (fitting.py:130-153, bolometric.py:167-183): ``run_mcmc`` returning a 3-iterable
+state, ``reset``, ``chain``, ``flatchain``, ``get_chain``, ``get_log_prob``, ``acceptance_fraction``.
+
+The walker ensemble, its log-probabilities and the stored chain live in HBM for the whole run; each
+stretch-move half-step is one fused kernel launch (proposal + prior + model + filter integration +
+chi-square + accept + chain write-back).
+"""
+import ctypes as C
+import numpy as np
+
+from ._capi import lib, check, dptr, iptr, f64, i32
+
+
+class State:
+    """Minimal ``emcee.State``: unpacks to ``(coords, log_prob, random_state)``."""
+
+    def __init__(self, coords, log_prob, random_state=None):
+        self.coords, self.log_prob, self.random_state = coords, log_prob, random_state
+
+    def __iter__(self):
+        return iter((self.coords, self.log_prob, self.random_state))
+
+    def __len__(self):
+        return 3
+
+    def __getitem__(self, i):
+        return (self.coords, self.log_prob, self.random_state)[i]
+
+
+def walkers_independent(coords):
+    """emcee's initial-state check: finite, non-degenerate, condition number <= 1e8."""
+    if not np.all(np.isfinite(coords)):
+        return False
+    Cm = coords - np.mean(coords, axis=0)[None, :]
+    colmax = np.amax(np.abs(Cm), axis=0)
+    if np.any(colmax == 0):
+        return False
+    Cm = Cm / colmax
+    Cm = Cm / np.sqrt(np.sum(Cm ** 2, axis=0))
+    return np.linalg.cond(Cm.astype(float)) <= 1e8
+
+
+class EnsembleSampler:
+    """Stretch-move ensemble sampler over a :class:`~lightcurve_fitting_b200.problem.DeviceProblem`.
+
+    Parameters
+    ----------
+    nwalkers, ndim : int
+    problem : DeviceProblem
+        Replaces emcee's ``log_prob_fn``: the log-posterior is evaluated inside the kernels.
+    seed : int, optional
+        Key of the counter-based device RNG.  Default: drawn from numpy's global legacy RNG, so that
+        ``np.random.seed(s)`` before a fit makes it reproducible, as with the reference.
+    rank, world : int
+        Shard one ensemble over ``world`` GPUs (see ``parallel.py``).
+    """
+
+    def __init__(self, nwalkers, ndim, problem, seed=None, rank=0, world=1):
+        if ndim != problem.ndim:
+            raise ValueError('ndim does not match the problem')
+        self.nwalkers, self.ndim, self.problem = int(nwalkers), int(ndim), problem
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + int(np.random.randint(0, 2 ** 31 - 1))
+        self.seed = int(seed)
+        h = C.c_void_p()
+        check(lib().lcf_ensemble_create(problem.handle, self.nwalkers, C.c_uint64(self.seed), rank, world, C.byref(h)))
+        self.handle = h
+        self.iteration = 0
+        self.last_ms = 0.
+        self.last_launches = 0
+
+    def __del__(self):
+        h = getattr(self, 'handle', None)
+        if h is not None:
+            try:
+                lib().lcf_ensemble_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- emcee surface ----------------------------------------------------------------------
+    def _set_initial(self, initial, skip_initial_state_check):
+        if isinstance(initial, State):
+            coords, log_prob = initial.coords, initial.log_prob
+        else:
+            coords, log_prob = initial, None
+        coords = f64(np.atleast_2d(coords))
+        if coords.shape != (self.nwalkers, self.ndim):
+            raise ValueError('incompatible input dimensions')
+        if not skip_initial_state_check and not walkers_independent(coords):
+            raise ValueError('Initial state has a large condition number. Make sure that your walkers are linearly '
+                             'independent for the best performance')
+        lp = None if log_prob is None else f64(log_prob)
+        check(lib().lcf_ensemble_set_state(self.handle, dptr(coords), dptr(lp) if lp is not None else None))
+
+    def _state(self):
+        coords = np.empty((self.nwalkers, self.ndim))
+        lp = np.empty(self.nwalkers)
+        check(lib().lcf_ensemble_get_state(self.handle, dptr(coords), dptr(lp)))
+        return State(coords, lp, None)
+
+    def _timing(self):
+        ms = C.c_double(0.)
+        n = C.c_int64(0)
+        check(lib().lcf_ensemble_last_timing(self.handle, C.byref(ms), C.byref(n)))
+        self.last_ms, self.last_launches = ms.value, n.value
+
+    def run_mcmc(self, initial_state, nsteps, progress=False, progress_kwargs=None, skip_initial_state_check=False,
+                 store=True, **kwargs):
+        """Iterate the stretch move ``nsteps`` times from ``initial_state`` ([nwalkers, ndim] or a State; ``None``
+        continues from the current position).  Returns a State that unpacks to (coords, log_prob, random_state)."""
+        if initial_state is not None:
+            self._set_initial(initial_state, skip_initial_state_check)
+        check(lib().lcf_ensemble_run(self.handle, int(nsteps), 1 if store else 0))
+        self._timing()
+        self.iteration += int(nsteps) if store else 0
+        return self._state()
+
+    def run_replay(self, initial_state, draws, store=True):
+        """Drive the move with injected draws in emcee's order (see ``lcf_ensemble_run_replay``).
+
+        ``draws`` is the list recorded by the oracle's ``StretchReplay``: one dict per step with ``inds`` (split
+        label per walker) and ``halves`` = [{'z', 'rint', 'logu'}, ...] for split 0 and split 1.
+        """
+        if initial_state is not None:
+            self._set_initial(initial_state, True)
+        S, W = len(draws), self.nwalkers
+        split = np.empty((S, W), np.int32)
+        z = np.empty((S, W))
+        rint = np.empty((S, W), np.int32)
+        logu = np.empty((S, W))
+        for s, d in enumerate(draws):
+            split[s] = d['inds']
+            z[s] = np.concatenate([h['z'] for h in d['halves']])
+            rint[s] = np.concatenate([h['rint'] for h in d['halves']])
+            logu[s] = np.concatenate([h['logu'] for h in d['halves']])
+        check(lib().lcf_ensemble_run_replay(self.handle, S, 1 if store else 0, iptr(split), dptr(z), iptr(rint), dptr(logu)))
+        self._timing()
+        self.iteration += S if store else 0
+        return self._state()
+
+    def reset(self):
+        check(lib().lcf_ensemble_reset(self.handle))
+        self.iteration = 0
+
+    def get_chain(self, flat=False, thin=1, discard=0):
+        n = lib().lcf_ensemble_nstored(self.handle)
+        out = np.empty((n, self.nwalkers, self.ndim))
+        check(lib().lcf_ensemble_get_chain(self.handle, dptr(out)))
+        out = out[discard + thin - 1::thin]
+        return out.reshape(-1, self.ndim) if flat else out
+
+    def get_log_prob(self, flat=False, thin=1, discard=0):
+        n = lib().lcf_ensemble_nstored(self.handle)
+        out = np.empty((n, self.nwalkers))
+        check(lib().lcf_ensemble_get_log_prob(self.handle, dptr(out)))
+        out = out[discard + thin - 1::thin]
+        return out.reshape(-1) if flat else out
+
+    @property
+    def chain(self):
+        """[nwalkers, nsteps, ndim] (emcee's deprecated but still-used layout, fitting.py:139)."""
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def flatchain(self):
+        """[nsteps * nwalkers, ndim], step-major (fitting.py:147)."""
+        return self.get_chain(flat=True)
+
+    @property
+    def lnprobability(self):
+        return np.swapaxes(self.get_log_prob(), 0, 1)
+
+    @property
+    def flatlnprobability(self):
+        return self.get_log_prob(flat=True)
+
+    @property
+    def acceptance_fraction(self):
+        acc = np.empty(self.nwalkers, np.int64)
+        check(lib().lcf_ensemble_get_accepted(self.handle, acc.ctypes.data_as(C.POINTER(C.c_int64))))
+        return acc / max(self.iteration, 1)

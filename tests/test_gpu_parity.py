@@ -1,0 +1,258 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): log-posterior rtol 1e-9 in FP64 mode, 1e-4 in FP32 mode; chains driven
+with identical stretch-move draws reproduce the oracle's emcee-order chains to the same tolerance.
+"""
+import numpy as np
+import pytest
+
+from tests import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {'fp64': 1e-9, 'fp32': 1e-4}
+
+
+def _params(wl, n, seed, widen=0.):
+    """Parameter sets inside the start box, optionally widened so that some fall outside the priors."""
+    rng = np.random.default_rng(seed)
+    span = wl.p_up - wl.p_lo
+    return (wl.p_lo - widen * span) + rng.random((n, wl.ndim)) * span * (1. + 2. * widen)
+
+
+def _check_logpost(wl, precision, n=24, seed=0, widen=0.):
+    prob = wl.device_problem(precision)
+    P = _params(wl, n, seed, widen)
+    lp = W.oracle_log_posterior(wl)
+    want = np.array([lp(p) for p in P])
+    got = prob.log_posterior(P)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(want), np.isneginf(got))
+    np.testing.assert_allclose(got[fin], want[fin], rtol=RTOL[precision])
+    return got, want
+
+
+WORKLOADS = {
+    'sc4_example': lambda: W.example_sc4(),
+    'sc4_example_sigma_rel': lambda: W.example_sc4(npoints=80, use_sigma=True),
+    'sc4_example_sigma_abs': lambda: W.example_sc4(npoints=80, use_sigma=True, sigma_type='absolute'),
+    'sc3_synth': lambda: W.synthetic_sc3(npoints=160),
+    'sc3_synth_sigma': lambda: W.synthetic_sc3(npoints=96, use_sigma=True),
+    'cs3_synth': lambda: W.synthetic_cs3(npoints=150),
+    'sed': lambda: W.sed_epoch(np.random.default_rng(7)),
+    'sed_sigma': lambda: W.sed_epoch(np.random.default_rng(8), use_sigma=True),
+}
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+@pytest.mark.parametrize('name', sorted(WORKLOADS))
+def test_log_posterior_parity(name, precision):
+    _check_logpost(WORKLOADS[name](), precision)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_log_posterior_outside_prior(precision):
+    """-inf outside the strict prior bounds (models.py:1055-1059), likelihood skipped (fitting.py:125)."""
+    got, want = _check_logpost(W.example_sc4(npoints=40), precision, n=64, seed=3, widen=0.6)
+    assert np.isneginf(want).any() and np.isfinite(want).any()
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_points_before_explosion_contribute_zero_model(precision):
+    """power() returns 0 for t <= t_exp (models.py:42-48): move t_0 into the middle of the data."""
+    wl = W.example_sc4(npoints=60)
+    wl.priors_spec[4] = ('uniform', 57460., 57480.)
+    wl.p_lo[4], wl.p_up[4] = 57470., 57475.
+    _check_logpost(wl, precision, n=16, seed=5)
+
+
+def _shock_variants():
+    from lightcurve_fitting_b200 import synthetic
+    base = W.example_sc4(npoints=50)
+    out = []
+    for model_name, kw, lo, hi in [
+        ('ShockCooling', {}, [0.5, 0.1, 0.1, 1., 57468.5], [2., 2., 10., 10., 57468.7]),
+        ('ShockCooling', {'n': 3.}, [0.5, 0.1, 0.1, 1., 57468.5], [2., 2., 10., 10., 57468.7]),
+        ('ShockCooling', {'RW': True}, [0.5, 0.1, 0.1, 1., 57468.5], [2., 2., 10., 10., 57468.7]),
+        ('ShockCooling2', {}, [10., 0.5, 2., 57468.5], [30., 5., 10., 57468.7]),
+    ]:
+        pri = [('uniform', -1e3, 1e5)] * len(lo)
+        out.append(synthetic.Workload('variant-' + model_name, model_name, base.t, base.filter_names, base.y, base.dy, pri,
+                                      lo, hi, z=base.z, model_kwargs=kw))
+    return out
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_shockcooling_variants(precision):
+    for wl in _shock_variants():
+        _check_logpost(wl, precision, n=12, seed=11)
+
+
+def _companion_variants():
+    from lightcurve_fitting_b200 import synthetic
+    base = W.synthetic_cs3(npoints=90)
+    out = []
+    tpk = 58000.
+    for model_name, lo, hi in [
+        ('CompanionShocking', [tpk - 17.5, 0.05, 0.5, tpk - 0.5, 0.9, 0.8, 0.8, 0.8], [tpk - 17., 0.15, 2., tpk + 0.5, 1.1, 1.2, 1.2, 1.2]),
+        ('CompanionShocking2', [tpk - 17.5, 0.05, 0.5, tpk - 0.5, 0.9, -0.5, -0.5], [tpk - 17., 0.15, 2., tpk + 0.5, 1.1, 0.5, 0.5]),
+    ]:
+        pri = [('uniform', -1e6, 1e6)] * len(lo)
+        out.append(synthetic.Workload('variant-' + model_name, model_name, base.t, base.filter_names, base.y, base.dy, pri,
+                                      lo, hi, z=base.z))
+    return out
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_companion_variants(precision):
+    for wl in _companion_variants():
+        _check_logpost(wl, precision, n=12, seed=13)
+
+
+@pytest.mark.parametrize('name', ['sc4_example', 'sc3_synth', 'cs3_synth'])
+def test_model_call_pointwise_and_grid(name):
+    """Model.__call__(t, f, *params): pointwise and grid modes (models.py:1161-1164, fitting.py:350-352)."""
+    wl = WORKLOADS[name]()
+    model = wl.model('fp64')
+    omodel, _, _ = W.oracle_for(wl)
+    p = 0.5 * (wl.p_lo + wl.p_up)
+    f, of = np.array(wl.filters(), dtype=object), W.oracle_filters(wl.filter_names)
+    got = model(wl.t, f, *p)
+    want = omodel(wl.t, of, *p)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    # grid: 3 filters x 7 times x 4 parameter sets
+    uf = list(dict.fromkeys(wl.filter_names))[:3]
+    tg = np.linspace(wl.t.min(), wl.t.max(), 7)
+    ps = np.array([wl.p_lo + (wl.p_up - wl.p_lo) * u for u in (0.1, 0.4, 0.6, 0.9)]).T
+    got = model(tg, [f[wl.filter_names.index(n)] for n in uf], *ps)
+    want = omodel(tg, W.oracle_filters(uf), *ps)
+    assert got.shape == want.shape == (3, 7, 4)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+
+
+def test_log_likelihood_method():
+    wl = W.example_sc4(npoints=50, use_sigma=True)
+    model = wl.model('fp64')
+    omodel, _, _ = W.oracle_for(wl)
+    p = 0.5 * (wl.p_lo + wl.p_up)
+    got = model.log_likelihood(wl.lc(), p, use_sigma=True, sigma_type='relative')
+    want = omodel.log_likelihood(wl.t, W.oracle_filters(wl.filter_names), wl.y, wl.dy, p, use_sigma=True)
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    with pytest.raises(Exception, match='sigma_type'):
+        model.log_likelihood(wl.lc(), p, use_sigma=True, sigma_type='bogus')
+
+
+def test_blackbody_to_filters_and_planck():
+    from lightcurve_fitting_b200 import models as M
+    from lightcurve_fitting_b200.filters import filtdict
+    from oracle import reference_port as rp
+    names = ['U', 'B', 'g', 'r', 'UVW2', 'F444W']
+    T = np.array([5., 9., 14., 22., 40., 3.])
+    R = np.array([1., 2., 0.5, 3., 1.5, 10.])
+    f = [filtdict[n] for n in names]
+    of = W.oracle_filters(names)
+    for kw in ({}, {'z': 0.05}, {'z': 0.01, 'cutoff_freq': 700.}, {'ebv': 0.2}):
+        np.testing.assert_allclose(M.blackbody_to_filters(f, T, R, **kw), rp.blackbody_to_filters(of, T, R, **kw), rtol=1e-9)
+        np.testing.assert_allclose(M.blackbody_to_filters(f[:2], T, R, **kw), rp.blackbody_to_filters(of[:2], T, R, **kw),
+                                   rtol=1e-9)
+    nu = np.linspace(100., 1500., 57)
+    np.testing.assert_allclose(M.planck_fast(nu, 12., 3.), rp.planck_fast(nu, 12., 3.), rtol=1e-9)
+    np.testing.assert_allclose(M.planck_fast(nu, T, R, 600.), rp.planck_fast(nu, T, R, 600.), rtol=1e-9)
+    # zero / negative temperature: power() semantics give exactly 0
+    assert np.all(M.planck_fast(nu, np.array([0., -3.]), np.array([1., 1.])) == 0.)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+@pytest.mark.parametrize('name', ['sc4_example', 'sc3_synth_sigma', 'sed'])
+def test_chain_replay_matches_oracle(name, precision):
+    """Identical (split, z, partner, log u) draws => the chain reproduces the oracle's emcee-order chain."""
+    from oracle import reference_port as rp
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = WORKLOADS[name]()
+    if name == 'sc4_example':
+        wl = W.example_sc4(npoints=40)
+    nw, nsteps = 2 * wl.ndim + 6, 12
+    _, _, lp = W.oracle_for(wl)
+    rs = np.random.RandomState(42)
+    p0 = wl.p_lo + rs.rand(nw, wl.ndim) * (wl.p_up - wl.p_lo)
+    ref = rp.StretchReplay(nw, wl.ndim, lp, random_state=rs)
+    ref.run_mcmc(p0, nsteps, record=True)
+    s = EnsembleSampler(nw, wl.ndim, wl.device_problem(precision), seed=0)
+    state = s.run_replay(p0, ref.draws)
+    got, want = s.get_chain(), ref.get_chain()
+    assert got.shape == want.shape == (nsteps, nw, wl.ndim)
+    if precision == 'fp64':
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+        np.testing.assert_allclose(s.get_log_prob(), ref.get_log_prob(), rtol=1e-9)
+        np.testing.assert_array_equal(s.acceptance_fraction, ref.acceptance_fraction)
+    else:
+        # FP32 log-posteriors differ at the 1e-4 level, so a borderline accept decision may flip; require that
+        # the bulk of the walkers agree and that agreeing walkers match to tolerance
+        same = np.all(np.isclose(got, want, rtol=1e-4, atol=0), axis=(0, 2))
+        assert same.mean() >= 0.7
+    np.testing.assert_allclose(state.coords, got[-1])
+    assert s.chain.shape == (nw, nsteps, wl.ndim) and s.flatchain.shape == (nsteps * nw, wl.ndim)
+
+
+def test_native_rng_sampler_statistics():
+    """Device Philox stretch move: posterior medians / 68 % intervals agree with the oracle sampler (SED case,
+    cheap enough for the oracle to run long chains)."""
+    from oracle import reference_port as rp
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.sed_epoch(np.random.default_rng(21))
+    nw, nburn, nsteps = 32, 300, 600
+    _, _, lp = W.oracle_for(wl)
+    rs = np.random.RandomState(5)
+    p0 = wl.p_lo + rs.rand(nw, wl.ndim) * (wl.p_up - wl.p_lo)
+    ref = rp.StretchReplay(nw, wl.ndim, lp, random_state=rs)
+    pos, lnp, _ = ref.run_mcmc(p0, nburn)
+    ref.reset()
+    ref.run_mcmc(pos, nsteps, log_prob0=lnp)
+    s = EnsembleSampler(nw, wl.ndim, wl.device_problem('fp64'), seed=77)
+    s.run_mcmc(p0, nburn)
+    s.reset()
+    s.run_mcmc(None, nsteps)
+    a, b = s.flatchain, ref.flatchain
+    qa, qb = np.percentile(a, [16, 50, 84], axis=0), np.percentile(b, [16, 50, 84], axis=0)
+    width = qb[2] - qb[0]
+    assert np.all(np.abs(qa[1] - qb[1]) < 0.25 * width)          # medians within a quarter of the 68 % width
+    assert np.all(np.abs((qa[2] - qa[0]) / width - 1.) < 0.35)    # interval widths agree
+    assert 0.1 < s.acceptance_fraction.mean() < 0.9
+
+
+def test_nan_posterior_raises_like_emcee():
+    """A NaN log-probability raises ValueError (emcee) -- negative radius makes L ** 0.5 NaN (models.py:268)."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.example_sc4(npoints=30)
+    wl.priors_spec = [('uniform', -100., 100.)] * 4 + [('uniform', 57460., 57470.)]
+    prob = wl.device_problem('fp64')
+    rng = np.random.default_rng(0)
+    p0 = wl.start(16, rng)
+    p0[3, 3] = -2.
+    s = EnsembleSampler(16, wl.ndim, prob, seed=0)
+    with pytest.raises(ValueError, match='NaN'):
+        s.run_mcmc(p0, 2)
+    with pytest.raises(RuntimeError, match='fewer walkers'):
+        EnsembleSampler(6, wl.ndim, prob, seed=0)
+
+
+def test_batched_ensembles_match_single():
+    """lcf_batch (one CTA per problem, whole chain in one launch) == the per-problem half-step launches."""
+    from lightcurve_fitting_b200.bolometric import BatchSampler
+    rng = np.random.default_rng(3)
+    wls = [W.sed_epoch(rng) for _ in range(7)]
+    probs = [w.device_problem('fp64') for w in wls]
+    nw, nburn, nsteps = 10, 20, 15
+    p0 = np.stack([w.start(nw, rng) for w in wls])
+    b = BatchSampler(probs, nw, seed=9).run(p0, nburn, nsteps)
+    chain = b.get_chain()
+    assert chain.shape == (7, nsteps, nw, 2)
+    assert np.all(b.status == 0)
+    # every stored position must carry its own log-posterior
+    lnp = b.get_log_prob()
+    for i, w in enumerate(wls):
+        flat = chain[i].reshape(-1, 2)
+        np.testing.assert_allclose(probs[i].log_posterior(flat), lnp[i].reshape(-1), rtol=1e-12)
+        lp = W.oracle_log_posterior(w)
+        np.testing.assert_allclose(lnp[i, -1], [lp(p) for p in chain[i, -1]], rtol=1e-9)
+    assert 0.05 < b.acceptance_fraction.mean() < 0.95
