@@ -158,6 +158,8 @@ int  lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store);
    complementary set, ascending walker order), logu (log of the acceptance uniform).        */
 int  lcf_ensemble_run_replay(lcf_ensemble *e, int64_t nsteps, int store, const int32_t *split,
                              const double *z, const int32_t *partner, const double *logu);
+/* pre-allocate HBM for nsteps more stored iterations (otherwise grown geometrically on demand) */
+int  lcf_ensemble_reserve(lcf_ensemble *e, int64_t nsteps);
 /* one half-step only (multi-GPU drivers interleave the all-gather between half-steps)      */
 int  lcf_ensemble_half_step(lcf_ensemble *e, int half, int store);
 int  lcf_ensemble_end_step(lcf_ensemble *e, int store);
@@ -169,6 +171,9 @@ int  lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted /* [nwalkers] 
    coords are stored colour-major: rows [0, n0) even walkers, [n0, nwalkers) odd walkers.    */
 int  lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream,
                               int64_t *n0, int64_t *own_begin /* [2] */, int64_t *own_count /* [2] */);
+/* launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's current stream, so that
+   collectives issued by the caller are stream-ordered with the half-step kernels.           */
+int  lcf_ensemble_set_stream(lcf_ensemble *e, void *stream);
 int  lcf_ensemble_sync(lcf_ensemble *e);
 /* device time (ms) spent in the last lcf_ensemble_run* call, measured with CUDA events on the
    handle's stream; kernel launches issued by that call.                                    */

@@ -59,6 +59,7 @@ SYMBOLS = [
     ('lcf_ensemble_reset', C.c_int, [_vp]),
     ('lcf_ensemble_run', C.c_int, [_vp, C.c_int64, C.c_int]),
     ('lcf_ensemble_run_replay', C.c_int, [_vp, C.c_int64, C.c_int, _pi, _pd, _pi, _pd]),
+    ('lcf_ensemble_reserve', C.c_int, [_vp, C.c_int64]),
     ('lcf_ensemble_half_step', C.c_int, [_vp, C.c_int, C.c_int]),
     ('lcf_ensemble_end_step', C.c_int, [_vp, C.c_int]),
     ('lcf_ensemble_nstored', C.c_int64, [_vp]),
@@ -67,6 +68,7 @@ SYMBOLS = [
     ('lcf_ensemble_get_accepted', C.c_int, [_vp, C.POINTER(C.c_int64)]),
     ('lcf_ensemble_device_view', C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ('lcf_ensemble_set_stream', C.c_int, [_vp, _vp]),
     ('lcf_ensemble_sync', C.c_int, [_vp]),
     ('lcf_ensemble_last_timing', C.c_int, [_vp, _pd, C.POINTER(C.c_int64)]),
     ('lcf_batch_create', C.c_int, [C.c_int64, C.POINTER(_vp), C.c_int64, C.c_uint64, C.POINTER(_vp)]),

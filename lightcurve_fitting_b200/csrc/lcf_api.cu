@@ -111,6 +111,7 @@ struct lcf_ensemble {
     double *d_chain = nullptr, *d_lnp = nullptr;
     long long cap = 0, nstored = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool has_state = false;
     double last_ms = 0.;
@@ -119,7 +120,7 @@ struct lcf_ensemble {
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        if (stream && own_stream) cudaStreamDestroy(stream);
     }
 };
 
@@ -683,6 +684,12 @@ static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
     }
 }
 
+int lcf_ensemble_reserve(lcf_ensemble *e, int64_t nsteps) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    return ensure_capacity(e, e->nstored + nsteps);
+}
+
 int lcf_ensemble_half_step(lcf_ensemble *e, int half, int store) {
     if (!e) return fail(LCF_ERR_ARG, "null argument");
     if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
@@ -830,6 +837,15 @@ int lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob
     if (n0) *n0 = e->n0;
     if (own_begin) { own_begin[0] = e->own_begin[0]; own_begin[1] = e->own_begin[1]; }
     if (own_count) { own_count[0] = e->own_count[0]; own_count[1] = e->own_count[1]; }
+    return 0;
+}
+int lcf_ensemble_set_stream(lcf_ensemble *e, void *stream) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    e->stream = reinterpret_cast<cudaStream_t>(stream);
+    e->own_stream = false;
     return 0;
 }
 int lcf_ensemble_sync(lcf_ensemble *e) {

@@ -609,7 +609,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                 if (acc) {
                     for (int d = 0; d < D; ++d) crd[d] = s_q[tid * D + d];
                     Mv.logp[row] = nlp;
-                    Mv.accepted[j] += 1ull;
+                    if (Mv.accepted) Mv.accepted[j] += 1ull;
                 }
                 if (Mv.chain_step) {
                     for (int d = 0; d < D; ++d) Mv.chain_step[j * D + d] = acc ? s_q[tid * D + d] : crd[d];
@@ -682,7 +682,8 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
     MoveDev Mv;
     Mv.coords = B.coords + prob * B.W * D;
     Mv.logp = B.logp + prob * B.W;
-    Mv.accepted = B.accepted + prob * B.W;
+    unsigned long long *acc_ptr = B.accepted + prob * B.W;
+    Mv.accepted = nullptr;
     Mv.nanflag = B.status + prob;
     Mv.W = B.W; Mv.n0 = B.n0;
     Mv.wpb_log2 = B.wpb_log2;
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
     const long long n1 = B.W - B.n0;
     for (long long it = 0; it < B.nburn + B.nsteps; ++it) {
         const bool store = it >= B.nburn;
+        Mv.accepted = store ? acc_ptr : nullptr;          // acceptance counts cover the stored phase only
         Mv.chain_step = store ? B.chain + ((prob * B.nsteps + (it - B.nburn)) * B.W) * D : nullptr;
         Mv.lnp_step = store ? B.lnp + (prob * B.nsteps + (it - B.nburn)) * B.W : nullptr;
         for (int half = 0; half < 2; ++half) {

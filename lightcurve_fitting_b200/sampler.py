@@ -144,16 +144,22 @@ class EnsembleSampler:
         check(lib().lcf_ensemble_reset(self.handle))
         self.iteration = 0
 
-    def get_chain(self, flat=False, thin=1, discard=0):
+    def get_chain(self, flat=False, thin=1, discard=0, out=None):
         n = lib().lcf_ensemble_nstored(self.handle)
-        out = np.empty((n, self.nwalkers, self.ndim))
+        if out is None:
+            out = np.empty((n, self.nwalkers, self.ndim))
+        else:                                    # caller-provided (e.g. pinned) buffer
+            out = out.reshape(-1)[:n * self.nwalkers * self.ndim].reshape(n, self.nwalkers, self.ndim)
         check(lib().lcf_ensemble_get_chain(self.handle, dptr(out)))
         out = out[discard + thin - 1::thin]
         return out.reshape(-1, self.ndim) if flat else out
 
-    def get_log_prob(self, flat=False, thin=1, discard=0):
+    def get_log_prob(self, flat=False, thin=1, discard=0, out=None):
         n = lib().lcf_ensemble_nstored(self.handle)
-        out = np.empty((n, self.nwalkers))
+        if out is None:
+            out = np.empty((n, self.nwalkers))
+        else:
+            out = out.reshape(-1)[:n * self.nwalkers].reshape(n, self.nwalkers)
         check(lib().lcf_ensemble_get_log_prob(self.handle, dptr(out)))
         out = out[discard + thin - 1::thin]
         return out.reshape(-1) if flat else out
