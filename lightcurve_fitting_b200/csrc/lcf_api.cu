@@ -194,7 +194,7 @@ constexpr size_t kSmemMax = 227 * 1024;
 
 int build_tiles(lcf_problem *p, int l) {
     if (p->tiles_built[l]) return 0;
-    const int ppt = 32 >> l;
+    const int ppt = 2 * (32 >> l);              // two points per lane
     std::vector<int4> t;
     const int N = p->dev.npoints;
     int i = 0;
@@ -280,26 +280,30 @@ int check_device() {
 template <typename R>
 int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale) {
     const int F = d->nfilters, N = d->npoints;
-    const int ns = d->bank_offsets[F];
-    const int ns_pad = (ns + 1) & ~1;                        // TMA bulk copies move multiples of 16 bytes
+    // every filter padded to an even number of samples (pad: a = last a, w = 0): the kernels consume sample
+    // pairs and the TMA bulk copy moves multiples of 16 bytes
+    std::vector<int> foff(F + 1, 0);
+    for (int f = 0; f < F; ++f) foff[f + 1] = foff[f] + ((d->bank_offsets[f + 1] - d->bank_offsets[f] + 1) & ~1);
+    const int ns_pad = foff[F];
     typedef typename Vec2<R>::type R2;
     const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
-    std::vector<R2> bank(ns_pad);
-    std::vector<R> kap(ns_pad, (R)0), famin(F);
-    for (int k = 0; k < ns_pad; ++k) {
-        if (k < ns) {
-            bank[k].x = (R)(d->bank_alpha[k] * kLog2e);
-            bank[k].y = (R)(d->bank_w[k] * wfac);
-            if (d->bank_kappa) kap[k] = (R)(d->bank_kappa[k] * 0.4 * 3.3219280948873623479);   // 0.4*log2(10)
-        } else {
-            bank[k].x = (R)1;
-            bank[k].y = (R)0;
-        }
-    }
+    std::vector<R2> bank(ns_pad), frange(F);
+    std::vector<R> kap(ns_pad, (R)0);
     for (int f = 0; f < F; ++f) {
-        double m = INFINITY;
-        for (int k = d->bank_offsets[f]; k < d->bank_offsets[f + 1]; ++k) m = std::min(m, d->bank_alpha[k] * kLog2e);
-        famin[f] = (R)m;
+        const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
+        double mn = INFINITY, mx = 0.;
+        for (int k = 0; k < foff[f + 1] - foff[f]; ++k) {
+            const int src = b0 + std::min(k, n - 1);
+            R2 v;
+            v.x = (R)(d->bank_alpha[src] * kLog2e);
+            v.y = (k < n) ? (R)(d->bank_w[src] * wfac) : (R)0;
+            bank[foff[f] + k] = v;
+            if (d->bank_kappa) kap[foff[f] + k] = (R)(d->bank_kappa[src] * 0.4 * 3.3219280948873623479);   // 0.4*log2(10)
+            mn = std::min(mn, (double)v.x);
+            mx = std::max(mx, (double)v.x);
+        }
+        frange[f].x = (R)mn;
+        frange[f].y = (R)mx;
     }
     std::vector<R> y(N), e1(N), e2(N);
     for (int i = 0; i < N; ++i) {
@@ -319,7 +323,8 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     ProblemDev &P = p->dev;
     if ((rc = upload(bank, &dp))) return rc;  p->allocs.push_back(dp); P.bank = dp;
     if ((rc = upload(kap, &dp))) return rc;   p->allocs.push_back(dp); P.kappa = dp;
-    if ((rc = upload(famin, &dp))) return rc; p->allocs.push_back(dp); P.famin = dp;
+    if ((rc = upload(frange, &dp))) return rc; p->allocs.push_back(dp); P.frange = dp;
+    if ((rc = upload(foff, &dp))) return rc;  p->allocs.push_back(dp); P.foff = reinterpret_cast<const int *>(dp);
     if ((rc = upload(y, &dp))) return rc;     p->allocs.push_back(dp); P.y = dp;
     if ((rc = upload(e1, &dp))) return rc;    p->allocs.push_back(dp); P.e1 = dp;
     if ((rc = upload(e2, &dp))) return rc;    p->allocs.push_back(dp); P.e2 = dp;
@@ -451,12 +456,9 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
     p->h_point_filter.assign(d->point_filter, d->point_filter + d->npoints);
 
     void *dp;
-    std::vector<int> foff(d->bank_offsets, d->bank_offsets + d->nfilters + 1);
     std::vector<int> role(d->nfilters, 0);
     if (d->filter_role) role.assign(d->filter_role, d->filter_role + d->nfilters);
     std::vector<double> t(d->t, d->t + d->npoints);
-    if ((rc = upload(foff, &dp))) { delete p; return rc; }
-    p->allocs.push_back(dp); P.foff = reinterpret_cast<const int *>(dp);
     if ((rc = upload(role, &dp))) { delete p; return rc; }
     p->allocs.push_back(dp); P.frole = reinterpret_cast<const int *>(dp);
     if ((rc = upload(t, &dp))) { delete p; return rc; }

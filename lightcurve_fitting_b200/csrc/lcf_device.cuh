@@ -35,7 +35,7 @@ struct ProblemDev {
     int npoints, nfilters, nsamples, spl_nint;
     const void *bank;      // real2[nsamples]: (alpha*log2(e), w/scale)
     const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
-    const void *famin;     // real[nfilters]: min_k bank.x                    (FP32 slow-path guard)
+    const void *frange;    // real2[nfilters]: (min_k, max_k) of bank.x      (FP32 fast-path guards)
     const int *foff;       // [nfilters+1]
     const int *frole;      // [nfilters]
     const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
@@ -249,12 +249,18 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
 
 // ---------------------------------------------------------------------------------------
 // Planck x transmission sums:  S(invT) = sum_k w_k / (2^(a_k invT) - 1)
+//
+// Bank layout: every filter is padded to an even number of samples (pad: a = last a, w = 0) and
+// starts on a 16-byte boundary, so the loops below consume sample PAIRS: one LDS.128 broadcast
+// (a0,w0,a1,w1) in FP32.  ShockCooling3's per-walker reddened weights live in a pair table
+// tab2[pair][walker] (one conflict-free LDS.64 per lane per pair).
 // ---------------------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ R planck_term_safe(R a, R invT) {
     // power(exp(x) - 1, -1) semantics (models.py:1128): 0 when exp(x)-1 is 0 or inf
     if (sizeof(R) == 4) {
-        float d = expm1f((float)(a * invT) * (float)kLn2);
+        float x = (float)(a * invT);
+        float d = (x < 0.0625f) ? expm1f(x * (float)kLn2) : (Mth<float>::ex2(x) - 1.f);
         return (d > 0.f) ? (R)(1.f / d) : (R)0;
     } else {
         double d = exp2((double)(a * invT)) - 1.0;
@@ -262,57 +268,44 @@ __device__ __forceinline__ R planck_term_safe(R a, R invT) {
     }
 }
 
-// one blackbody.  `tab`: optional per-walker weight table (ShockCooling3: w_k * E_k), stride `ts`.
+// Careful path (any precision): one blackbody, exact guards.  K2 = number of sample pairs.
 template <typename R, bool TAB>
-__device__ __forceinline__ R planck_sum(const typename Vec2<R>::type *__restrict__ b, int K, R invT, bool slow,
-                                        const R *__restrict__ tab, int ts) {
+__device__ __forceinline__ R planck_sum_safe(const typename Vec2<R>::type *__restrict__ b, int K2, R invT,
+                                             const typename Vec2<R>::type *__restrict__ tab, int ts) {
     R acc0 = 0, acc1 = 0;
-    if (sizeof(R) == 4 && !slow) {
-        int k = 0;
-#pragma unroll 4
-        for (; k + 1 < K; k += 2) {
-            typename Vec2<R>::type s0 = b[k], s1 = b[k + 1];
-            R w0 = TAB ? tab[k * ts] : s0.y, w1 = TAB ? tab[(k + 1) * ts] : s1.y;
-            R e0 = Mth<R>::ex2(s0.x * invT), e1 = Mth<R>::ex2(s1.x * invT);
-            acc0 = fma(w0, Mth<R>::rcp(e0 - (R)1), acc0);
-            acc1 = fma(w1, Mth<R>::rcp(e1 - (R)1), acc1);
-        }
-        if (k < K) {
-            typename Vec2<R>::type s0 = b[k];
-            R w0 = TAB ? tab[k * ts] : s0.y;
-            acc0 = fma(w0, Mth<R>::rcp(Mth<R>::ex2(s0.x * invT) - (R)1), acc0);
-        }
-    } else {
-        for (int k = 0; k < K; ++k) {
-            typename Vec2<R>::type s0 = b[k];
-            R w0 = TAB ? tab[k * ts] : s0.y;
-            acc0 = fma(w0, planck_term_safe<R>(s0.x, invT), acc0);
-        }
+    for (int k = 0; k < K2; ++k) {
+        typename Vec2<R>::type s0 = b[2 * k], s1 = b[2 * k + 1];
+        R w0 = s0.y, w1 = s1.y;
+        if (TAB) { typename Vec2<R>::type t = tab[k * ts]; w0 = t.x; w1 = t.y; }
+        acc0 = fma(w0, planck_term_safe<R>(s0.x, invT), acc0);
+        acc1 = fma(w1, planck_term_safe<R>(s1.x, invT), acc1);
     }
     return acc0 + acc1;
 }
 
-// two blackbodies sharing the curve (ShockCooling4: T and 0.74 T), models.py:629-630
-template <typename R>
-__device__ __forceinline__ void planck_sum2(const typename Vec2<R>::type *__restrict__ b, int K, R invTa, R invTb, bool slow,
-                                            R &Sa, R &Sb) {
-    R a0 = 0, b0 = 0;
-    if (sizeof(R) == 4 && !slow) {
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-            typename Vec2<R>::type s = b[k];
-            R ea = Mth<R>::ex2(s.x * invTa), eb = Mth<R>::ex2(s.x * invTb);
-            a0 = fma(s.y, Mth<R>::rcp(ea - (R)1), a0);
-            b0 = fma(s.y, Mth<R>::rcp(eb - (R)1), b0);
-        }
-    } else {
-        for (int k = 0; k < K; ++k) {
-            typename Vec2<R>::type s = b[k];
-            a0 = fma(s.y, planck_term_safe<R>(s.x, invTa), a0);
-            b0 = fma(s.y, planck_term_safe<R>(s.x, invTb), b0);
-        }
+// FP32 fast path: TWO blackbodies (inverse temperatures iA, iB) sharing the curve.  The two
+// reciprocals of a sample are obtained from ONE MUFU.RCP:  r = 1/(dA dB), 1/dA = r dB, 1/dB = r dA,
+// i.e. 1.5 MUFU ops per Planck sample instead of 2.  Callers guarantee a_max*max(iA,iB) <= 63
+// (no overflow of dA*dB) and a_min*min(iA,iB) >= 1/16 (no cancellation in 2^x - 1).
+template <bool TAB>
+__device__ __forceinline__ void planck_pair_f32(const float2 *__restrict__ b, int K2, float iA, float iB,
+                                                const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
+    typedef Mth<float> M;
+    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(b);
+    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < K2; ++k) {
+        const float4 s = b4[k];
+        float w0 = s.y, w1 = s.w;
+        if (TAB) { const float2 t = tab[k * ts]; w0 = t.x; w1 = t.y; }
+        const float dA0 = M::ex2(s.x * iA) - 1.f, dB0 = M::ex2(s.x * iB) - 1.f;
+        const float dA1 = M::ex2(s.z * iA) - 1.f, dB1 = M::ex2(s.z * iB) - 1.f;
+        const float t0 = w0 * M::rcp(dA0 * dB0), t1 = w1 * M::rcp(dA1 * dB1);
+        a0 = fmaf(t0, dB0, a0); c0 = fmaf(t0, dA0, c0);
+        a1 = fmaf(t1, dB1, a1); c1 = fmaf(t1, dA1, c1);
     }
-    Sa = a0; Sb = b0;
+    SA = a0 + a1;
+    SB = c0 + c1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -337,88 +330,131 @@ __device__ __forceinline__ R sifto_eval(const ProblemDev &P, int f, R tau) {
     return (v != v) ? (R)0 : v;
 }
 
-// Model value at one photometry point for one walker (scaled units).
+// Front end of one (walker, point): blackbody inverse temperature and amplitude, so that the
+// blackbody part of the model is  amp * S(invT)  (ShockCooling4: min(amp S(invT), amp 0.74^-4 S(invT/0.74))).
+//   state 1: needs the Planck sum; state 0: blackbody part is `amp` as is (0, or NaN to propagate)
 //   SW family (1,2,3): wc0 = K_T, wc1 = K_L, wc2 = log2(a/t_tr) | -inf, (3: wc3 = E(B-V))
-//        T = K_T t^eps_T ; L = K_L t^eps_L exp(-(a t/t_tr)^alpha) ; yhat = L/T^4 * S(1/T)
+//        T = K_T t^eps_T ; L = K_L t^eps_L exp(-(a t/t_tr)^alpha) ; amp = L/T^4
 //   SC4: wc0 = T_col_br/k_B, wc1 = c3^2 L_br, wc2 = -log2(t_br), wc3 = log2(a/t_tr)
 //   CS*: wc0, wc1 Kasen T/R^2 coefficients, wc2 Kasen factor, wc3 stretch, wc4.. r_r,r_i,r_U | dt_U,dt_i
 //   SED: wc0 = 1/T, wc1 = R^2
+template <typename R> struct PointFE {
+    R invT, amp;
+    int state;
+};
+
 template <int MODEL, typename R>
-__device__ __forceinline__ R point_model(const ProblemDev &P, const LaneWalker<R> &w, const typename Vec2<R>::type *bank,
-                                         const int *s_foff, int f, double tp, const R *tab, int ts) {
+__device__ __forceinline__ PointFE<R> front_end(const ProblemDev &P, const LaneWalker<R> &w, double tp) {
     typedef Mth<R> M;
-    const int k0 = s_foff[f], K = s_foff[f + 1] - k0;
-    const typename Vec2<R>::type *b = bank + k0;
-    const R amin = reinterpret_cast<const R *>(P.famin)[f];
+    PointFE<R> fe;
+    fe.invT = (R)1;
+    fe.state = 0;
     if (MODEL == 8) {
-        R invT = w.wc[0];
-        if (!(invT > (R)0)) return w.wc[1] * (R)0;
-        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
-        return w.wc[1] * planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
+        fe.invT = w.wc[0];
+        fe.amp = w.wc[1];
+        if (fe.invT > (R)0) fe.state = 1; else { fe.amp = w.wc[1] * (R)0; fe.invT = (R)1; }
+        return fe;
     }
-    R dt = (R)(tp - w.t0);
-    R yk = (R)0;
+    const R dt = (R)(tp - w.t0);
+    R T, L;
     if (MODEL >= 1 && MODEL <= 3) {
-        if (!(dt > (R)0)) return (w.wc[0] * w.wc[1]) * (R)0;   // t <= t_exp: zero (NaN constants propagate)
+        if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }   // t <= t_exp: zero (NaN constants propagate)
         const R epsT = (R)(2. * P.mc[3] - 0.5), epsL = (R)(-2. * P.mc[4]), alpha = (R)P.mc[2];
-        R lt = M::lg2(dt);
-        R T = w.wc[0] * M::ex2(epsT * lt);
-        R sup = (w.wc[2] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[2]))) : (R)1;
-        R L = w.wc[1] * M::ex2(epsL * lt) * sup;
-        if (L < (R)0) return M::nan();                          // L ** 0.5 (models.py:268)
-        if (!(T > (R)0)) return (T != T) ? M::nan() : L * (R)0;
-        R invT = M::rcp(T);
-        R i2 = invT * invT;
-        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
-        R S = (MODEL == 3) ? planck_sum<R, true>(b, K, invT, slow, tab + (size_t)k0 * ts, ts)
-                           : planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
-        return L * (i2 * i2) * S;
-    }
-    if (MODEL == 4) {
-        if (!(dt > (R)0)) return (w.wc[0] * w.wc[1]) * (R)0;
+        const R lt = M::lg2(dt);
+        T = w.wc[0] * M::ex2(epsT * lt);
+        const R sup = (w.wc[2] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[2]))) : (R)1;
+        L = w.wc[1] * M::ex2(epsL * lt) * sup;
+    } else if (MODEL == 4) {
+        if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }
         const R A = (R)P.mc[0], alpha = (R)P.mc[2];
-        R l0 = M::lg2(dt);
-        R lt = l0 + w.wc[2];                                    // log2(ttilde); NaN when t_br invalid
-        R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (l0 + w.wc[3]))) : (R)1;
-        R L = w.wc[1] * (M::ex2((R)(-4. / 3.) * lt) + A * sup * M::ex2((R)(-0.17) * lt));
-        R T = w.wc[0] * M::mn((R)0.97 * M::ex2((R)(-1. / 3.) * lt), M::ex2((R)(-0.45) * lt));
-        if (L < (R)0) return M::nan();
-        if (!(T > (R)0)) return (T != T) ? M::nan() : L * (R)0;
-        R invT = M::rcp(T);
-        R i2 = invT * invT;
-        R R2 = L * (i2 * i2);
-        R invTb = invT * (R)(1. / 0.74);
-        bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
-        R Sa, Sb;
-        planck_sum2<R>(b, K, invT, invTb, slow, Sa, Sb);
-        // min(B(T,R), B(0.74 T, 0.74^-2 R)), models.py:629-631
-        return M::mn(R2 * Sa, R2 * (R)(1. / (0.74 * 0.74 * 0.74 * 0.74)) * Sb);
+        const R l0 = M::lg2(dt);
+        const R lt = l0 + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
+        const R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (l0 + w.wc[3]))) : (R)1;
+        L = w.wc[1] * (M::ex2((R)(-4. / 3.) * lt) + A * sup * M::ex2((R)(-0.17) * lt));
+        T = w.wc[0] * M::mn((R)0.97 * M::ex2((R)(-1. / 3.) * lt), M::ex2((R)(-0.45) * lt));
+    } else {                                                    // Kasen, models.py:752-754
+        if (!(dt > (R)0)) { fe.amp = (R)0; return fe; }
+        const R lt = M::lg2(dt);
+        T = w.wc[0] * M::ex2((R)(-74. / 144.) * lt);
+        L = w.wc[1] * M::ex2((R)(14. / 9.) * lt);               // = R^2 here
     }
-    // CompanionShocking family
+    if (MODEL <= 4 && L < (R)0) { fe.amp = M::nan(); return fe; }               // L ** 0.5 (models.py:268)
+    if (!(T > (R)0)) { fe.amp = (T != T) ? M::nan() : L * (R)0; return fe; }
+    fe.invT = M::rcp(T);
+    if (MODEL <= 4) { const R i2 = fe.invT * fe.invT; fe.amp = L * (i2 * i2); } else fe.amp = L;
+    fe.state = 1;
+    return fe;
+}
+
+// Combine the blackbody part with the rest of the model (SiFTO template, per-filter factors).
+template <int MODEL, typename R>
+__device__ __forceinline__ R finish_point(const ProblemDev &P, const LaneWalker<R> &w, int f, double tp, R ybb) {
+    if (MODEL < 5 || MODEL == 8) return ybb;
     const int role = P.frole[f];
-    if (dt > (R)0) {
-        R lt = M::lg2(dt);
-        R T = w.wc[0] * M::ex2((R)(-74. / 144.) * lt);
-        R R2 = w.wc[1] * M::ex2((R)(14. / 9.) * lt);
-        if (T > (R)0) {
-            R invT = M::rcp(T);
-            bool slow = (sizeof(R) == 4) && (amin * invT < (R)(1. / 16.));
-            yk = R2 * planck_sum<R, false>(b, K, invT, slow, nullptr, 0);
-        } else if (T != T) {
-            yk = M::nan();
+    const R tw = (R)(tp - w.t1);                                // t_wrt_peak, models.py:816
+    if (MODEL == 5) {
+        const R ys = sifto_eval<R>(P, f, tw / w.wc[3]);
+        const R kf = (role & 1) ? w.wc[6] : (R)1;
+        const R sf = (role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1);
+        return ybb * kf + ys * sf;                              // models.py:915
+    }
+    const R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
+    const R ys = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
+    return ybb * w.wc[2] + ys;                                  // models.py:979, 1044
+}
+
+// Blackbody part of up to two points of one filter for one walker.
+template <int MODEL, typename R>
+__device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typename Vec2<R>::type *bank, const int *s_foff, int f,
+                                               const PointFE<R> &f0, const PointFE<R> &f1, bool two,
+                                               const typename Vec2<R>::type *tab, int ts, R &y0, R &y1) {
+    typedef Mth<R> M;
+    typedef typename Vec2<R>::type R2;
+    const int k0 = s_foff[f], K2 = (s_foff[f + 1] - k0) >> 1;
+    const R2 *b = bank + k0;
+    const R2 *tb = tab + (size_t)(k0 >> 1) * ts;
+    const R c74 = (R)(1. / 0.74), c74_4 = (R)(1. / (0.74 * 0.74 * 0.74 * 0.74));
+    y0 = f0.amp;
+    y1 = f1.amp;
+    const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
+    if (!n0 && !n1) return;
+    if (sizeof(R) == 4) {
+        const float2 rng = reinterpret_cast<const float2 *>(P.frange)[f];       // (a_min, a_max) of the filter
+        const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
+        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
+        const bool fast = (rng.x * imin >= 0.0625f) && (rng.y * imax <= 63.f);
+        if (fast) {
+            const float2 *bf = reinterpret_cast<const float2 *>(b);
+            const float2 *tf = reinterpret_cast<const float2 *>(tb);
+            float S0, S1;
+            if (MODEL == 4) {                                   // pairs (T, 0.74 T) of each point, models.py:629-630
+                float S0b, S1b;
+                planck_pair_f32<false>(bf, K2, i0, i0 * (float)(1. / 0.74), nullptr, 0, S0, S0b);
+                if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0b);
+                if (n1) {
+                    planck_pair_f32<false>(bf, K2, i1, i1 * (float)(1. / 0.74), nullptr, 0, S1, S1b);
+                    y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1b);
+                }
+            } else {                                            // pairs (point 0, point 1)
+                if (MODEL == 3) planck_pair_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                else planck_pair_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                if (n0) y0 = (R)((float)f0.amp * S0);
+                if (n1) y1 = (R)((float)f1.amp * S1);
+            }
+            return;
         }
     }
-    R tw = (R)(tp - w.t1);                                      // t_wrt_peak, models.py:816
-    R ys;
-    if (MODEL == 5) {
-        ys = sifto_eval<R>(P, f, tw / w.wc[3]);
-        R kf = (role & 1) ? w.wc[6] : (R)1;
-        R sf = (role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1);
-        return yk * kf + ys * sf;                               // models.py:915
+    // careful path (FP64 always; FP32 when 2^x - 1 would cancel or the pair product would overflow)
+    if (n0) {
+        const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f0.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f0.invT, nullptr, 0);
+        y0 = f0.amp * S;
+        if (MODEL == 4) y0 = M::mn(y0, f0.amp * c74_4 * planck_sum_safe<R, false>(b, K2, f0.invT * c74, nullptr, 0));
     }
-    R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
-    ys = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
-    return yk * w.wc[2] + ys;                                   // models.py:979, 1044
+    if (n1) {
+        const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f1.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f1.invT, nullptr, 0);
+        y1 = f1.amp * S;
+        if (MODEL == 4) y1 = M::mn(y1, f1.amp * c74_4 * planck_sum_safe<R, false>(b, K2, f1.invT * c74, nullptr, 0));
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -429,7 +465,7 @@ template <typename R> struct SmemLayout {
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
-        off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;          o = (o + 15) & ~(size_t)15;
+        off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;     // R2[nsamples/2][wpb]          o = (o + 15) & ~(size_t)15;
         off_foff = o; o += (size_t)(nfilters + 1) * sizeof(int);                  o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
@@ -455,7 +491,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const int wpb = 1 << Mv.wpb_log2;
     const int D = P.ndim;
     R2 *s_bank = reinterpret_cast<R2 *>(smem + L.off_bank);
-    R *s_tab = reinterpret_cast<R *>(smem + L.off_tab);
+    R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
     int *s_foff = reinterpret_cast<int *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
     double *s_t = reinterpret_cast<double *>(smem + L.off_t);
@@ -528,20 +564,23 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     __syncthreads();
     if (need_stage) mbar_wait(s_bar, bar_parity);
 
-    // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33)
+    // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33), pair layout
     if (MODEL == 3) {
         const R *kap = reinterpret_cast<const R *>(P.kappa);
-        const int n = P.nsamples * wpb;
+        const int n = (P.nsamples >> 1) * wpb;
         for (int idx = tid; idx < n; idx += blockDim.x) {
-            int k = idx >> Mv.wpb_log2, wl = idx & (wpb - 1);
-            R ebv = s_wc[wl * kNumWC + 3];
-            s_tab[idx] = s_bank[k].y * Mth<R>::ex2(-ebv * kap[k]);
+            const int kp = idx >> Mv.wpb_log2, wl = idx & (wpb - 1);
+            const R ebv = s_wc[wl * kNumWC + 3];
+            R2 v;
+            v.x = s_bank[2 * kp].y * Mth<R>::ex2(-ebv * kap[2 * kp]);
+            v.y = s_bank[2 * kp + 1].y * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
+            s_tab[idx] = v;
         }
         __syncthreads();
     }
 
-    // ---- phase 2: tiles ------------------------------------------------------------------
-    const int wl = lane & (wpb - 1), slot = lane >> Mv.wpb_log2;
+    // ---- phase 2: tiles (each lane: up to two points of the tile's filter) ----------------
+    const int wl = lane & (wpb - 1), slot = lane >> Mv.wpb_log2, ppt = 32 >> Mv.wpb_log2;
     const long long iw = g * wpb + wl;
     const bool skip = s_flag[wl] != 0;
     LaneWalker<R> lw;
@@ -556,17 +595,35 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     for (int tile = warp; tile < TL.ntiles; tile += nw) {
         const int4 tl = TL.tiles[tile];
         if (!skip && slot < tl.y) {
-            const int pi = tl.x + slot;
-            R yhat = point_model<MODEL, R>(P, lw, s_bank, s_foff, tl.z, P.t[pi], s_tab + wl, wpb);
+            const int pa = tl.x + slot, pb = pa + ppt;
+            const bool two = slot + ppt < tl.y;
+            const double ta = P.t[pa], tb = two ? P.t[pb] : ta;
+            const PointFE<R> fa = front_end<MODEL, R>(P, lw, ta);
+            PointFE<R> fb = fa;
+            if (two) fb = front_end<MODEL, R>(P, lw, tb);
+            R ya, yb;
+            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, ya, yb);
+            ya = finish_point<MODEL, R>(P, lw, tl.z, ta, ya);
+            if (two) yb = finish_point<MODEL, R>(P, lw, tl.z, tb, yb);
             if (Mv.mode == MODE_MODEL) {
-                Mv.out[iw * P.npoints + pi] = (double)yhat * P.scale;
+                Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
+                if (two) Mv.out[iw * P.npoints + pb] = (double)yb * P.scale;
             } else if (P.use_sigma) {
-                R s2 = pe1[pi] + lw.wc[7] * pe2[pi];                 // models.py:130
-                R r = py[pi] - yhat;
-                chi += Mth<R>::lg2(s2) * (R)kLn2 + r * r * Mth<R>::rcp(s2);
+                const R s2a = pe1[pa] + lw.wc[7] * pe2[pa];          // models.py:130
+                const R ra = py[pa] - ya;
+                chi += Mth<R>::lg2(s2a) * (R)kLn2 + ra * ra * Mth<R>::rcp(s2a);
+                if (two) {
+                    const R s2b = pe1[pb] + lw.wc[7] * pe2[pb];
+                    const R rb = py[pb] - yb;
+                    chi += Mth<R>::lg2(s2b) * (R)kLn2 + rb * rb * Mth<R>::rcp(s2b);
+                }
             } else {
-                R r = (py[pi] - yhat) * pe1[pi];                      // models.py:135
-                chi = fma(r, r, chi);
+                const R ra = (py[pa] - ya) * pe1[pa];                 // models.py:135
+                chi = fma(ra, ra, chi);
+                if (two) {
+                    const R rb = (py[pb] - yb) * pe1[pb];
+                    chi = fma(rb, rb, chi);
+                }
             }
         }
     }
