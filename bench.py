@@ -98,8 +98,13 @@ def oracle_truth(model_name, t, filter_names, params, z):
     return W.oracle_truth(model_name, t, filter_names, params, z)
 
 
+MODEL = 'sc3'
+
+
 def workload(truth, npoints=NPOINTS):
     from lightcurve_fitting_b200 import synthetic
+    if MODEL == 'sc4':      # the same shape with the MSW23 model (two blackbody syntheses per point)
+        return synthetic.synthetic_sc4(truth, npoints=npoints, seed=1, filters=['U', 'B', 'V', 'R', 'I', 'g', 'r', 'i'])
     return synthetic.synthetic_sc3(truth, npoints=npoints, seed=1)
 
 
@@ -291,7 +296,7 @@ def run_ours(args):
     hbm_gbs = chain_bytes_per_step * args.steps / (ms * 1e-3) / 1e9
     roofline = {
         'bound': 'sfu (MUFU ex2+rcp per Planck sample; the path has no dense contraction and ~72 B/walker-step of HBM)',
-        'kernel': 'lcf::k_pass<3,float>' if args.precision == 'fp32' else 'lcf::k_pass<3,double>',
+        'kernel': 'lcf::k_pass<%d,%s>' % (3 if MODEL == 'sc3' else 4, 'float' if args.precision == 'fp32' else 'double'),
         'achieved': samples_per_s_gpu / 1e9, 'peak': peak_samples / 1e9, 'unit': 'GPlanck-samples/s',
         'frac': samples_per_s_gpu / peak_samples,
         'peak_basis': '8 samples/clk/SM x 148 SMs x %.0f MHz (SM clock measured during the timed region)' % sm_mhz,
@@ -307,8 +312,8 @@ def run_ours(args):
         'metric': 'walker-steps/s', 'value': value, 'unit': 'walker-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f64', 'data': 'synthetic',
-        'config': {'workload': 'cfg2: ShockCooling3, synthetic %d-point 8-filter light curve, %d walkers per GPU'
-                               % (args.npoints, args.walkers),
+        'config': {'workload': 'cfg2: %s, synthetic %d-point 8-filter light curve, %d walkers per GPU'
+                               % ('ShockCooling3' if MODEL == 'sc3' else 'ShockCooling4', args.npoints, args.walkers),
                    'walkers_total': W_total, 'ndim': D, 'planck_samples_per_eval': samples_per_eval,
                    'parallelism': 'one ensemble, half-ensembles split over %d GPU(s), all-gather per half-step' % world,
                    'l2': 'working set per CTA (light curve 24 KB + bank 3 KB) is L2/SMEM resident by design; walker '
@@ -331,11 +336,14 @@ def main():
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--walkers', type=int, default=WALKERS_PER_GPU)
     ap.add_argument('--npoints', type=int, default=NPOINTS)
+    ap.add_argument('--model', default='sc3', choices=['sc3', 'sc4'])
     ap.add_argument('--wpb', type=int, default=0)
     ap.add_argument('--nw', type=int, default=0)
     ap.add_argument('--cpu-budget', type=float, default=15.)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    global MODEL
+    MODEL = args.model
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -283,12 +283,15 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec2<R>::type *__res
     return acc0 + acc1;
 }
 
-// FP32 fast path: TWO blackbodies (inverse temperatures iA, iB) sharing the curve.  The two
-// reciprocals of a sample are obtained from ONE MUFU.RCP:  r = 1/(dA dB), 1/dA = r dB, 1/dB = r dA,
-// i.e. 1.5 MUFU ops per Planck sample instead of 2.  Callers guarantee a_max*max(iA,iB) <= 63
-// (no overflow of dA*dB) and a_min*min(iA,iB) >= 1/16 (no cancellation in 2^x - 1).
+// FP32 fast paths.  Four Planck denominators share ONE MUFU.RCP:
+//     r = 1/(d0 d1 d2 d3);  1/(d0 d1) = r (d2 d3);  1/d0 = d1/(d0 d1) ...
+// i.e. 1.25 MUFU ops per Planck sample (1 EX2 + 1/4 RCP) instead of 2, paid for with FMULs on the
+// otherwise idle FMA pipe.  Callers guarantee that the four exponents sum to <= 126 (no overflow of the
+// product) and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
+//
+// (a) two blackbodies (points A, B of one walker) x two consecutive samples of the curve
 template <bool TAB>
-__device__ __forceinline__ void planck_pair_f32(const float2 *__restrict__ b, int K2, float iA, float iB,
+__device__ __forceinline__ void planck_quad_f32(const float2 *__restrict__ b, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
     typedef Mth<float> M;
     const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(b);
@@ -297,15 +300,37 @@ __device__ __forceinline__ void planck_pair_f32(const float2 *__restrict__ b, in
     for (int k = 0; k < K2; ++k) {
         const float4 s = b4[k];
         float w0 = s.y, w1 = s.w;
-        if (TAB) { const float2 t = tab[k * ts]; w0 = t.x; w1 = t.y; }
+        if (TAB) { const float2 t = tab[0]; tab += ts; w0 = t.x; w1 = t.y; }
         const float dA0 = M::ex2(s.x * iA) - 1.f, dB0 = M::ex2(s.x * iB) - 1.f;
         const float dA1 = M::ex2(s.z * iA) - 1.f, dB1 = M::ex2(s.z * iB) - 1.f;
-        const float t0 = w0 * M::rcp(dA0 * dB0), t1 = w1 * M::rcp(dA1 * dB1);
+        const float p0 = dA0 * dB0, p1 = dA1 * dB1;
+        const float r = M::rcp(p0 * p1);
+        const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
         a0 = fmaf(t0, dB0, a0); c0 = fmaf(t0, dA0, c0);
         a1 = fmaf(t1, dB1, a1); c1 = fmaf(t1, dA1, c1);
     }
     SA = a0 + a1;
     SB = c0 + c1;
+}
+
+// (b) ShockCooling4: two points x (T, 0.74 T) at the same sample (models.py:629-630)
+__device__ __forceinline__ void planck_quad_sc4_f32(const float2 *__restrict__ b, int K, float iA, float iB, float &SA,
+                                                    float &SAs, float &SB, float &SBs) {
+    typedef Mth<float> M;
+    const float iAs = iA * (float)(1. / 0.74), iBs = iB * (float)(1. / 0.74);
+    float a = 0.f, as = 0.f, c = 0.f, cs = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float2 s = b[k];
+        const float dA = M::ex2(s.x * iA) - 1.f, dAs = M::ex2(s.x * iAs) - 1.f;
+        const float dB = M::ex2(s.x * iB) - 1.f, dBs = M::ex2(s.x * iBs) - 1.f;
+        const float pA = dA * dAs, pB = dB * dBs;
+        const float r = M::rcp(pA * pB);
+        const float tA = s.y * (r * pB), tB = s.y * (r * pA);
+        a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
+        c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
+    }
+    SA = a; SAs = as; SB = c; SBs = cs;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -421,23 +446,21 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
     if (sizeof(R) == 4) {
         const float2 rng = reinterpret_cast<const float2 *>(P.frange)[f];       // (a_min, a_max) of the filter
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
-        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
-        const bool fast = (rng.x * imin >= 0.0625f) && (rng.y * imax <= 63.f);
+        const float imin = fminf(i0, i1);
+        const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
+        const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
         if (fast) {
             const float2 *bf = reinterpret_cast<const float2 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
-            if (MODEL == 4) {                                   // pairs (T, 0.74 T) of each point, models.py:629-630
-                float S0b, S1b;
-                planck_pair_f32<false>(bf, K2, i0, i0 * (float)(1. / 0.74), nullptr, 0, S0, S0b);
-                if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0b);
-                if (n1) {
-                    planck_pair_f32<false>(bf, K2, i1, i1 * (float)(1. / 0.74), nullptr, 0, S1, S1b);
-                    y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1b);
-                }
-            } else {                                            // pairs (point 0, point 1)
-                if (MODEL == 3) planck_pair_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
-                else planck_pair_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+            if (MODEL == 4) {
+                float S0s, S1s;
+                planck_quad_sc4_f32(bf, 2 * K2, i0, i1, S0, S0s, S1, S1s);
+                if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
+                if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
+            } else {
+                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }

@@ -256,3 +256,142 @@ def test_batched_ensembles_match_single():
         lp = W.oracle_log_posterior(w)
         np.testing.assert_allclose(lnp[i, -1], [lp(p) for p in chain[i, -1]], rtol=1e-9)
     assert 0.05 < b.acceptance_fraction.mean() < 0.95
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The CUDA path against golden vectors produced by the reference's OWN code (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.npz'))
+
+
+def _pf(names):
+    from lightcurve_fitting_b200.filters import filtdict
+    return np.array([filtdict[str(n)] for n in names], dtype=object)
+
+
+def _lc_from(t, f, y, dy, q='lum'):
+    from lightcurve_fitting_b200.synthetic import _PreparedLC
+    return _PreparedLC({'MJD': t, 'filter': f, q: y, 'd' + q: dy})
+
+
+@pytest.mark.parametrize('tag', ['sc_n15', 'sc_n3', 'sc_rw', 'sc2', 'sc3', 'sc4'])
+def test_models_match_reference_golden(tag):
+    from lightcurve_fitting_b200 import models as M
+    m = {'sc_n15': lambda: M.ShockCooling(redshift=0.002), 'sc_n3': lambda: M.ShockCooling(redshift=0.002, n=3.),
+         'sc_rw': lambda: M.ShockCooling(redshift=0.002, RW=True), 'sc2': lambda: M.ShockCooling2(redshift=0.002),
+         'sc3': lambda: M.ShockCooling3(redshift=0.005), 'sc4': lambda: M.ShockCooling4(redshift=0.002)}[tag]()
+    t, f = GOLD['lc/t'], _pf(GOLD['lc/filters'])
+    P, y, dy = GOLD[tag + '/P'], GOLD[tag + '/y'], GOLD[tag + '/dy']
+    want = GOLD[tag + '/point']
+    got = np.array([m(t, f, *p) for p in P])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
+    assert np.array_equal(got == 0., want == 0.)                     # exact zeros before t_0
+    np.testing.assert_allclose(m(GOLD['lc/tgrid'], _pf(GOLD['lc/gridfilters']), *P.T), GOLD[tag + '/grid'], rtol=1e-9)
+    lc = _lc_from(t, f, y, dy, m.output_quantity)
+    np.testing.assert_allclose([m.log_likelihood(lc, p) for p in P], GOLD[tag + '/loglike'], rtol=1e-9)
+    for st in ('relative', 'absolute'):
+        Ps = GOLD[tag + '/Psig_' + st]
+        np.testing.assert_allclose([m.log_likelihood(lc, p, use_sigma=True, sigma_type=st) for p in Ps],
+                                   GOLD[tag + '/loglike_sig_' + st], rtol=1e-9)
+    # FP32 throughput mode: 1e-4 on the log-likelihood
+    m.precision = 'fp32'
+    np.testing.assert_allclose([m.log_likelihood(lc, p) for p in P], GOLD[tag + '/loglike'], rtol=1e-4)
+
+
+@pytest.mark.parametrize('tag,cls', [('cs1', 'CompanionShocking'), ('cs2', 'CompanionShocking2'), ('cs3', 'CompanionShocking3')])
+def test_companion_models_match_reference_golden(tag, cls):
+    from lightcurve_fitting_b200 import models as M
+    t, f, y, dy = GOLD['cs/t'], _pf(GOLD['cs/filters']), GOLD['cs/y'], GOLD['cs/dy']
+    lc = _lc_from(t, f, y, dy)
+    m = getattr(M, cls)(lc, redshift=0.01)
+    P = GOLD[tag + '/P']
+    np.testing.assert_allclose(np.array([m(t, f, *p) for p in P]), GOLD[tag + '/point'], rtol=1e-9)
+    np.testing.assert_allclose(m(GOLD['cs/tgrid'], _pf(GOLD['cs/gridfilters']), *P.T), GOLD[tag + '/grid'], rtol=1e-9)
+    np.testing.assert_allclose([m.log_likelihood(lc, p) for p in P], GOLD[tag + '/loglike'], rtol=1e-9)
+    np.testing.assert_allclose([m.log_likelihood(lc, p, use_sigma=True) for p in GOLD[tag + '/Psig']],
+                               GOLD[tag + '/loglike_sig'], rtol=1e-9)
+    m.precision = 'fp32'
+    np.testing.assert_allclose([m.log_likelihood(lc, p) for p in P], GOLD[tag + '/loglike'], rtol=1e-4)
+
+
+def test_planck_and_synthesis_match_reference_golden():
+    from lightcurve_fitting_b200 import models as M
+    nu, T, R = GOLD['planck/nu'], GOLD['planck/T'], GOLD['planck/R']
+    np.testing.assert_allclose(M.planck_fast(nu, T, R), GOLD['planck/out'], rtol=1e-9)
+    np.testing.assert_allclose(M.planck_fast(nu, T, R, 900.), GOLD['planck/out_cutoff'], rtol=1e-9)
+    np.testing.assert_allclose(M.planck_fast(nu, 12., 3.), GOLD['planck/out_scalar'], rtol=1e-9)
+    names, Tb, Rb = GOLD['bb/names'], GOLD['bb/T'], GOLD['bb/R']
+    for tag, kw in (('plain', {}), ('z', {'z': 0.05}), ('cut', {'z': 0.01, 'cutoff_freq': 700.}), ('ebv', {'ebv': 0.2}),
+                    ('zebv', {'z': 0.02, 'ebv': 0.35})):
+        np.testing.assert_allclose(M.blackbody_to_filters(_pf(names), Tb, Rb, **kw), GOLD['bb/point_' + tag], rtol=1e-9)
+        np.testing.assert_allclose(M.blackbody_to_filters(_pf(names[:3]), Tb, Rb, **kw), GOLD['bb/grid_' + tag], rtol=1e-9)
+    np.testing.assert_allclose(M.blackbody_to_filters(_pf(names[:2]), np.outer(Tb[:3], [1., 1.1]), np.outer(Rb[:3], [1., 0.9])),
+                               GOLD['bb/grid2d'], rtol=1e-9)
+    np.testing.assert_allclose(M.blackbody_to_filters(_pf(names[:3]), Tb[:4], Rb[:4], ebv=np.array([0., 0.1, 0.2, 0.3])),
+                               GOLD['bb/ebv_vec'], rtol=1e-9)
+    with pytest.raises(Exception, match='same shape'):
+        M.blackbody_to_filters(_pf(names[:2]), Tb[:3], Rb[:2])
+    f = _pf(['g'])[0]
+    np.testing.assert_allclose(f.synthesize(M.planck_fast, 14., 0.5), GOLD['bb/point_plain'][2], rtol=1e-9)
+    with pytest.raises(NotImplementedError):
+        f.synthesize(lambda nu, T: nu, 1.)
+
+
+def test_reference_lightcurve_mcmc_chain_reproduced_on_device():
+    """The chain the reference's lightcurve_mcmc produced (golden) is reproduced by the device sampler when it is
+    driven with the same stretch-move draws (recorded by the oracle under the reference's RNG protocol)."""
+    from oracle import reference_port as rp
+    from lightcurve_fitting_b200 import models as M
+    from lightcurve_fitting_b200.fitting import build_problem
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    t, fn = GOLD['lc/t'], GOLD['lc/filters']
+    y, dy = GOLD['sc4/y'], GOLD['sc4/dy']
+    nw, nburn, nsteps = 12, 5, 6
+    # oracle run, recording draws (CPU test test_driver_chain_matches_reference_lightcurve_mcmc pins it to the golden)
+    om = rp.ShockCooling4(redshift=0.002)
+    opri = [rp.UniformPrior(0., 10.), rp.UniformPrior(0., 10.), rp.UniformPrior(0., 100.), rp.UniformPrior(0., 100.),
+            rp.UniformPrior(57460., 57468.5)]
+    lp = rp.make_log_posterior(om, opri, t, W.oracle_filters(fn), y, dy)
+    np.random.seed(12345)
+    rs = np.random.RandomState()
+    rs.set_state(np.random.get_state())
+    ref = rp.StretchReplay(nw, 5, lp, random_state=rs)
+    start = np.random.rand(nw, 5) * (GOLD['mcmc/p_up'] - GOLD['mcmc/p_lo']) + GOLD['mcmc/p_lo']
+    pos, _, _ = ref.run_mcmc(start, nburn, record=True)
+    burn_draws = list(ref.draws)
+    ref.reset()
+    ref.run_mcmc(pos, nsteps, record=True)
+    # device run
+    m = M.ShockCooling4(redshift=0.002)
+    pri = [M.UniformPrior(0., 10.), M.UniformPrior(0., 10.), M.UniformPrior(0., 100.), M.UniformPrior(0., 100.),
+           M.UniformPrior(57460., 57468.5)]
+    prob = build_problem(_lc_from(t, _pf(fn), y, dy), m, pri)
+    s = EnsembleSampler(nw, 5, prob, seed=0)
+    s.run_replay(start, burn_draws)
+    s.reset()
+    s.run_replay(None, ref.draws)
+    np.testing.assert_allclose(s.flatchain, GOLD['mcmc/flatchain'], rtol=1e-9)
+    np.testing.assert_allclose(s.chain, GOLD['mcmc/chain'], rtol=1e-9)
+    np.testing.assert_allclose(s.get_log_prob(), GOLD['mcmc/lnprob'], rtol=1e-9)
+    np.testing.assert_array_equal(s.acceptance_fraction, GOLD['mcmc/acceptance'])
+
+
+def test_lightcurve_mcmc_end_to_end_example():
+    """docs/source/usage.rst:174-200 shaped call on the bundled light curve (ShockCooling4, 5 + 1 parameters)."""
+    from lightcurve_fitting_b200 import lightcurve_mcmc, LC, models as M
+    lc = LC.example().where(MJD_min=57468., MJD_max=57485.)
+    lc = lc[~np.asarray(lc['nondet'].data, bool)]
+    model = M.ShockCooling4(lc)
+    priors = [M.UniformPrior(0., 10.), M.UniformPrior(0., 10.), M.UniformPrior(0., 100.), M.UniformPrior(0., 100.),
+              M.UniformPrior(57468., 57468.7), M.GaussianPrior(0., 10.)]
+    np.random.seed(1)
+    sampler = lightcurve_mcmc(lc, model, priors=priors, p_lo=[0.5, 0.1, 0.1, 1., 57468.5, 0.], p_up=[2., 2., 10., 10., 57468.7, 1.],
+                              nwalkers=40, nsteps=60, nsteps_burnin=60, use_sigma=True, sigma_type='relative')
+    assert model.nparams == 6 and sampler.flatchain.shape == (60 * 40, 6) and sampler.chain.shape == (40, 60, 6)
+    assert np.all(np.isfinite(sampler.get_log_prob())) and 0.02 < sampler.acceptance_fraction.mean() < 0.9
+    fc = sampler.flatchain
+    assert np.all(fc[:, 4] > 57468.) and np.all(fc[:, 4] < 57468.7) and np.all(fc[:, :4] > 0.)
+    # the log-probabilities stored in the chain are the log-posterior of the stored positions
+    np.testing.assert_allclose(sampler.problem.log_posterior(fc[-40:]), sampler.get_log_prob()[-1], rtol=1e-12)
