@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 WALKERS_PER_GPU = 100_000
 NPOINTS = 2000
 MUFU_LANES_PER_CLK_SM = 16
+BALANCED_SAMPLES_PER_CLK_SM = 13.5    # FMA+MUFU balanced bound of the Planck-sample formulation
 SMS = 148
 
 
@@ -48,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -286,7 +287,8 @@ def run_ours(args):
     samples_per_eval = wl.planck_samples_per_eval()
     samples_per_s_gpu = value * samples_per_eval / world
     sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
-    peak_samples = MUFU_LANES_PER_CLK_SM / 2 * SMS * sm_mhz * 1e6
+    peak_samples = BALANCED_SAMPLES_PER_CLK_SM * SMS * sm_mhz * 1e6
+    naive_samples = MUFU_LANES_PER_CLK_SM / 2 * SMS * sm_mhz * 1e6
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -295,11 +297,14 @@ def run_ours(args):
     chain_bytes_per_step = args.walkers * (D + 1) * 8
     hbm_gbs = chain_bytes_per_step * args.steps / (ms * 1e-3) / 1e9
     roofline = {
-        'bound': 'sfu (MUFU ex2+rcp per Planck sample; the path has no dense contraction and ~72 B/walker-step of HBM)',
+        'bound': 'fp32+sfu arithmetic (the path has no dense contraction and moves ~72 B of HBM per walker-step)',
         'kernel': 'lcf::k_pass<%d,%s>' % (3 if MODEL == 'sc3' else 4, 'float' if args.precision == 'fp32' else 'double'),
         'achieved': samples_per_s_gpu / 1e9, 'peak': peak_samples / 1e9, 'unit': 'GPlanck-samples/s',
         'frac': samples_per_s_gpu / peak_samples,
-        'peak_basis': '8 samples/clk/SM x 148 SMs x %.0f MHz (SM clock measured during the timed region)' % sm_mhz,
+        'peak_basis': '13.5 Planck samples/clk/SM (balanced FMA+MUFU bound, SURVEY.md 8(d)) x 148 SMs x %.0f MHz (SM clock '
+                      'measured during the timed region); MEASURED_PEAKS.json has no FP32/SFU entry' % sm_mhz,
+        'frac_vs_naive_mufu': samples_per_s_gpu / naive_samples,
+        'naive_mufu_peak': naive_samples / 1e9,
         'algorithmic_per_unit': '4 FP32 flops + 2 transcendentals per Planck sample; %d samples per log-posterior' % samples_per_eval,
         'fp32_tflops': 4 * samples_per_s_gpu / 1e12,
         'fp32_peak_tflops': 2 * 128 * SMS * sm_mhz * 1e6 / 1e12,
@@ -330,8 +335,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp64'])
     ap.add_argument('--walkers', type=int, default=WALKERS_PER_GPU)

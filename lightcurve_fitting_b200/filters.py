@@ -194,14 +194,14 @@ class Filter:
         Only the built-in ``planck_fast`` spectrum runs on the device; an arbitrary Python callable cannot, and
         there is no CPU fallback in this package.
         """
-        from .models import planck_fast, blackbody_to_filters
+        from .models import planck_fast, _sed_eval
         if spectrum is not planck_fast:
             raise NotImplementedError('only spectrum=planck_fast can be synthesised on the device')
         T, R = args[0], args[1]
         cutoff = args[2] if len(args) > 2 else kwargs.get('cutoff_freq', np.inf)
         T = np.asarray(T, float)
-        out = blackbody_to_filters([self], np.atleast_1d(T), np.atleast_1d(np.asarray(R, float)), z=z,
-                                   cutoff_freq=cutoff, ebv=ebv)[0]
+        R = np.broadcast_to(np.asarray(R, float), T.shape)
+        out = _sed_eval([self], T.ravel(), R.ravel(), z, cutoff, float(ebv))[:, 0]
         return out.reshape(T.shape) if T.ndim else float(out[0])
 
     def __str__(self):

@@ -395,3 +395,62 @@ def test_lightcurve_mcmc_end_to_end_example():
     assert np.all(fc[:, 4] > 57468.) and np.all(fc[:, 4] < 57468.7) and np.all(fc[:, :4] > 0.)
     # the log-probabilities stored in the chain are the log-posterior of the stored positions
     np.testing.assert_allclose(sampler.problem.log_posterior(fc[-40:]), sampler.get_log_prob()[-1], rtol=1e-12)
+
+
+def test_pseudo_and_spectrum_mcmc_and_calculate_bolometric(tmp_path):
+    """bolometric.py drop-ins: pseudo() vs the oracle; spectrum_mcmc / blackbody_mcmc on one epoch; the batched
+    calculate_bolometric on the bundled light curve (79 epochs with >= 3 filters)."""
+    import warnings
+    from oracle import reference_port as rp
+    from lightcurve_fitting_b200 import bolometric as B, models as M, LC
+    T = np.array([6., 11., 25.])
+    R = np.array([3., 1.5, 0.7])
+    np.testing.assert_allclose(B.pseudo(T, R, 0.002), rp.pseudo(T, R, 0.002), rtol=1e-9)
+    np.testing.assert_allclose(B.pseudo(T, R, 0.01, cutoff_freq=800.), rp.pseudo(T, R, 0.01, cutoff_freq=800.), rtol=1e-9)
+    assert B.blackbody_mcmc is B.spectrum_mcmc
+
+    lc = LC.example()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t0, batch = B.calculate_bolometric(lc, outpath=str(tmp_path), res=1., nwalkers=10, burnin_steps=200, steps=100,
+                                           colors=['B-V', 'g-r'], seed=3, return_sampler=True)
+    assert len(t0) == 79
+    for col in ('MJD', 'temp', 'radius', 'L_bol', 'L', 'temp_mcmc', 'radius_mcmc', 'dtemp_mcmc0', 'dtemp_mcmc1', 'L_bol_mcmc',
+                'L_mcmc', 'dL_mcmc0', 'dL_mcmc1', 'L_int', 'npoints', 'B-V', 'd(B-V)', 'filts', 'L_opt', 'lum', 'dtemp0'):
+        assert col in t0.colnames
+    assert np.all(np.diff(t0['MJD'].data) > 0) and np.all(t0['npoints'].data >= 3)
+    ok = np.isfinite(t0['temp'].data)
+    assert ok.sum() >= 70
+    # MCMC medians agree with the least-squares fit within a few times the posterior width
+    dT = np.abs(t0['temp_mcmc'].data - t0['temp'].data)[ok]
+    wT = (t0['dtemp_mcmc0'].data + t0['dtemp_mcmc1'].data)[ok]
+    assert np.median(dT / wT) < 1.0
+    assert np.all(batch.status == 0) and 0.1 < batch.acceptance_fraction.mean() < 0.9
+    chain = batch.get_chain()
+    assert chain.shape == (79, 100, 10, 2)
+    assert np.all(chain[..., 0] > 1.) and np.all(chain[..., 0] < 100.) and np.all(chain[..., 1] > 0.01)
+
+    # one epoch through spectrum_mcmc, against the oracle's posterior statistics on the same data
+    epochs = B.group_by_epoch(lc[np.isfinite(lc['dmag'].data) & (lc['dmag'].data > 0.)], 1.)
+    e = max(epochs, key=len)
+    e.calcFlux(); e = e.bin(delta=np.inf); e.meta = dict(lc.meta); e.calcMag(); e.calcAbsMag(); e.calcLum()
+    priors = [M.UniformPrior(1., 100.), M.LogUniformPrior(0.01, 1000.)]
+    rng = np.random.default_rng(0)
+    sg = rng.normal(size=(20, 2)) * 0.3 + np.array([9., 3.])
+    s = B.spectrum_mcmc(M.planck_fast, e, priors, sg, z=0.002, outpath=str(tmp_path), nwalkers=20, burnin_steps=300, steps=300,
+                        save_chains=True, seed=5)
+    assert s.flatchain.shape == (6000, 2)
+    of = W.oracle_filters([f.name for f in e['filter'].data])
+    om = rp.BlackbodySED(redshift=0.002)
+    lp = rp.make_log_posterior(om, [rp.UniformPrior(1., 100.), rp.LogUniformPrior(0.01, 1000.)], np.zeros(len(e)), of,
+                               e['lum'].data, e['dlum'].data)
+    np.testing.assert_allclose(s.problem.log_posterior(s.flatchain[-5:]), [lp(p) for p in s.flatchain[-5:]], rtol=1e-9)
+    ref = rp.StretchReplay(20, 2, lp, random_state=np.random.RandomState(1))
+    pos, lnp, _ = ref.run_mcmc(sg, 300)
+    ref.reset()
+    ref.run_mcmc(pos, 300, log_prob0=lnp)
+    qa, qb = np.percentile(s.flatchain, [16, 50, 84], axis=0), np.percentile(ref.flatchain, [16, 50, 84], axis=0)
+    width = qb[2] - qb[0]
+    assert np.all(np.abs(qa[1] - qb[1]) < 0.3 * width)
+    with pytest.raises(NotImplementedError):
+        B.spectrum_mcmc(lambda nu, T, R: nu, e, priors, sg)
