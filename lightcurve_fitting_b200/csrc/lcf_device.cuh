@@ -20,7 +20,7 @@
 namespace lcf {
 
 constexpr int kMaxDim = 12;
-constexpr int kNumWC = 8;  // per-walker model constants held in registers
+constexpr int kNumWC = 10; // per-walker model constants held in registers (wc7 = sigma^2 when use_sigma)
 
 enum Mode : int { MODE_MOVE = 0, MODE_LOGPOST = 1, MODE_LOGLIKE = 2, MODE_MODEL = 3 };
 
@@ -199,6 +199,8 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
         s.wc[0] = KT; s.wc[1] = KL;
         s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
         if (MODEL == 3) s.wc[3] = p[5];                   // E(B-V)
+        s.wc[4] = (KT > 0.) ? 1. / KT : 0.;               // 1/T = wc4 t^-eps_T
+        s.wc[5] = (KT > 0.) ? KL / (KT * KT * KT * KT) : 0.;   // L/T^4 = wc5 t^(eps_L - 4 eps_T) exp(-(a t/t_tr)^alpha)
         s.t0 = texp;
     } else if (MODEL == 2) {
         // ShockCooling2.evaluate, models.py:403-407
@@ -206,6 +208,8 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
         s.wc[0] = p[0];
         s.wc[1] = c3sq * p[1] * 1e42;
         s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.wc[4] = (p[0] > 0.) ? 1. / p[0] : 0.;
+        s.wc[5] = (p[0] > 0.) ? s.wc[1] / (p[0] * p[0] * p[0] * p[0]) : 0.;
         s.t0 = p[3];
     } else if (MODEL == 4) {
         // ShockCooling4.temperature_radius, models.py:584-587 (kappa = 1)
@@ -221,6 +225,8 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
         s.wc[1] = c3sq * L_br;
         s.wc[2] = (t_br > 0.) ? -log2(t_br) : Mth<double>::nan();   // log2(ttilde) = log2(t) + wc2
         s.wc[3] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.wc[4] = 1. / (0.97 * s.wc[0]);                    // 1/T on the early branch: wc4 ttilde^(1/3)
+        s.wc[5] = 1. / s.wc[0];                             // 1/T on the late branch:  wc5 ttilde^0.45
         s.t0 = p[4];
     } else if (MODEL == 5 || MODEL == 6 || MODEL == 7) {
         // BaseCompanionShocking.temperature_radius, models.py:752-754 (kappa = 1)
@@ -236,6 +242,7 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
             s.wc[2] = (0.5 * cos(th) + 0.5) * (0.14 * (th * th) - 0.4 * th + 1.);
         }
         s.wc[3] = p[4];                                     // stretch
+        s.wc[8] = (s.wc[0] > 0.) ? 1. / s.wc[0] : 0.;       // 1/T = wc8 t^(74/144)
         if (MODEL == 5) { s.wc[4] = p[5]; s.wc[5] = p[6]; s.wc[6] = p[7]; }   // r_r, r_i, r_U
         else            { s.wc[4] = p[5]; s.wc[5] = p[6]; }                   // dt_U, dt_i
         s.t0 = p[0];
@@ -289,20 +296,31 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec2<R>::type *__res
 // otherwise idle FMA pipe.  Callers guarantee that the four exponents sum to <= 126 (no overflow of the
 // product) and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
 //
-// (a) two blackbodies (points A, B of one walker) x two consecutive samples of the curve
+// (a) two blackbodies (points A, B of one walker) x two consecutive samples of the curve.
+//     TAB = false: `src` is the bank viewed as float4 (a0, w0, a1, w1): one LDS.128 broadcast per 4 samples.
+//     TAB = true (ShockCooling3): `src` is the pair array (a0, a1) (LDS.64 broadcast) and the weights come from the
+//     per-walker reddened table `tab` (conflict-free LDS.64 per lane, stride `ts` float2).
 template <bool TAB>
-__device__ __forceinline__ void planck_quad_f32(const float2 *__restrict__ b, int K2, float iA, float iB,
+__device__ __forceinline__ void planck_quad_f32(const void *__restrict__ src, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
     typedef Mth<float> M;
-    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(b);
+    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(src);
+    const float2 *__restrict__ ap = reinterpret_cast<const float2 *>(src);
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 2
     for (int k = 0; k < K2; ++k) {
-        const float4 s = b4[k];
-        float w0 = s.y, w1 = s.w;
-        if (TAB) { const float2 t = tab[0]; tab += ts; w0 = t.x; w1 = t.y; }
-        const float dA0 = M::ex2(s.x * iA) - 1.f, dB0 = M::ex2(s.x * iB) - 1.f;
-        const float dA1 = M::ex2(s.z * iA) - 1.f, dB1 = M::ex2(s.z * iB) - 1.f;
+        float x0, x1, w0, w1;
+        if (TAB) {
+            const float2 a = *ap++;
+            const float2 t = *tab;
+            tab += ts;
+            x0 = a.x; x1 = a.y; w0 = t.x; w1 = t.y;
+        } else {
+            const float4 s = *b4++;
+            x0 = s.x; w0 = s.y; x1 = s.z; w1 = s.w;
+        }
+        const float dA0 = M::ex2(x0 * iA) - 1.f, dB0 = M::ex2(x0 * iB) - 1.f;
+        const float dA1 = M::ex2(x1 * iA) - 1.f, dB1 = M::ex2(x1 * iB) - 1.f;
         const float p0 = dA0 * dB0, p1 = dA1 * dB1;
         const float r = M::rcp(p0 * p1);
         const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
@@ -381,33 +399,48 @@ __device__ __forceinline__ PointFE<R> front_end(const ProblemDev &P, const LaneW
         return fe;
     }
     const R dt = (R)(tp - w.t0);
-    R T, L;
+    R L;
     if (MODEL >= 1 && MODEL <= 3) {
+        // 4 transcendentals: lg2(t), (a t/t_tr)^alpha, L/T^4, 1/T
         if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }   // t <= t_exp: zero (NaN constants propagate)
-        const R epsT = (R)(2. * P.mc[3] - 0.5), epsL = (R)(-2. * P.mc[4]), alpha = (R)P.mc[2];
+        if (w.wc[1] < (R)0) { fe.amp = M::nan(); return fe; }                  // L < 0: L ** 0.5 is NaN (models.py:268)
+        if (!(w.wc[4] > (R)0)) { fe.amp = (w.wc[0] != w.wc[0]) ? M::nan() : w.wc[1] * (R)0; return fe; }   // T <= 0
+        const R epsT = (R)(2. * P.mc[3] - 0.5), epsA = (R)(-2. * P.mc[4] - 4. * (2. * P.mc[3] - 0.5)), alpha = (R)P.mc[2];
         const R lt = M::lg2(dt);
-        T = w.wc[0] * M::ex2(epsT * lt);
-        const R sup = (w.wc[2] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[2]))) : (R)1;
-        L = w.wc[1] * M::ex2(epsL * lt) * sup;
-    } else if (MODEL == 4) {
+        const R pw_ = (w.wc[2] > -M::inf()) ? M::ex2(alpha * (lt + w.wc[2])) : (R)0;
+        fe.amp = w.wc[5] * M::ex2(epsA * lt - (R)kLog2e * pw_);
+        fe.invT = w.wc[4] * M::ex2(-epsT * lt);
+        fe.state = 1;
+        return fe;
+    }
+    if (MODEL == 4) {
+        // 6 transcendentals: lg2(t), suppression (2), two powers of ttilde for L, one for 1/T (branch selected)
         if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }
         const R A = (R)P.mc[0], alpha = (R)P.mc[2];
         const R l0 = M::lg2(dt);
         const R lt = l0 + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
         const R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (l0 + w.wc[3]))) : (R)1;
         L = w.wc[1] * (M::ex2((R)(-4. / 3.) * lt) + A * sup * M::ex2((R)(-0.17) * lt));
-        T = w.wc[0] * M::mn((R)0.97 * M::ex2((R)(-1. / 3.) * lt), M::ex2((R)(-0.45) * lt));
-    } else {                                                    // Kasen, models.py:752-754
-        if (!(dt > (R)0)) { fe.amp = (R)0; return fe; }
-        const R lt = M::lg2(dt);
-        T = w.wc[0] * M::ex2((R)(-74. / 144.) * lt);
-        L = w.wc[1] * M::ex2((R)(14. / 9.) * lt);               // = R^2 here
+        // T = T_br min(0.97 u^-1/3, u^-0.45): the first branch is the smaller one for log2(u) < -log2(0.97)/(0.45-1/3)
+        const bool early = lt < (R)0.37665701296944757;
+        const R invT = (early ? w.wc[4] : w.wc[5]) * M::ex2((early ? (R)(1. / 3.) : (R)0.45) * lt);
+        if (L < (R)0) { fe.amp = M::nan(); return fe; }
+        if (!(invT > (R)0)) { fe.amp = (invT != invT) ? M::nan() : L * (R)0; return fe; }
+        const R i2 = invT * invT;
+        fe.invT = invT;
+        fe.amp = L * (i2 * i2);
+        fe.state = 1;
+        return fe;
     }
-    if (MODEL <= 4 && L < (R)0) { fe.amp = M::nan(); return fe; }               // L ** 0.5 (models.py:268)
-    if (!(T > (R)0)) { fe.amp = (T != T) ? M::nan() : L * (R)0; return fe; }
-    fe.invT = M::rcp(T);
-    if (MODEL <= 4) { const R i2 = fe.invT * fe.invT; fe.amp = L * (i2 * i2); } else fe.amp = L;
-    fe.state = 1;
+    // Kasen, models.py:752-754: 3 transcendentals
+    if (!(dt > (R)0)) { fe.amp = (R)0; return fe; }
+    if (!(w.wc[8] > (R)0)) { fe.amp = (w.wc[0] != w.wc[0]) ? M::nan() : (R)0; return fe; }
+    {
+        const R lt = M::lg2(dt);
+        fe.invT = w.wc[8] * M::ex2((R)(74. / 144.) * lt);
+        fe.amp = w.wc[1] * M::ex2((R)(14. / 9.) * lt);          // = R^2 here
+        fe.state = 1;
+    }
     return fe;
 }
 
@@ -432,7 +465,7 @@ __device__ __forceinline__ R finish_point(const ProblemDev &P, const LaneWalker<
 template <int MODEL, typename R>
 __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typename Vec2<R>::type *bank, const int *s_foff, int f,
                                                const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, int ts, R &y0, R &y1) {
+                                               const typename Vec2<R>::type *tab, int ts, const float2 *apair, R &y0, R &y1) {
     typedef Mth<R> M;
     typedef typename Vec2<R>::type R2;
     const int k0 = s_foff[f], K2 = (s_foff[f + 1] - k0) >> 1;
@@ -459,7 +492,7 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                if (MODEL == 3) planck_quad_f32<true>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
                 else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
@@ -484,11 +517,12 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
 // shared-memory carve-up (dynamic), identical for the half-step and the chain kernels
 // ---------------------------------------------------------------------------------------
 template <typename R> struct SmemLayout {
-    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
+    size_t off_bank, off_tab, off_ap, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;     // R2[nsamples/2][wpb]          o = (o + 15) & ~(size_t)15;
+        off_ap = o;   o += (tab && sizeof(R) == 4) ? (size_t)nsamples * sizeof(float) : 0;   o = (o + 15) & ~(size_t)15;
         off_foff = o; o += (size_t)(nfilters + 1) * sizeof(int);                  o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
@@ -515,6 +549,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const int D = P.ndim;
     R2 *s_bank = reinterpret_cast<R2 *>(smem + L.off_bank);
     R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
+    float2 *s_ap = reinterpret_cast<float2 *>(smem + L.off_ap);
     int *s_foff = reinterpret_cast<int *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
     double *s_t = reinterpret_cast<double *>(smem + L.off_t);
@@ -599,6 +634,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             v.y = s_bank[2 * kp + 1].y * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
             s_tab[idx] = v;
         }
+        if (sizeof(R) == 4)
+            for (int kp = tid; kp < (P.nsamples >> 1); kp += blockDim.x)
+                s_ap[kp] = make_float2((float)s_bank[2 * kp].x, (float)s_bank[2 * kp + 1].x);
         __syncthreads();
     }
 
@@ -625,7 +663,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             PointFE<R> fb = fa;
             if (two) fb = front_end<MODEL, R>(P, lw, tb);
             R ya, yb;
-            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, ya, yb);
+            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, s_ap, ya, yb);
             ya = finish_point<MODEL, R>(P, lw, tl.z, ta, ya);
             if (two) yb = finish_point<MODEL, R>(P, lw, tl.z, tb, yb);
             if (Mv.mode == MODE_MODEL) {
