@@ -266,8 +266,7 @@ def run_ours(args):
         e2.set_state(pin_in.numpy())                                                  # H2D start positions
         e2.run(args.steps, store=True)
         e2.finish()
-        chain = e2.sampler.get_chain(out=pin_chain.numpy())                           # D2H (own walkers' rows are filled)
-        lnp = e2.sampler.get_log_prob(out=pin_lnp.numpy())
+        chain, lnp = e2.get_own_chain(pin_chain.numpy(), pin_lnp.numpy())                # D2H of this rank's walkers
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device='cuda', dtype=torch.float64)
@@ -276,7 +275,7 @@ def run_ours(args):
         api = 'ShardedEnsemble.set_state(host) + run(store) + get_chain() + get_log_prob() on every rank'
     e2e = {'value': W_total * args.steps / dt, 'unit': 'walker-steps/s',
            'h2d_bytes_per_step': int(pin_in.numel() * 8 / args.steps),
-           'd2h_bytes_per_step': int((pin_chain.numel() + pin_lnp.numel()) * 8 / args.steps),
+           'd2h_bytes_per_step': int(W_total * (D + 1) * 8),
            'api': api}
 
     if rank != 0:

@@ -166,6 +166,9 @@ int  lcf_ensemble_end_step(lcf_ensemble *e, int store);
 int64_t lcf_ensemble_nstored(lcf_ensemble *e);
 int  lcf_ensemble_get_chain(lcf_ensemble *e, double *chain /* [nstored][nwalkers][ndim] */);
 int  lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob /* [nstored][nwalkers] */);
+/* the stored chain of walkers [first, first+count) only: chain[nstored][count][ndim], log_prob[nstored][count]
+   (either may be NULL).  A rank of a sharded ensemble owns the contiguous walkers [2*own_begin, 2*(own_begin+own_count)). */
+int  lcf_ensemble_get_chain_slice(lcf_ensemble *e, int64_t first, int64_t count, double *chain, double *log_prob);
 int  lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted /* [nwalkers] */);
 /* device-side view for the multi-GPU exchange (torch.distributed wraps these raw pointers):
    coords are stored colour-major: rows [0, n0) even walkers, [n0, nwalkers) odd walkers.    */

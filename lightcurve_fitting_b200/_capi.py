@@ -65,6 +65,7 @@ SYMBOLS = [
     ('lcf_ensemble_nstored', C.c_int64, [_vp]),
     ('lcf_ensemble_get_chain', C.c_int, [_vp, _pd]),
     ('lcf_ensemble_get_log_prob', C.c_int, [_vp, _pd]),
+    ('lcf_ensemble_get_chain_slice', C.c_int, [_vp, C.c_int64, C.c_int64, _pd, _pd]),
     ('lcf_ensemble_get_accepted', C.c_int, [_vp, C.POINTER(C.c_int64)]),
     ('lcf_ensemble_device_view', C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

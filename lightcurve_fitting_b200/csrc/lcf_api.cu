@@ -92,6 +92,7 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     TileDev tiles[6];                           // per wpb_log2
     bool tiles_built[6] = {false, false, false, false, false, false};
+    struct { long long Ns = -1; int l = 0, nw = 0, tune = 0; size_t smem = 0; } shape_cache;
     int device = 0;
     ~lcf_problem() {
         for (void *p : allocs) cudaFree(p);
@@ -215,7 +216,15 @@ int build_tiles(lcf_problem *p, int l) {
 }
 
 // launch-shape heuristic: walkers per CTA (2^l) and warps per CTA
+// Launch shape for an active set of Ns walkers: walkers per CTA (2^l) and warps per CTA.
+// The kernel is bound by a per-SM pipe (XU), so what matters is (i) many more CTAs than CTA slots so that the SMs
+// stay balanced (a 1.06-wave grid costs 2x), (ii) lanes not wasted on partial tiles (a tile is 2*32/2^l points of ONE
+// filter), (iii) the per-CTA reddening table (ShockCooling3) fitting in shared memory.
 int choose_shape(lcf_problem *p, long long Ns, int *l_out, int *nw_out, size_t *smem_out) {
+    if (p->shape_cache.Ns == Ns && p->shape_cache.tune == g_tune_wpb * 64 + g_tune_nw) {
+        *l_out = p->shape_cache.l; *nw_out = p->shape_cache.nw; *smem_out = p->shape_cache.smem;
+        return 0;
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     int l = 5;
@@ -223,24 +232,42 @@ int choose_shape(lcf_problem *p, long long Ns, int *l_out, int *nw_out, size_t *
         l = 0;
         while ((1 << l) < g_tune_wpb && l < 5) ++l;
     } else {
-        // enough CTAs to cover the SMs a few times over, otherwise trade walkers/CTA for CTAs
-        while (l > 0 && (Ns + (1 << l) - 1) / (1 << l) < 2LL * sms) --l;
+        // cost model: the busiest SM executes ceil(CTAs / SMs) CTAs back to back, each costing its number of
+        // tiles (a tile = one pass over a transmission curve for <= 64 (walker, point) pairs, XU-bound whatever the
+        // number of active lanes) plus a fixed proposal/accept overhead worth ~16 tiles
+        double best = 1e300;
+        for (int cand = 5; cand >= 0; --cand) {
+            if (smem_bytes(p, 1 << cand, 16) > kSmemMax / 2 && cand > 0) continue;   // keep >= 2 CTAs/SM
+            const int slots = 2 * (32 >> cand);
+            long long tiles = 0;
+            int i = 0;
+            const int N = p->dev.npoints;
+            while (i < N) {
+                int f = p->h_point_filter[i], j = i;
+                while (j < N && p->h_point_filter[j] == f) ++j;
+                tiles += (j - i + slots - 1) / slots;
+                i = j;
+            }
+            const long long ctas = (Ns + (1 << cand) - 1) >> cand;
+            const double cost = (double)((ctas + sms - 1) / sms) * ((double)tiles + 16.);
+            if (cost < best * 0.98) { best = cost; l = cand; }      // prefer more walkers per CTA on near-ties
+        }
     }
-    while (l > 0 && smem_bytes(p, 1 << l, 16) > kSmemMax / 2) --l;   // keep >= 2 CTAs/SM when the table is big
     while (l > 0 && smem_bytes(p, 1 << l, 16) > kSmemMax) --l;
     int rc = build_tiles(p, l);
     if (rc) return rc;
-    int nw = g_tune_nw > 0 ? g_tune_nw : 8;
-    long long ngroups = (Ns + (1 << l) - 1) / (1 << l);
-    if (g_tune_nw <= 0) {
-        if (ngroups >= 16LL * sms) nw = 4;          // plenty of CTAs: small CTAs balance better
-        if (ngroups < 2LL * sms) nw = 16;           // few CTAs: spread the points over more warps
-    }
+    // measured on B200 (cfg2 shape): 16 warps per CTA beat 4 and 8 by 3-6 %; fewer only when there are fewer tiles
+    int nw = g_tune_nw > 0 ? g_tune_nw : 16;
     nw = std::max(1, std::min(nw, std::min(16, p->tiles[l].ntiles)));
     size_t sm = smem_bytes(p, 1 << l, nw);
     if (sm > kSmemMax)
         return fail(LCF_ERR_ARG, "filter bank needs %zu bytes of shared memory (> %zu): too many transmission samples", sm,
                     kSmemMax);
+    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
+    if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
+    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    p->shape_cache.Ns = Ns; p->shape_cache.l = l; p->shape_cache.nw = nw; p->shape_cache.smem = sm;
+    p->shape_cache.tune = g_tune_wpb * 64 + g_tune_nw;
     *l_out = l;
     *nw_out = nw;
     *smem_out = sm;
@@ -256,8 +283,6 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     if (rc) return rc;
     mv.wpb_log2 = l;
     PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
-    if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long ngroups = (mv.Ns + (1 << l) - 1) / (1 << l);
     long long grid = std::min<long long>(ngroups, 1LL << 30);
     k<<<(unsigned)grid, nw * 32, smem, stream>>>(p->dev, p->tiles[l], mv);
@@ -287,7 +312,9 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     const int ns_pad = foff[F];
     typedef typename Vec2<R>::type R2;
     const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
-    std::vector<R2> bank(ns_pad), frange(F);
+    typedef typename Vec4<R>::type R4;
+    std::vector<R2> bank(ns_pad);
+    std::vector<R4> frange(F);
     std::vector<R> kap(ns_pad, (R)0);
     for (int f = 0; f < F; ++f) {
         const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
@@ -302,8 +329,13 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
             mn = std::min(mn, (double)v.x);
             mx = std::max(mx, (double)v.x);
         }
+        double dmax = 0.;
+        for (int k = 0; k + 1 < foff[f + 1] - foff[f]; k += 2)
+            dmax = std::max(dmax, std::fabs((double)bank[foff[f] + k + 1].x - (double)bank[foff[f] + k].x));
         frange[f].x = (R)mn;
         frange[f].y = (R)mx;
+        frange[f].z = (R)dmax;
+        frange[f].w = (R)0;
     }
     std::vector<R> y(N), e1(N), e2(N);
     for (int i = 0; i < N; ++i) {
@@ -821,6 +853,21 @@ int lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob) {
     CUDA_TRY(cudaSetDevice(e->p->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (e->nstored) CUDA_TRY(cudaMemcpy(log_prob, e->d_lnp, sizeof(double) * e->nstored * e->W, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int lcf_ensemble_get_chain_slice(lcf_ensemble *e, int64_t first, int64_t count, double *chain, double *log_prob) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (first < 0 || count < 0 || first + count > e->W) return fail(LCF_ERR_ARG, "walker range out of bounds");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (!e->nstored || !count) return 0;
+    const size_t D = e->D;
+    if (chain)
+        CUDA_TRY(cudaMemcpy2D(chain, count * D * sizeof(double), e->d_chain + first * D, e->W * D * sizeof(double),
+                              count * D * sizeof(double), e->nstored, cudaMemcpyDeviceToHost));
+    if (log_prob)
+        CUDA_TRY(cudaMemcpy2D(log_prob, count * sizeof(double), e->d_lnp + first, e->W * sizeof(double), count * sizeof(double),
+                              e->nstored, cudaMemcpyDeviceToHost));
     return 0;
 }
 int lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted) {

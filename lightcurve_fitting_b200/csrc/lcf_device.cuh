@@ -35,7 +35,7 @@ struct ProblemDev {
     int npoints, nfilters, nsamples, spl_nint;
     const void *bank;      // real2[nsamples]: (alpha*log2(e), w/scale)
     const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
-    const void *frange;    // real2[nfilters]: (min_k, max_k) of bank.x      (FP32 fast-path guards)
+    const void *frange;    // real4[nfilters]: (min a, max a, max |a1-a0| per pair, 0) (FP32 fast-path guards)
     const int *foff;       // [nfilters+1]
     const int *frole;      // [nfilters]
     const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
@@ -137,6 +137,7 @@ template <typename R> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 
+constexpr bool kUseRecurrence = false;
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kLn2 = 0.69314718055994530942;
 
@@ -296,16 +297,30 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec2<R>::type *__res
 // otherwise idle FMA pipe.  Callers guarantee that the four exponents sum to <= 126 (no overflow of the
 // product) and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
 //
+// RECUR: one of the four exponentials of a quad is not a MUFU.EX2 but a recurrence on the FMA pipe,
+//     2^(x1 i) = 2^(x0 i) * 2^((x1-x0) i),   2^y = degree-5 Taylor polynomial in u = y ln2  (|u| <= 0.173: error 4e-8),
+// valid because consecutive samples of a transmission curve are close in frequency.  That balances the two pipes:
+// per Planck sample 1 MUFU (8 XU clk) against ~7.6 issue slots.  Callers check |x1-x0| * i <= 0.25 and x >= 1/2.
+__device__ __forceinline__ float exp2_small_times(float e0, float u) {       // e0 * 2^(u/ln2) - 1
+    float g = fmaf(u, 1.f / 120.f, 1.f / 24.f);
+    g = fmaf(u, g, 1.f / 6.f);
+    g = fmaf(u, g, 0.5f);
+    g = fmaf(u, g, 1.f);
+    g = fmaf(u, g, 1.f);
+    return fmaf(e0, g, -1.f);
+}
+
 // (a) two blackbodies (points A, B of one walker) x two consecutive samples of the curve.
 //     TAB = false: `src` is the bank viewed as float4 (a0, w0, a1, w1): one LDS.128 broadcast per 4 samples.
 //     TAB = true (ShockCooling3): `src` is the pair array (a0, a1) (LDS.64 broadcast) and the weights come from the
 //     per-walker reddened table `tab` (conflict-free LDS.64 per lane, stride `ts` float2).
-template <bool TAB>
+template <bool TAB, bool RECUR>
 __device__ __forceinline__ void planck_quad_f32(const void *__restrict__ src, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
     typedef Mth<float> M;
     const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(src);
     const float2 *__restrict__ ap = reinterpret_cast<const float2 *>(src);
+    const float uB = iB * (float)kLn2;
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 2
     for (int k = 0; k < K2; ++k) {
@@ -319,8 +334,10 @@ __device__ __forceinline__ void planck_quad_f32(const void *__restrict__ src, in
             const float4 s = *b4++;
             x0 = s.x; w0 = s.y; x1 = s.z; w1 = s.w;
         }
-        const float dA0 = M::ex2(x0 * iA) - 1.f, dB0 = M::ex2(x0 * iB) - 1.f;
-        const float dA1 = M::ex2(x1 * iA) - 1.f, dB1 = M::ex2(x1 * iB) - 1.f;
+        const float eB0 = M::ex2(x0 * iB);
+        const float dA0 = M::ex2(x0 * iA) - 1.f, dB0 = eB0 - 1.f;
+        const float dA1 = M::ex2(x1 * iA) - 1.f;
+        const float dB1 = RECUR ? exp2_small_times(eB0, (x1 - x0) * uB) : (M::ex2(x1 * iB) - 1.f);
         const float p0 = dA0 * dB0, p1 = dA1 * dB1;
         const float r = M::rcp(p0 * p1);
         const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
@@ -331,22 +348,40 @@ __device__ __forceinline__ void planck_quad_f32(const void *__restrict__ src, in
     SB = c0 + c1;
 }
 
-// (b) ShockCooling4: two points x (T, 0.74 T) at the same sample (models.py:629-630)
-__device__ __forceinline__ void planck_quad_sc4_f32(const float2 *__restrict__ b, int K, float iA, float iB, float &SA,
+// (b) ShockCooling4: two points x (T, 0.74 T) (models.py:629-630), two consecutive samples per iteration;
+//     each quad = (A, A*, B, B*) at one sample.  RECUR: the two 0.74 T exponentials of the second sample by recurrence.
+template <bool RECUR>
+__device__ __forceinline__ void planck_quad_sc4_f32(const float2 *__restrict__ b, int K2, float iA, float iB, float &SA,
                                                     float &SAs, float &SB, float &SBs) {
     typedef Mth<float> M;
+    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(b);
     const float iAs = iA * (float)(1. / 0.74), iBs = iB * (float)(1. / 0.74);
+    const float uAs = iAs * (float)kLn2, uBs = iBs * (float)kLn2;
     float a = 0.f, as = 0.f, c = 0.f, cs = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        const float2 s = b[k];
-        const float dA = M::ex2(s.x * iA) - 1.f, dAs = M::ex2(s.x * iAs) - 1.f;
-        const float dB = M::ex2(s.x * iB) - 1.f, dBs = M::ex2(s.x * iBs) - 1.f;
-        const float pA = dA * dAs, pB = dB * dBs;
-        const float r = M::rcp(pA * pB);
-        const float tA = s.y * (r * pB), tB = s.y * (r * pA);
-        a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
-        c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
+#pragma unroll 2
+    for (int k = 0; k < K2; ++k) {
+        const float4 s = *b4++;
+        const float eAs0 = M::ex2(s.x * iAs), eBs0 = M::ex2(s.x * iBs);
+        {
+            const float dA = M::ex2(s.x * iA) - 1.f, dAs = eAs0 - 1.f;
+            const float dB = M::ex2(s.x * iB) - 1.f, dBs = eBs0 - 1.f;
+            const float pA = dA * dAs, pB = dB * dBs;
+            const float r = M::rcp(pA * pB);
+            const float tA = s.y * (r * pB), tB = s.y * (r * pA);
+            a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
+            c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
+        }
+        {
+            const float dx = s.z - s.x;
+            const float dA = M::ex2(s.z * iA) - 1.f, dB = M::ex2(s.z * iB) - 1.f;
+            const float dAs = RECUR ? exp2_small_times(eAs0, dx * uAs) : (M::ex2(s.z * iAs) - 1.f);
+            const float dBs = RECUR ? exp2_small_times(eBs0, dx * uBs) : (M::ex2(s.z * iBs) - 1.f);
+            const float pA = dA * dAs, pB = dB * dBs;
+            const float r = M::rcp(pA * pB);
+            const float tA = s.w * (r * pB), tB = s.w * (r * pA);
+            a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
+            c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
+        }
     }
     SA = a; SAs = as; SB = c; SBs = cs;
 }
@@ -477,23 +512,32 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
     const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
     if (!n0 && !n1) return;
     if (sizeof(R) == 4) {
-        const float2 rng = reinterpret_cast<const float2 *>(P.frange)[f];       // (a_min, a_max) of the filter
+        const float4 rng = reinterpret_cast<const float4 *>(P.frange)[f];       // (a_min, a_max, max |a1 - a0| of a pair, 0)
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
-        const float imin = fminf(i0, i1);
+        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
         if (fast) {
+            // measured on B200: the FMA-pipe recurrence variant is ~4 % SLOWER than four MUFU.EX2 per quad (issue-bound),
+            // so it is compiled but disabled; see DESIGN.md section 4
+            const bool recur = kUseRecurrence && (rng.z * imax <= 0.25f) && (rng.x * imin >= 0.5f);
             const float2 *bf = reinterpret_cast<const float2 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
             if (MODEL == 4) {
                 float S0s, S1s;
-                planck_quad_sc4_f32(bf, 2 * K2, i0, i1, S0, S0s, S1, S1s);
+                if (recur) planck_quad_sc4_f32<true>(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                else planck_quad_sc4_f32<false>(bf, K2, i0, i1, S0, S0s, S1, S1s);
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) planck_quad_f32<true>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
-                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                if (MODEL == 3) {
+                    if (recur) planck_quad_f32<true, true>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
+                    else planck_quad_f32<true, false>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
+                } else {
+                    if (recur) planck_quad_f32<false, true>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                    else planck_quad_f32<false, false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                }
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }

@@ -116,6 +116,27 @@ class ShardedEnsemble:
         self.torch.cuda.current_stream().synchronize()
         check(lib().lcf_ensemble_sync(self.sampler.handle))
 
+    def own_walkers(self):
+        """(first, count) of the logical walkers this rank owns (both colours of its slice are contiguous)."""
+        (b0, c0), (b1, c1) = self.own
+        if (b0, c0) != (b1, c1):
+            raise ValueError('uneven colour slices: use gather_chain()')
+        return 2 * b0, 2 * c0
+
+    def get_own_chain(self, out_chain=None, out_log_prob=None):
+        """This rank's part of the stored chain: ([nsteps, count, ndim], [nsteps, count]); D2H of own rows only."""
+        from ._capi import dptr
+        first, count = self.own_walkers()
+        n = lib().lcf_ensemble_nstored(self.sampler.handle)
+        if out_chain is None:
+            out_chain = np.empty((n, count, self.ndim))
+        if out_log_prob is None:
+            out_log_prob = np.empty((n, count))
+        ch = out_chain.reshape(-1)[:n * count * self.ndim].reshape(n, count, self.ndim)
+        lp = out_log_prob.reshape(-1)[:n * count].reshape(n, count)
+        check(lib().lcf_ensemble_get_chain_slice(self.sampler.handle, first, count, dptr(ch), dptr(lp)))
+        return ch, lp
+
     def gather_chain(self):
         """Full stored chain ``[nsteps, nwalkers, ndim]`` on every rank (each rank stored only its walkers)."""
         import torch.distributed as dist

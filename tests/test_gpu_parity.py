@@ -454,3 +454,62 @@ def test_pseudo_and_spectrum_mcmc_and_calculate_bolometric(tmp_path):
     assert np.all(np.abs(qa[1] - qb[1]) < 0.3 * width)
     with pytest.raises(NotImplementedError):
         B.spectrum_mcmc(lambda nu, T, R: nu, e, priors, sg)
+
+
+def test_sharded_ensemble_emulated_two_ranks_matches_single():
+    """The multi-GPU split (rank/world slicing in the C library, RNG keyed by the global walker) emulated on ONE GPU:
+    two rank-local ensembles exchange their colour slices by device copies after every half-step.  The chain must be
+    bit-identical to the single-rank run -- this is what `ShardedEnsemble` does with an NCCL all-gather."""
+    import ctypes as C
+    import torch
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.parallel import _DevArray
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_sc3(npoints=96)
+    prob = wl.device_problem('fp32')
+    nw, nsteps = 64, 6
+    # pin the launch shape: in the FP32 fast path the two points a lane pairs up share one reciprocal, and which
+    # points are paired depends on the tile size (walkers per CTA); with the same shape the chains are bit-identical
+    # across GPU counts, otherwise they agree to FP32 rounding
+    check(lib().lcf_set_tuning(8, 4))
+    p0 = wl.start(nw, np.random.default_rng(2))
+    single = EnsembleSampler(nw, wl.ndim, prob, seed=42)
+    single.run_mcmc(p0, nsteps, skip_initial_state_check=True)
+
+    ranks = [EnsembleSampler(nw, wl.ndim, prob, seed=42, rank=r, world=2) for r in range(2)]
+    views, owns = [], []
+    for s in ranks:
+        s._set_initial(p0, True)
+        dc, dl, st = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n0 = C.c_int64()
+        ob, oc = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        check(lib().lcf_ensemble_device_view(s.handle, C.byref(dc), C.byref(dl), C.byref(st), C.byref(n0), ob, oc))
+        views.append(torch.as_tensor(_DevArray(dc.value, (nw, wl.ndim)), device='cuda'))
+        owns.append(((ob[0], oc[0]), (ob[1], oc[1])))
+    n0 = n0.value
+    check(lib().lcf_ensemble_reserve(ranks[0].handle, nsteps))
+    check(lib().lcf_ensemble_reserve(ranks[1].handle, nsteps))
+    for _ in range(nsteps):
+        for half in (0, 1):
+            for s in ranks:
+                check(lib().lcf_ensemble_half_step(s.handle, half, 1))
+            for s in ranks:
+                check(lib().lcf_ensemble_sync(s.handle))
+            base = n0 if half else 0
+            for r in range(2):                       # "all-gather": copy each rank's updated slice into the other replica
+                b, c = owns[r][half]
+                views[1 - r][base + b:base + b + c] = views[r][base + b:base + b + c]
+            torch.cuda.synchronize()
+        for s in ranks:
+            check(lib().lcf_ensemble_end_step(s.handle, 1))
+    ref = single.get_chain()
+    for r, s in enumerate(ranks):
+        (b, c) = owns[r][0]
+        first, count = 2 * b, 2 * c
+        ch = np.empty((nsteps, count, wl.ndim))
+        lp = np.empty((nsteps, count))
+        check(lib().lcf_ensemble_get_chain_slice(s.handle, first, count, ch.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 lp.ctypes.data_as(C.POINTER(C.c_double))))
+        np.testing.assert_array_equal(ch, ref[:, first:first + count])
+        np.testing.assert_array_equal(lp, single.get_log_prob()[:, first:first + count])
+    check(lib().lcf_set_tuning(0, 0))
