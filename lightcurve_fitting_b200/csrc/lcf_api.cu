@@ -311,31 +311,26 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     for (int f = 0; f < F; ++f) foff[f + 1] = foff[f] + ((d->bank_offsets[f + 1] - d->bank_offsets[f] + 1) & ~1);
     const int ns_pad = foff[F];
     typedef typename Vec2<R>::type R2;
-    const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
     typedef typename Vec4<R>::type R4;
-    std::vector<R2> bank(ns_pad);
-    std::vector<R4> frange(F);
+    const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
+    std::vector<R4> bank(ns_pad / 2);                     // pair records (a0, a1, w0, w1)
+    std::vector<R2> frange(F);
     std::vector<R> kap(ns_pad, (R)0);
     for (int f = 0; f < F; ++f) {
         const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
         double mn = INFINITY, mx = 0.;
         for (int k = 0; k < foff[f + 1] - foff[f]; ++k) {
             const int src = b0 + std::min(k, n - 1);
-            R2 v;
-            v.x = (R)(d->bank_alpha[src] * kLog2e);
-            v.y = (k < n) ? (R)(d->bank_w[src] * wfac) : (R)0;
-            bank[foff[f] + k] = v;
+            const R a = (R)(d->bank_alpha[src] * kLog2e);
+            const R w = (k < n) ? (R)(d->bank_w[src] * wfac) : (R)0;
+            R4 &rec = bank[(foff[f] + k) >> 1];
+            if (k & 1) { rec.y = a; rec.w = w; } else { rec.x = a; rec.z = w; }
             if (d->bank_kappa) kap[foff[f] + k] = (R)(d->bank_kappa[src] * 0.4 * 3.3219280948873623479);   // 0.4*log2(10)
-            mn = std::min(mn, (double)v.x);
-            mx = std::max(mx, (double)v.x);
+            mn = std::min(mn, (double)a);
+            mx = std::max(mx, (double)a);
         }
-        double dmax = 0.;
-        for (int k = 0; k + 1 < foff[f + 1] - foff[f]; k += 2)
-            dmax = std::max(dmax, std::fabs((double)bank[foff[f] + k + 1].x - (double)bank[foff[f] + k].x));
         frange[f].x = (R)mn;
         frange[f].y = (R)mx;
-        frange[f].z = (R)dmax;
-        frange[f].w = (R)0;
     }
     std::vector<R> y(N), e1(N), e2(N);
     for (int i = 0; i < N; ++i) {

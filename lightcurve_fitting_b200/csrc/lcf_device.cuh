@@ -33,9 +33,9 @@ struct PriorDev {
 struct ProblemDev {
     int model, ndim, nmodel, use_sigma;
     int npoints, nfilters, nsamples, spl_nint;
-    const void *bank;      // real2[nsamples]: (alpha*log2(e), w/scale)
+    const void *bank;      // real4[nsamples/2] pair records (a0, a1, w0, w1), a = alpha*log2(e), w = w/scale
     const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
-    const void *frange;    // real4[nfilters]: (min a, max a, max |a1-a0| per pair, 0) (FP32 fast-path guards)
+    const void *frange;    // real2[nfilters]: (min a, max a)                (FP32 fast-path guards)
     const int *foff;       // [nfilters+1]
     const int *frole;      // [nfilters]
     const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
@@ -137,7 +137,6 @@ template <typename R> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 
-constexpr bool kUseRecurrence = false;
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kLn2 = 0.69314718055994530942;
 
@@ -258,10 +257,10 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
 // ---------------------------------------------------------------------------------------
 // Planck x transmission sums:  S(invT) = sum_k w_k / (2^(a_k invT) - 1)
 //
-// Bank layout: every filter is padded to an even number of samples (pad: a = last a, w = 0) and
-// starts on a 16-byte boundary, so the loops below consume sample PAIRS: one LDS.128 broadcast
-// (a0,w0,a1,w1) in FP32.  ShockCooling3's per-walker reddened weights live in a pair table
-// tab2[pair][walker] (one conflict-free LDS.64 per lane per pair).
+// Bank layout: every filter is padded to an even number of samples (pad: a = last a, w = 0); the bank is an array of
+// PAIR records (a0, a1, w0, w1), 16 bytes in FP32: one LDS.128 broadcast feeds four Planck samples (two points).
+// ShockCooling3's per-walker reddened weights live in a pair table tab2[pair][walker] (one conflict-free LDS.64 per
+// lane per pair); the kernel then reads only the (a0, a1) half of the record.
 // ---------------------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ R planck_term_safe(R a, R invT) {
@@ -278,112 +277,81 @@ __device__ __forceinline__ R planck_term_safe(R a, R invT) {
 
 // Careful path (any precision): one blackbody, exact guards.  K2 = number of sample pairs.
 template <typename R, bool TAB>
-__device__ __forceinline__ R planck_sum_safe(const typename Vec2<R>::type *__restrict__ b, int K2, R invT,
+__device__ __forceinline__ R planck_sum_safe(const typename Vec4<R>::type *__restrict__ b, int K2, R invT,
                                              const typename Vec2<R>::type *__restrict__ tab, int ts) {
     R acc0 = 0, acc1 = 0;
     for (int k = 0; k < K2; ++k) {
-        typename Vec2<R>::type s0 = b[2 * k], s1 = b[2 * k + 1];
-        R w0 = s0.y, w1 = s1.y;
+        const typename Vec4<R>::type s = b[k];
+        R w0 = s.z, w1 = s.w;
         if (TAB) { typename Vec2<R>::type t = tab[k * ts]; w0 = t.x; w1 = t.y; }
-        acc0 = fma(w0, planck_term_safe<R>(s0.x, invT), acc0);
-        acc1 = fma(w1, planck_term_safe<R>(s1.x, invT), acc1);
+        acc0 = fma(w0, planck_term_safe<R>(s.x, invT), acc0);
+        acc1 = fma(w1, planck_term_safe<R>(s.y, invT), acc1);
     }
     return acc0 + acc1;
 }
 
-// FP32 fast paths.  Four Planck denominators share ONE MUFU.RCP:
-//     r = 1/(d0 d1 d2 d3);  1/(d0 d1) = r (d2 d3);  1/d0 = d1/(d0 d1) ...
-// i.e. 1.25 MUFU ops per Planck sample (1 EX2 + 1/4 RCP) instead of 2, paid for with FMULs on the
-// otherwise idle FMA pipe.  Callers guarantee that the four exponents sum to <= 126 (no overflow of the
-// product) and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
-//
-// RECUR: one of the four exponentials of a quad is not a MUFU.EX2 but a recurrence on the FMA pipe,
-//     2^(x1 i) = 2^(x0 i) * 2^((x1-x0) i),   2^y = degree-5 Taylor polynomial in u = y ln2  (|u| <= 0.173: error 4e-8),
-// valid because consecutive samples of a transmission curve are close in frequency.  That balances the two pipes:
-// per Planck sample 1 MUFU (8 XU clk) against ~7.6 issue slots.  Callers check |x1-x0| * i <= 0.25 and x >= 1/2.
-__device__ __forceinline__ float exp2_small_times(float e0, float u) {       // e0 * 2^(u/ln2) - 1
-    float g = fmaf(u, 1.f / 120.f, 1.f / 24.f);
-    g = fmaf(u, g, 1.f / 6.f);
-    g = fmaf(u, g, 0.5f);
-    g = fmaf(u, g, 1.f);
-    g = fmaf(u, g, 1.f);
-    return fmaf(e0, g, -1.f);
+// FP32 fast paths (sm_100a).
+//  * Four Planck denominators share ONE MUFU.RCP:  r = 1/(d0 d1 d2 d3);  1/(d0 d1) = r (d2 d3);  1/d0 = d1/(d0 d1):
+//    1.25 MUFU ops per Planck sample (1 EX2 + 1/4 RCP) instead of 2.
+//  * The FP32 arithmetic around them uses Blackwell's packed instructions (FMUL2 / FADD2 / FFMA2 via __fmul2_rn,
+//    __fadd2_rn, __ffma2_rn): the two samples of a pair ride in one 64-bit register pair, halving the issue slots.
+// Callers guarantee that the four exponents sum to <= 126 (no overflow of the product) and that every exponent is
+// >= 1/16 (no cancellation in 2^x - 1).
+__device__ __forceinline__ float2 ex2m1_pair(float2 x) {                 // (2^x.x - 1, 2^x.y - 1)
+    return __fadd2_rn(make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y)), make_float2(-1.f, -1.f));
 }
 
-// (a) two blackbodies (points A, B of one walker) x two consecutive samples of the curve.
-//     TAB = false: `src` is the bank viewed as float4 (a0, w0, a1, w1): one LDS.128 broadcast per 4 samples.
-//     TAB = true (ShockCooling3): `src` is the pair array (a0, a1) (LDS.64 broadcast) and the weights come from the
-//     per-walker reddened table `tab` (conflict-free LDS.64 per lane, stride `ts` float2).
-template <bool TAB, bool RECUR>
-__device__ __forceinline__ void planck_quad_f32(const void *__restrict__ src, int K2, float iA, float iB,
+// (a) two blackbodies (points A, B of one walker) x the two samples of a pair record
+template <bool TAB>
+__device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
-    typedef Mth<float> M;
-    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(src);
-    const float2 *__restrict__ ap = reinterpret_cast<const float2 *>(src);
-    const float uB = iB * (float)kLn2;
-    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+    const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB);
+    float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int k = 0; k < K2; ++k) {
-        float x0, x1, w0, w1;
+        float2 a, w;
         if (TAB) {
-            const float2 a = *ap++;
-            const float2 t = *tab;
+            a = *reinterpret_cast<const float2 *>(b4 + k);
+            w = *tab;
             tab += ts;
-            x0 = a.x; x1 = a.y; w0 = t.x; w1 = t.y;
         } else {
-            const float4 s = *b4++;
-            x0 = s.x; w0 = s.y; x1 = s.z; w1 = s.w;
+            const float4 s = b4[k];
+            a = make_float2(s.x, s.y);
+            w = make_float2(s.z, s.w);
         }
-        const float eB0 = M::ex2(x0 * iB);
-        const float dA0 = M::ex2(x0 * iA) - 1.f, dB0 = eB0 - 1.f;
-        const float dA1 = M::ex2(x1 * iA) - 1.f;
-        const float dB1 = RECUR ? exp2_small_times(eB0, (x1 - x0) * uB) : (M::ex2(x1 * iB) - 1.f);
-        const float p0 = dA0 * dB0, p1 = dA1 * dB1;
-        const float r = M::rcp(p0 * p1);
-        const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
-        a0 = fmaf(t0, dB0, a0); c0 = fmaf(t0, dA0, c0);
-        a1 = fmaf(t1, dB1, a1); c1 = fmaf(t1, dA1, c1);
+        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2));               // (dA0, dA1)
+        const float2 dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 p = __fmul2_rn(dA, dB);                            // (dA0 dB0, dA1 dB1)
+        const float r = Mth<float>::rcp(p.x * p.y);
+        const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));  // (w0/(dA0 dB0), w1/(dA1 dB1))
+        accA = __ffma2_rn(t, dB, accA);                                 // += w/dA
+        accB = __ffma2_rn(t, dA, accB);                                 // += w/dB
     }
-    SA = a0 + a1;
-    SB = c0 + c1;
+    SA = accA.x + accA.y;
+    SB = accB.x + accB.y;
 }
 
-// (b) ShockCooling4: two points x (T, 0.74 T) (models.py:629-630), two consecutive samples per iteration;
-//     each quad = (A, A*, B, B*) at one sample.  RECUR: the two 0.74 T exponentials of the second sample by recurrence.
-template <bool RECUR>
-__device__ __forceinline__ void planck_quad_sc4_f32(const float2 *__restrict__ b, int K2, float iA, float iB, float &SA,
+// (b) ShockCooling4: two points x (T, 0.74 T) (models.py:629-630); each quad = (A, A*, B, B*) at ONE sample, the two
+//     samples of the pair record are processed side by side in the packed lanes (two reciprocals per record).
+__device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float &SA,
                                                     float &SAs, float &SB, float &SBs) {
-    typedef Mth<float> M;
-    const float4 *__restrict__ b4 = reinterpret_cast<const float4 *>(b);
-    const float iAs = iA * (float)(1. / 0.74), iBs = iB * (float)(1. / 0.74);
-    const float uAs = iAs * (float)kLn2, uBs = iBs * (float)kLn2;
-    float a = 0.f, as = 0.f, c = 0.f, cs = 0.f;
+    const float c = (float)(1. / 0.74);
+    const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB), iAs2 = make_float2(iA * c, iA * c), iBs2 = make_float2(iB * c, iB * c);
+    float2 a = make_float2(0.f, 0.f), as = a, bb = a, bs = a;
 #pragma unroll 2
     for (int k = 0; k < K2; ++k) {
-        const float4 s = *b4++;
-        const float eAs0 = M::ex2(s.x * iAs), eBs0 = M::ex2(s.x * iBs);
-        {
-            const float dA = M::ex2(s.x * iA) - 1.f, dAs = eAs0 - 1.f;
-            const float dB = M::ex2(s.x * iB) - 1.f, dBs = eBs0 - 1.f;
-            const float pA = dA * dAs, pB = dB * dBs;
-            const float r = M::rcp(pA * pB);
-            const float tA = s.y * (r * pB), tB = s.y * (r * pA);
-            a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
-            c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
-        }
-        {
-            const float dx = s.z - s.x;
-            const float dA = M::ex2(s.z * iA) - 1.f, dB = M::ex2(s.z * iB) - 1.f;
-            const float dAs = RECUR ? exp2_small_times(eAs0, dx * uAs) : (M::ex2(s.z * iAs) - 1.f);
-            const float dBs = RECUR ? exp2_small_times(eBs0, dx * uBs) : (M::ex2(s.z * iBs) - 1.f);
-            const float pA = dA * dAs, pB = dB * dBs;
-            const float r = M::rcp(pA * pB);
-            const float tA = s.w * (r * pB), tB = s.w * (r * pA);
-            a = fmaf(tA, dAs, a); as = fmaf(tA, dA, as);
-            c = fmaf(tB, dBs, c); cs = fmaf(tB, dB, cs);
-        }
+        const float4 s = b4[k];
+        const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
+        const float2 dA = ex2m1_pair(__fmul2_rn(x, iA2)), dAs = ex2m1_pair(__fmul2_rn(x, iAs2));
+        const float2 dB = ex2m1_pair(__fmul2_rn(x, iB2)), dBs = ex2m1_pair(__fmul2_rn(x, iBs2));
+        const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
+        const float2 pp = __fmul2_rn(pA, pB);
+        const float2 r = make_float2(Mth<float>::rcp(pp.x), Mth<float>::rcp(pp.y));
+        const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
+        a = __ffma2_rn(tA, dAs, a);   as = __ffma2_rn(tA, dA, as);
+        bb = __ffma2_rn(tB, dBs, bb); bs = __ffma2_rn(tB, dB, bs);
     }
-    SA = a; SAs = as; SB = c; SBs = cs;
+    SA = a.x + a.y; SAs = as.x + as.y; SB = bb.x + bb.y; SBs = bs.x + bs.y;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -498,53 +466,45 @@ __device__ __forceinline__ R finish_point(const ProblemDev &P, const LaneWalker<
 
 // Blackbody part of up to two points of one filter for one walker.
 template <int MODEL, typename R>
-__device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typename Vec2<R>::type *bank, const int *s_foff, int f,
+__device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typename Vec4<R>::type *bank, const int *s_foff, int f,
                                                const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, int ts, const float2 *apair, R &y0, R &y1) {
+                                               const typename Vec2<R>::type *tab, int ts, R &y0, R &y1) {
     typedef Mth<R> M;
     typedef typename Vec2<R>::type R2;
-    const int k0 = s_foff[f], K2 = (s_foff[f + 1] - k0) >> 1;
-    const R2 *b = bank + k0;
-    const R2 *tb = tab + (size_t)(k0 >> 1) * ts;
+    typedef typename Vec4<R>::type R4;
+    const int k0 = s_foff[f] >> 1, K2 = (s_foff[f + 1] >> 1) - k0;      // pair records of this filter
+    const R4 *b = bank + k0;
+    const R2 *tb = tab + (size_t)k0 * ts;
     const R c74 = (R)(1. / 0.74), c74_4 = (R)(1. / (0.74 * 0.74 * 0.74 * 0.74));
     y0 = f0.amp;
     y1 = f1.amp;
     const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
     if (!n0 && !n1) return;
     if (sizeof(R) == 4) {
-        const float4 rng = reinterpret_cast<const float4 *>(P.frange)[f];       // (a_min, a_max, max |a1 - a0| of a pair, 0)
+        const float2 rng = reinterpret_cast<const float2 *>(P.frange)[f];       // (a_min, a_max) of the filter
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
-        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
+        const float imin = fminf(i0, i1);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
         if (fast) {
-            // measured on B200: the FMA-pipe recurrence variant is ~4 % SLOWER than four MUFU.EX2 per quad (issue-bound),
-            // so it is compiled but disabled; see DESIGN.md section 4
-            const bool recur = kUseRecurrence && (rng.z * imax <= 0.25f) && (rng.x * imin >= 0.5f);
-            const float2 *bf = reinterpret_cast<const float2 *>(b);
+            const float4 *bf = reinterpret_cast<const float4 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
             if (MODEL == 4) {
                 float S0s, S1s;
-                if (recur) planck_quad_sc4_f32<true>(bf, K2, i0, i1, S0, S0s, S1, S1s);
-                else planck_quad_sc4_f32<false>(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) {
-                    if (recur) planck_quad_f32<true, true>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
-                    else planck_quad_f32<true, false>(apair + (k0 >> 1), K2, i0, i1, tf, ts, S0, S1);
-                } else {
-                    if (recur) planck_quad_f32<false, true>(bf, K2, i0, i1, nullptr, 0, S0, S1);
-                    else planck_quad_f32<false, false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
-                }
+                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }
             return;
         }
     }
-    // careful path (FP64 always; FP32 when 2^x - 1 would cancel or the pair product would overflow)
+    // careful path (FP64 always; FP32 when 2^x - 1 would cancel or the quad product would overflow)
     if (n0) {
         const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f0.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f0.invT, nullptr, 0);
         y0 = f0.amp * S;
@@ -561,12 +521,11 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
 // shared-memory carve-up (dynamic), identical for the half-step and the chain kernels
 // ---------------------------------------------------------------------------------------
 template <typename R> struct SmemLayout {
-    size_t off_bank, off_tab, off_ap, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
+    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;     // R2[nsamples/2][wpb]          o = (o + 15) & ~(size_t)15;
-        off_ap = o;   o += (tab && sizeof(R) == 4) ? (size_t)nsamples * sizeof(float) : 0;   o = (o + 15) & ~(size_t)15;
         off_foff = o; o += (size_t)(nfilters + 1) * sizeof(int);                  o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
@@ -591,9 +550,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int wpb = 1 << Mv.wpb_log2;
     const int D = P.ndim;
-    R2 *s_bank = reinterpret_cast<R2 *>(smem + L.off_bank);
+    typedef typename Vec4<R>::type R4;
+    R4 *s_bank = reinterpret_cast<R4 *>(smem + L.off_bank);
     R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
-    float2 *s_ap = reinterpret_cast<float2 *>(smem + L.off_ap);
     int *s_foff = reinterpret_cast<int *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
     double *s_t = reinterpret_cast<double *>(smem + L.off_t);
@@ -607,7 +566,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // ---- phase 0: stage the packed filter bank with one TMA bulk copy -------------------
     if (need_stage) {
         if (tid == 0) {
-            uint32_t bytes = (uint32_t)((size_t)P.nsamples * sizeof(R2));
+            uint32_t bytes = (uint32_t)((size_t)(P.nsamples >> 1) * sizeof(R4));
             mbar_expect_tx(s_bar, bytes);
             tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
         }
@@ -673,14 +632,12 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         for (int idx = tid; idx < n; idx += blockDim.x) {
             const int kp = idx >> Mv.wpb_log2, wl = idx & (wpb - 1);
             const R ebv = s_wc[wl * kNumWC + 3];
+            const R4 rec = s_bank[kp];
             R2 v;
-            v.x = s_bank[2 * kp].y * Mth<R>::ex2(-ebv * kap[2 * kp]);
-            v.y = s_bank[2 * kp + 1].y * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
+            v.x = rec.z * Mth<R>::ex2(-ebv * kap[2 * kp]);
+            v.y = rec.w * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
             s_tab[idx] = v;
         }
-        if (sizeof(R) == 4)
-            for (int kp = tid; kp < (P.nsamples >> 1); kp += blockDim.x)
-                s_ap[kp] = make_float2((float)s_bank[2 * kp].x, (float)s_bank[2 * kp + 1].x);
         __syncthreads();
     }
 
@@ -707,7 +664,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             PointFE<R> fb = fa;
             if (two) fb = front_end<MODEL, R>(P, lw, tb);
             R ya, yb;
-            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, s_ap, ya, yb);
+            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, ya, yb);
             ya = finish_point<MODEL, R>(P, lw, tl.z, ta, ya);
             if (two) yb = finish_point<MODEL, R>(P, lw, tl.z, tb, yb);
             if (Mv.mode == MODE_MODEL) {
@@ -787,7 +744,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
 // Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
 // ---------------------------------------------------------------------------------------
 template <int MODEL, typename R>
-__global__ void __launch_bounds__(512) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
+__global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << Mv.wpb_log2;
     SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3);
