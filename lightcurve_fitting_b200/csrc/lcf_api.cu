@@ -314,7 +314,7 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     typedef typename Vec4<R>::type R4;
     const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
     std::vector<R4> bank(ns_pad / 2);                     // pair records (a0, a1, w0, w1)
-    std::vector<R2> frange(F);
+    std::vector<R4> frange(F);
     std::vector<R> kap(ns_pad, (R)0);
     for (int f = 0; f < F; ++f) {
         const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
@@ -329,8 +329,12 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
             mn = std::min(mn, (double)a);
             mx = std::max(mx, (double)a);
         }
+        double dmax = 0.;
+        for (int kp = foff[f] >> 1; kp < (foff[f + 1] >> 1); ++kp) dmax = std::max(dmax, std::fabs((double)bank[kp].y - (double)bank[kp].x));
         frange[f].x = (R)mn;
         frange[f].y = (R)mx;
+        frange[f].z = (R)dmax;
+        frange[f].w = (R)0;
     }
     std::vector<R> y(N), e1(N), e2(N);
     for (int i = 0; i < N; ++i) {

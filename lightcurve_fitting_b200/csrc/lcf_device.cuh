@@ -35,7 +35,7 @@ struct ProblemDev {
     int npoints, nfilters, nsamples, spl_nint;
     const void *bank;      // real4[nsamples/2] pair records (a0, a1, w0, w1), a = alpha*log2(e), w = w/scale
     const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
-    const void *frange;    // real2[nfilters]: (min a, max a)                (FP32 fast-path guards)
+    const void *frange;    // real4[nfilters]: (min a, max a, max |a1-a0| within a record, 0) (FP32 fast-path guards)
     const int *foff;       // [nfilters+1]
     const int *frole;      // [nfilters]
     const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
@@ -137,6 +137,8 @@ template <typename R> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 
+constexpr bool kUseRecurrence = false;  // measured on B200 (profiles/r01_ncu_sc3_fp32_recurrence.txt): XU 54 %, FMA pipe 70 % busy, no faster
+constexpr bool kForceRecurrence = false;
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kLn2 = 0.69314718055994530942;
 
@@ -354,6 +356,87 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
     SA = a.x + a.y; SAs = as.x + as.y; SB = bb.x + bb.y; SBs = bs.x + bs.y;
 }
 
+// FP32 fastest path: the second sample of every pair record by RECURRENCE on the FMA pipe instead of MUFU.EX2,
+//     2^(a1 i) = 2^(a0 i) * 2^((a1 - a0) i),      2^y = degree-5 Taylor polynomial in u = y ln 2,
+// accurate to 4e-8 for |u| <= 0.173 because consecutive samples of a transmission curve are close in frequency.
+// Packed by POINT here ((A, B) at the same sample), so the polynomial runs as five FFMA2.  Per record of 4 Planck
+// samples: 2 MUFU.EX2 + 1 MUFU.RCP = 0.75 MUFU per sample (6 XU clk per warp-sample) against ~18 FMA-pipe instructions.
+// Callers check max|a1 - a0| * max(i) * ln2 <= 0.173, every exponent >= 1/2 and the usual overflow bound.
+__device__ __forceinline__ float2 exp2_step_m1(float2 e0, float2 u) {            // e0 * 2^(u / ln2) - 1, element-wise
+    float2 g = __ffma2_rn(u, make_float2(1.f / 120.f, 1.f / 120.f), make_float2(1.f / 24.f, 1.f / 24.f));
+    g = __ffma2_rn(u, g, make_float2(1.f / 6.f, 1.f / 6.f));
+    g = __ffma2_rn(u, g, make_float2(0.5f, 0.5f));
+    g = __ffma2_rn(u, g, make_float2(1.f, 1.f));
+    g = __ffma2_rn(u, g, make_float2(1.f, 1.f));
+    return __ffma2_rn(e0, g, make_float2(-1.f, -1.f));
+}
+
+template <bool TAB>
+__device__ __forceinline__ void planck_quad_rec_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
+                                                    const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
+    const float2 iAB = make_float2(iA, iB), uAB = make_float2(iA * (float)kLn2, iB * (float)kLn2);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int k = 0; k < K2; ++k) {
+        float a0, a1, w0, w1;
+        if (TAB) {
+            const float2 a = *reinterpret_cast<const float2 *>(b4 + k);
+            const float2 w = *tab;
+            tab += ts;
+            a0 = a.x; a1 = a.y; w0 = w.x; w1 = w.y;
+        } else {
+            const float4 s = b4[k];
+            a0 = s.x; a1 = s.y; w0 = s.z; w1 = s.w;
+        }
+        const float2 x0 = __fmul2_rn(iAB, make_float2(a0, a0));
+        const float2 e0 = make_float2(Mth<float>::ex2(x0.x), Mth<float>::ex2(x0.y));
+        const float2 d0 = __fadd2_rn(e0, make_float2(-1.f, -1.f));                 // (dA0, dB0)
+        const float dl = a1 - a0;
+        const float2 d1 = exp2_step_m1(e0, __fmul2_rn(uAB, make_float2(dl, dl)));  // (dA1, dB1)
+        const float p0 = d0.x * d0.y, p1 = d1.x * d1.y;
+        const float r = Mth<float>::rcp(p0 * p1);
+        const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
+        acc0 = __ffma2_rn(make_float2(t0, t0), d0, acc0);                           // .x += w0/dB0, .y += w0/dA0
+        acc1 = __ffma2_rn(make_float2(t1, t1), d1, acc1);
+    }
+    SA = acc0.y + acc1.y;
+    SB = acc0.x + acc1.x;
+}
+
+__device__ __forceinline__ void planck_quad_rec_sc4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float &SA,
+                                                        float &SAs, float &SB, float &SBs) {
+    const float c = (float)(1. / 0.74), l2 = (float)kLn2;
+    const float2 PA = make_float2(iA, iA * c), PB = make_float2(iB, iB * c);          // (T, 0.74 T) of point A, of point B
+    const float2 UA = make_float2(iA * l2, iA * c * l2), UB = make_float2(iB * l2, iB * c * l2);
+    float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int k = 0; k < K2; ++k) {
+        const float4 s = b4[k];
+        const float2 xA = __fmul2_rn(PA, make_float2(s.x, s.x)), xB = __fmul2_rn(PB, make_float2(s.x, s.x));
+        const float2 eA = make_float2(Mth<float>::ex2(xA.x), Mth<float>::ex2(xA.y));
+        const float2 eB = make_float2(Mth<float>::ex2(xB.x), Mth<float>::ex2(xB.y));
+        const float2 dA0 = __fadd2_rn(eA, make_float2(-1.f, -1.f)), dB0 = __fadd2_rn(eB, make_float2(-1.f, -1.f));
+        const float dl = s.y - s.x;
+        const float2 dA1 = exp2_step_m1(eA, __fmul2_rn(UA, make_float2(dl, dl)));
+        const float2 dB1 = exp2_step_m1(eB, __fmul2_rn(UB, make_float2(dl, dl)));
+        {
+            const float pA = dA0.x * dA0.y, pB = dB0.x * dB0.y;
+            const float r = Mth<float>::rcp(pA * pB);
+            const float tA = s.z * (r * pB), tB = s.z * (r * pA);
+            accA = __ffma2_rn(make_float2(tA, tA), dA0, accA);                      // .x += w/dAs, .y += w/dA
+            accB = __ffma2_rn(make_float2(tB, tB), dB0, accB);
+        }
+        {
+            const float pA = dA1.x * dA1.y, pB = dB1.x * dB1.y;
+            const float r = Mth<float>::rcp(pA * pB);
+            const float tA = s.w * (r * pB), tB = s.w * (r * pA);
+            accA = __ffma2_rn(make_float2(tA, tA), dA1, accA);
+            accB = __ffma2_rn(make_float2(tB, tB), dB1, accB);
+        }
+    }
+    SA = accA.y; SAs = accA.x; SB = accB.y; SBs = accB.x;
+}
+
 // ---------------------------------------------------------------------------------------
 // per-lane walker state in registers
 // ---------------------------------------------------------------------------------------
@@ -481,23 +564,30 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
     const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
     if (!n0 && !n1) return;
     if (sizeof(R) == 4) {
-        const float2 rng = reinterpret_cast<const float2 *>(P.frange)[f];       // (a_min, a_max) of the filter
+        const float4 rng = reinterpret_cast<const float4 *>(P.frange)[f];       // (a_min, a_max, max |a1 - a0| in a record, 0)
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
-        const float imin = fminf(i0, i1);
+        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
         if (fast) {
+            const bool rec = kUseRecurrence && (kForceRecurrence || ((rng.z * imax <= (float)(0.173 / kLn2)) && (rng.x * imin >= 0.5f)));
             const float4 *bf = reinterpret_cast<const float4 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
             if (MODEL == 4) {
                 float S0s, S1s;
-                planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                if (rec) planck_quad_rec_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                else planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
-                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                if (MODEL == 3) {
+                    if (rec) planck_quad_rec_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                    else planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
+                } else {
+                    if (rec) planck_quad_rec_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                    else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
+                }
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }
