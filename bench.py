@@ -195,8 +195,8 @@ def run_ours(args):
     from lightcurve_fitting_b200.parallel import ShardedEnsemble
     from lightcurve_fitting_b200.sampler import EnsembleSampler
     _capi.check(_capi.lib().lcf_set_device(local))
-    if args.wpb or args.nw:
-        _capi.check(_capi.lib().lcf_set_tuning(args.wpb, args.nw))
+    if args.wpb or args.nw or args.cluster:
+        _capi.check(_capi.lib().lcf_set_tuning_ex(args.wpb, args.nw, args.cluster))
 
     wl = workload(device_truth, args.npoints)
     prob = wl.device_problem(args.precision)
@@ -342,6 +342,7 @@ def main():
     ap.add_argument('--npoints', type=int, default=NPOINTS)
     ap.add_argument('--model', default='sc3', choices=['sc3', 'sc4'])
     ap.add_argument('--wpb', type=int, default=0)
+    ap.add_argument('--cluster', type=int, default=0)
     ap.add_argument('--nw', type=int, default=0)
     ap.add_argument('--cpu-budget', type=float, default=15.)
     ap.add_argument('--no-cpu', action='store_true')

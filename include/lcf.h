@@ -201,6 +201,9 @@ int  lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches);
 /* launch-shape overrides for tuning (0 = heuristic): walkers per CTA (power of two <= 32)
    and warps per CTA.                                                                       */
 int  lcf_set_tuning(int walkers_per_cta, int warps_per_cta);
+/* same, plus the thread-block-cluster size (power of two <= 8): the CTAs of a cluster share one
+   walker group and split its light curve between them (small ensembles on many SMs).          */
+int  lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblcf_b200.so')
+# LCF_B200_LIB: developer override used by tools/microbench to time experimental builds of the SAME library
+LIB_PATH = os.environ.get('LCF_B200_LIB') or os.path.join(_HERE, 'liblcf_b200.so')
 
 LCF_ERR_ARG, LCF_ERR_CUDA, LCF_ERR_NAN, LCF_ERR_STATE, LCF_ERR_NWALKERS = -1, -2, -3, -4, -5
 MODEL_IDS = {'ShockCooling': 1, 'ShockCooling2': 2, 'ShockCooling3': 3, 'ShockCooling4': 4,
@@ -47,6 +48,7 @@ SYMBOLS = [
     ('lcf_device_count', C.c_int, []),
     ('lcf_set_device', C.c_int, [C.c_int]),
     ('lcf_set_tuning', C.c_int, [C.c_int, C.c_int]),
+    ('lcf_set_tuning_ex', C.c_int, [C.c_int, C.c_int, C.c_int]),
     ('lcf_problem_create', C.c_int, [C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     ('lcf_problem_destroy', None, [_vp]),
     ('lcf_model_eval', C.c_int, [_vp, C.c_int64, _pd, _pd]),

@@ -20,7 +20,7 @@ using namespace lcf;
 namespace {
 
 thread_local std::string g_err;
-int g_tune_wpb = 0, g_tune_nw = 0;
+int g_tune_wpb = 0, g_tune_nw = 0, g_tune_cluster = 0;
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -92,7 +92,8 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     TileDev tiles[6];                           // per wpb_log2
     bool tiles_built[6] = {false, false, false, false, false, false};
-    struct { long long Ns = -1; int l = 0, nw = 0, tune = 0; size_t smem = 0; } shape_cache;
+    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1; size_t smem = 0; } shape_cache;
+    double mean_samples = 0.;                   // mean transmission samples per photometry point
     int device = 0;
     ~lcf_problem() {
         for (void *p : allocs) cudaFree(p);
@@ -158,6 +159,12 @@ namespace {
 typedef void (*PassKernel)(const ProblemDev, const TileDev, const MoveDev);
 typedef void (*ChainKernel)(const BatchDev);
 
+// LCF_DEV_ONLY_MODEL=<id> (tools/microbench builds): instantiate the FP32 half-step kernel of one model only, so that a
+// kernel experiment compiles in seconds.  Never defined for the shipped library.
+#ifdef LCF_DEV_ONLY_MODEL
+template <typename R> PassKernel pass_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_pass<LCF_DEV_ONLY_MODEL, R> : nullptr; }
+template <typename R> ChainKernel chain_kernel_for(int) { return nullptr; }
+#else
 template <typename R> PassKernel pass_kernel_for(int model) {
     switch (model) {
         case 1: return k_pass<1, R>;
@@ -184,6 +191,7 @@ template <typename R> ChainKernel chain_kernel_for(int model) {
     }
     return nullptr;
 }
+#endif
 
 size_t smem_bytes(const lcf_problem *p, int wpb, int nw) {
     if (p->precision == LCF_PRECISION_FP32)
@@ -215,78 +223,109 @@ int build_tiles(lcf_problem *p, int l) {
     return 0;
 }
 
-// launch-shape heuristic: walkers per CTA (2^l) and warps per CTA
-// Launch shape for an active set of Ns walkers: walkers per CTA (2^l) and warps per CTA.
-// The kernel is bound by a per-SM pipe (XU), so what matters is (i) many more CTAs than CTA slots so that the SMs
-// stay balanced (a 1.06-wave grid costs 2x), (ii) lanes not wasted on partial tiles (a tile is 2*32/2^l points of ONE
-// filter), (iii) the per-CTA reddening table (ShockCooling3) fitting in shared memory.
-int choose_shape(lcf_problem *p, long long Ns, int *l_out, int *nw_out, size_t *smem_out) {
-    if (p->shape_cache.Ns == Ns && p->shape_cache.tune == g_tune_wpb * 64 + g_tune_nw) {
-        *l_out = p->shape_cache.l; *nw_out = p->shape_cache.nw; *smem_out = p->shape_cache.smem;
+// Launch shape for an active set of Ns walkers: walkers per CTA (2^l), warps per CTA and cluster size S (CTAs that
+// share one walker group and split its light curve chunk-wise).  A small cost model in SM clocks picks it:
+//   * the kernel is bound by a per-SM pipe (XU in FP32, FP64 FMA in FP64), so the busiest SM decides: CTAs are dealt
+//     to SMs in waves of `occ` CTAs per SM and a wave costs  max(pipe time of its CTAs, latency of one warp's tiles)
+//     plus the serial FP64 proposal/setup phase;
+//   * a tile is always 64 (walker, point) pairs of ONE filter, so partial tiles (few points per filter, few walkers)
+//     waste lanes: the tile count per group grows as wpb shrinks only when the light curve has enough points;
+//   * the per-CTA tables (ShockCooling3 reddening table, front-end buffers) must fit in shared memory.
+int count_tiles(const lcf_problem *p, int l) {
+    const int slots = 2 * (32 >> l), N = p->dev.npoints;
+    int tiles = 0, i = 0;
+    while (i < N) {
+        int f = p->h_point_filter[i], j = i;
+        while (j < N && p->h_point_filter[j] == f) ++j;
+        tiles += (j - i + slots - 1) / slots;
+        i = j;
+    }
+    return tiles;
+}
+
+struct Shape { int l, nw, cluster; size_t smem; };
+
+int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
+    const int tune = (g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster;
+    if (p->shape_cache.Ns == Ns && p->shape_cache.tune == tune) {
+        out->l = p->shape_cache.l; out->nw = p->shape_cache.nw; out->cluster = p->shape_cache.cluster; out->smem = p->shape_cache.smem;
         return 0;
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-    int l = 5;
-    if (g_tune_wpb > 0) {
-        l = 0;
-        while ((1 << l) < g_tune_wpb && l < 5) ++l;
-    } else {
-        // cost model: the busiest SM executes ceil(CTAs / SMs) CTAs back to back, each costing its number of
-        // tiles (a tile = one pass over a transmission curve for <= 64 (walker, point) pairs, XU-bound whatever the
-        // number of active lanes) plus a fixed proposal/accept overhead worth ~16 tiles
-        double best = 1e300;
-        for (int cand = 5; cand >= 0; --cand) {
-            if (smem_bytes(p, 1 << cand, 16) > kSmemMax / 2 && cand > 0) continue;   // keep >= 2 CTAs/SM
-            const int slots = 2 * (32 >> cand);
-            long long tiles = 0;
-            int i = 0;
-            const int N = p->dev.npoints;
-            while (i < N) {
-                int f = p->h_point_filter[i], j = i;
-                while (j < N && p->h_point_filter[j] == f) ++j;
-                tiles += (j - i + slots - 1) / slots;
-                i = j;
+    const bool f32 = p->precision == LCF_PRECISION_FP32;
+    const double nbb = p->dev.model == 4 ? 2. : 1.;
+    const double K = std::max(1., p->mean_samples) * nbb;            // Planck samples per (walker, point)
+    const double pipe_tile = 64. * (f32 ? (1.0 * K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
+    const double lat_tile = (f32 ? 28. : 220.) * K + 400.;           // clocks one warp needs for a tile on its own
+    const double fixed = 25000.;                                     // proposal + priors + FP64 model constants
+    double best = 1e300;
+    Shape bs = {5, 16, 1, 0};
+    for (int l = 5; l >= 0; --l) {
+        if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
+        const int ntiles = count_tiles(p, l);
+        const long long groups = (Ns + (1 << l) - 1) >> l;
+        const int nw_cand[5] = {16, 8, 4, 2, g_tune_nw};   // candidates; the last entry is the override
+        for (int ci = (g_tune_nw > 0 ? 4 : 0); ci < (g_tune_nw > 0 ? 5 : 4); ++ci) {
+            const int nw = nw_cand[ci];
+            const size_t sm = smem_bytes(p, 1 << l, nw);
+            if (sm > kSmemMax) continue;
+            int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
+            occ = std::max(1, std::min(occ, 16));
+            for (int S = 1; S <= kMaxCluster; S <<= 1) {
+                if (g_tune_cluster > 0 && S != g_tune_cluster) continue;
+                if (S > 1 && (long long)nw * S > 2LL * ntiles && g_tune_cluster == 0) break;    // nothing left to split
+                const double tiles_warp = (double)((ntiles + nw * S - 1) / (nw * S));
+                const double tiles_cta = std::min<double>(ntiles, tiles_warp * nw);
+                const long long ctas = groups * S;
+                const long long per_wave = (long long)sms * occ;
+                const long long full = ctas / per_wave, rem = ctas - full * per_wave;
+                auto wave = [&](double cps) { return std::max(cps * tiles_cta * pipe_tile, tiles_warp * lat_tile) + fixed; };
+                double cost = (double)full * wave(occ);
+                if (rem > 0) cost += wave(std::ceil((double)rem / sms));
+                if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; }
             }
-            const long long ctas = (Ns + (1 << cand) - 1) >> cand;
-            const double cost = (double)((ctas + sms - 1) / sms) * ((double)tiles + 16.);
-            if (cost < best * 0.98) { best = cost; l = cand; }      // prefer more walkers per CTA on near-ties
         }
     }
-    while (l > 0 && smem_bytes(p, 1 << l, 16) > kSmemMax) --l;
-    int rc = build_tiles(p, l);
+    if (best >= 1e300) {
+        if (g_tune_nw > 16 || g_tune_wpb > 32) return fail(LCF_ERR_ARG, "bad tuning override");
+        return fail(LCF_ERR_ARG, "filter bank needs more than %zu bytes of shared memory: too many transmission samples", kSmemMax);
+    }
+    int rc = build_tiles(p, bs.l);
     if (rc) return rc;
-    // measured on B200 (cfg2 shape): 16 warps per CTA beat 4 and 8 by 3-6 %; fewer only when there are fewer tiles
-    int nw = g_tune_nw > 0 ? g_tune_nw : 16;
-    nw = std::max(1, std::min(nw, std::min(16, p->tiles[l].ntiles)));
-    size_t sm = smem_bytes(p, 1 << l, nw);
-    if (sm > kSmemMax)
-        return fail(LCF_ERR_ARG, "filter bank needs %zu bytes of shared memory (> %zu): too many transmission samples", sm,
-                    kSmemMax);
-    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
+    PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
     if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
-    if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    p->shape_cache.Ns = Ns; p->shape_cache.l = l; p->shape_cache.nw = nw; p->shape_cache.smem = sm;
-    p->shape_cache.tune = g_tune_wpb * 64 + g_tune_nw;
-    *l_out = l;
-    *nw_out = nw;
-    *smem_out = sm;
+    if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
+    p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
+    p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
+    *out = bs;
     return 0;
 }
 
 int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long long *launches) {
     MoveDev mv = mv_in;
     if (mv.Ns <= 0) return 0;
-    int l, nw;
-    size_t smem;
-    int rc = choose_shape(p, mv.Ns, &l, &nw, &smem);
+    Shape sh;
+    int rc = choose_shape(p, mv.Ns, &sh);
     if (rc) return rc;
-    mv.wpb_log2 = l;
+    mv.wpb_log2 = sh.l;
     PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
-    long long ngroups = (mv.Ns + (1 << l) - 1) / (1 << l);
-    long long grid = std::min<long long>(ngroups, 1LL << 30);
-    k<<<(unsigned)grid, nw * 32, smem, stream>>>(p->dev, p->tiles[l], mv);
-    CUDA_TRY(cudaGetLastError());
+    const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
+    const long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(clusters * sh.cluster), 1, 1);
+    cfg.blockDim = dim3((unsigned)(sh.nw * 32), 1, 1);
+    cfg.dynamicSmemBytes = sh.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)sh.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sh.cluster > 1 ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], mv));
     if (launches) ++*launches;
     return 0;
 }
@@ -314,7 +353,7 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     typedef typename Vec4<R>::type R4;
     const double wfac = (d->model_id == LCF_MODEL_SHOCKCOOLING3 ? consts().c4 : 1.) / scale;
     std::vector<R4> bank(ns_pad / 2);                     // pair records (a0, a1, w0, w1)
-    std::vector<R4> frange(F);
+    std::vector<int4> finfo(F);
     std::vector<R> kap(ns_pad, (R)0);
     for (int f = 0; f < F; ++f) {
         const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
@@ -329,36 +368,33 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
             mn = std::min(mn, (double)a);
             mx = std::max(mx, (double)a);
         }
-        double dmax = 0.;
-        for (int kp = foff[f] >> 1; kp < (foff[f + 1] >> 1); ++kp) dmax = std::max(dmax, std::fabs((double)bank[kp].y - (double)bank[kp].x));
-        frange[f].x = (R)mn;
-        frange[f].y = (R)mx;
-        frange[f].z = (R)dmax;
-        frange[f].w = (R)0;
+        const float fmn = (float)mn, fmx = (float)mx;       // FP32 fast-path guards (unused in FP64 mode)
+        int bmn, bmx;
+        memcpy(&bmn, &fmn, 4);
+        memcpy(&bmx, &fmx, 4);
+        finfo[f] = make_int4(foff[f] >> 1, (foff[f + 1] - foff[f]) >> 1, bmn, bmx);
     }
-    std::vector<R> y(N), e1(N), e2(N);
+    std::vector<R4> obs(N);
     for (int i = 0; i < N; ++i) {
-        y[i] = (R)(d->y[i] / scale);
+        obs[i].x = (R)(d->y[i] / scale);
         if (d->use_sigma) {
             double dys = d->dy[i] / scale;
             double su = (d->sigma_type == 0 ? d->dy[i] : d->sigma_unit_abs) / scale;
-            e1[i] = (R)(dys * dys);
-            e2[i] = (R)(su * su);
+            obs[i].y = (R)(dys * dys);
+            obs[i].z = (R)(su * su);
         } else {
-            e1[i] = (R)(scale / d->dy[i]);
-            e2[i] = (R)0;
+            obs[i].y = (R)(scale / d->dy[i]);
+            obs[i].z = (R)0;
         }
+        obs[i].w = (R)0;
     }
     void *dp;
     int rc;
     ProblemDev &P = p->dev;
     if ((rc = upload(bank, &dp))) return rc;  p->allocs.push_back(dp); P.bank = dp;
     if ((rc = upload(kap, &dp))) return rc;   p->allocs.push_back(dp); P.kappa = dp;
-    if ((rc = upload(frange, &dp))) return rc; p->allocs.push_back(dp); P.frange = dp;
-    if ((rc = upload(foff, &dp))) return rc;  p->allocs.push_back(dp); P.foff = reinterpret_cast<const int *>(dp);
-    if ((rc = upload(y, &dp))) return rc;     p->allocs.push_back(dp); P.y = dp;
-    if ((rc = upload(e1, &dp))) return rc;    p->allocs.push_back(dp); P.e1 = dp;
-    if ((rc = upload(e2, &dp))) return rc;    p->allocs.push_back(dp); P.e2 = dp;
+    if ((rc = upload(finfo, &dp))) return rc; p->allocs.push_back(dp); P.finfo = reinterpret_cast<const int4 *>(dp);
+    if ((rc = upload(obs, &dp))) return rc;   p->allocs.push_back(dp); P.obs = dp;
     P.nsamples = ns_pad;
     if (d->sifto_coef && d->sifto_nknots >= 2) {
         const int nint = d->sifto_nknots - 1;
@@ -412,6 +448,26 @@ int lcf_set_tuning(int walkers_per_cta, int warps_per_cta) {
     if (warps_per_cta < 0 || warps_per_cta > 16) return fail(LCF_ERR_ARG, "warps_per_cta must be in [0, 16]");
     g_tune_wpb = walkers_per_cta;
     g_tune_nw = warps_per_cta;
+    g_tune_cluster = 0;
+    return 0;
+}
+
+#ifdef LCF_X_TIMING
+int lcf_debug_phase_clocks(unsigned long long *out) {   // experiment builds only: read and reset the per-phase clock sums
+    unsigned long long z[8] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(z));
+    cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+    return 0;
+}
+#endif
+
+int lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size) {
+    if (cluster_size < 0 || cluster_size > kMaxCluster || (cluster_size & (cluster_size - 1)))
+        return fail(LCF_ERR_ARG, "cluster_size must be 0 or a power of two <= %d", kMaxCluster);
+    int rc = lcf_set_tuning(walkers_per_cta, warps_per_cta);
+    if (rc) return rc;
+    g_tune_cluster = cluster_size;
     return 0;
 }
 
@@ -458,6 +514,16 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
     P.kB = consts().kB;
     P.c3sq = consts().c3 * consts().c3;
     for (int i = 0; i < 16; ++i) P.mc[i] = d->model_consts[i];
+    for (int i = 0; i < 4; ++i) P.dk[i] = 0.;
+    if (d->model_id >= 1 && d->model_id <= 3) {          // T ~ t^eps_T, L/T^4 ~ t^(eps_L - 4 eps_T), suppression exponent alpha
+        P.dk[0] = 2. * P.mc[3] - 0.5;
+        P.dk[1] = -2. * P.mc[4] - 4. * (2. * P.mc[3] - 0.5);
+        P.dk[2] = P.mc[2];
+    } else if (d->model_id == 4) {
+        P.dk[0] = P.mc[0];
+        P.dk[1] = P.mc[2];
+    }
+    for (int i = 0; i < 4; ++i) P.fk[i] = (float)P.dk[i];
     for (int i = 0; i < d->ndim; ++i) {
         P.prior.kind[i] = d->prior_kind[i];
         P.prior.pmin[i] = d->prior_min[i];
@@ -494,6 +560,23 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
     p->allocs.push_back(dp); P.frole = reinterpret_cast<const int *>(dp);
     if ((rc = upload(t, &dp))) { delete p; return rc; }
     p->allocs.push_back(dp); P.t = reinterpret_cast<const double *>(dp);
+    {   // FP32 epochs: t - tref as hi + lo floats (see LaneWalker<float>), tref = first finite epoch
+        P.tref = 0.;
+        for (int i = 0; i < d->npoints; ++i) if (std::isfinite(d->t[i])) { P.tref = d->t[i]; break; }
+        std::vector<float2> t32(d->npoints);
+        for (int i = 0; i < d->npoints; ++i) {
+            const double r = d->t[i] - P.tref;
+            t32[i].x = (float)r;
+            t32[i].y = (float)(r - (double)t32[i].x);
+        }
+        if ((rc = upload(t32, &dp))) { delete p; return rc; }
+        p->allocs.push_back(dp); P.t32 = reinterpret_cast<const float2 *>(dp);
+        if ((rc = upload(p->h_point_filter, &dp))) { delete p; return rc; }
+        p->allocs.push_back(dp); P.pfilt = reinterpret_cast<const int *>(dp);
+        double sk = 0.;
+        for (int i = 0; i < d->npoints; ++i) sk += d->bank_offsets[d->point_filter[i] + 1] - d->bank_offsets[d->point_filter[i]];
+        p->mean_samples = sk / d->npoints;
+    }
     rc = (d->precision == LCF_PRECISION_FP32) ? build_problem_arrays<float>(d, p, scale) : build_problem_arrays<double>(d, p, scale);
     if (rc) { delete p; return rc; }
     *out = p;

@@ -19,6 +19,15 @@
 
 namespace lcf {
 
+#ifdef LCF_X_TIMING   // experiment builds: per-phase SM clocks summed over CTAs (thread 0), see tools/microbench
+__device__ unsigned long long g_phase_clk[8];
+#define LCF_TICK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#define LCF_TICK_INIT long long _t0 = clock64()
+#else
+#define LCF_TICK(i) do {} while (0)
+#define LCF_TICK_INIT do {} while (0)
+#endif
+
 constexpr int kMaxDim = 12;
 constexpr int kNumWC = 10; // per-walker model constants held in registers (wc7 = sigma^2 when use_sigma)
 
@@ -35,19 +44,21 @@ struct ProblemDev {
     int npoints, nfilters, nsamples, spl_nint;
     const void *bank;      // real4[nsamples/2] pair records (a0, a1, w0, w1), a = alpha*log2(e), w = w/scale
     const void *kappa;     // real[nsamples]: 0.4*log2(10)*kappa_k           (ShockCooling3)
-    const void *frange;    // real4[nfilters]: (min a, max a, max |a1-a0| within a record, 0) (FP32 fast-path guards)
-    const int *foff;       // [nfilters+1]
+    const int4 *finfo;     // [nfilters]: (first pair record, pair records, bits of float min a, bits of float max a)
     const int *frole;      // [nfilters]
     const void *spl;       // real4[nfilters][spl_nint]                       (CompanionShocking*)
     const double *t;       // [npoints]
-    const void *y;         // real[npoints]  y/scale
-    const void *e1;        // real[npoints]  use_sigma ? (dy/scale)^2 : scale/dy
-    const void *e2;        // real[npoints]  (sigma_units/scale)^2            (use_sigma only)
+    const float2 *t32;     // [npoints] t - tref as an unevaluated float sum hi + lo   (FP32 mode)
+    const int *pfilt;      // [npoints] filter of each point
+    const void *obs;       // real4[npoints]: (y/scale, use_sigma ? (dy/scale)^2 : scale/dy, (sigma_units/scale)^2, 0)
     double spl_x0, spl_dx;
+    double tref;           // reference epoch of t32
     double const_term;     // sum_i log(2 pi dy_i^2)  or  N*(log 2 pi + 2 log scale)
     double scale;          // FP32 unit scale (1 in FP64 mode)
     double kB, c3sq;       // models.py:10-11 constants (host computed)
     double mc[16];         // model constants
+    double dk[4];          // derived exponents, FP64 kernels:  SW family: eps_T, eps_L - 4 eps_T, alpha;  SC4: A, alpha
+    float fk[4];           // the same as floats (no F2F.F32.F64 on the hot path: conversions share the XU pipe)
     PriorDev prior;
 };
 
@@ -100,6 +111,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok) {
@@ -137,8 +151,7 @@ template <typename R> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 
-constexpr bool kUseRecurrence = false;  // measured on B200 (profiles/r01_ncu_sc3_fp32_recurrence.txt): XU 54 %, FMA pipe 70 % busy, no faster
-constexpr bool kForceRecurrence = false;
+constexpr int kTabStride = 32;      // ShockCooling3 weight table: [pair record][32 walker columns], whatever wpb is
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kLn2 = 0.69314718055994530942;
 
@@ -292,42 +305,79 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec4<R>::type *__res
     return acc0 + acc1;
 }
 
-// FP32 fast paths (sm_100a).
-//  * Four Planck denominators share ONE MUFU.RCP:  r = 1/(d0 d1 d2 d3);  1/(d0 d1) = r (d2 d3);  1/d0 = d1/(d0 d1):
-//    1.25 MUFU ops per Planck sample (1 EX2 + 1/4 RCP) instead of 2.
-//  * The FP32 arithmetic around them uses Blackwell's packed instructions (FMUL2 / FADD2 / FFMA2 via __fmul2_rn,
-//    __fadd2_rn, __ffma2_rn): the two samples of a pair ride in one 64-bit register pair, halving the issue slots.
-// Callers guarantee that the four exponents sum to <= 126 (no overflow of the product) and that every exponent is
-// >= 1/16 (no cancellation in 2^x - 1).
+// FP32 fast paths (sm_100a).  The loop is bound by the XU pipe (MUFU: 16 lanes/clk/SM, 8 clk per warp instruction),
+// so everything except the exponential itself is kept OFF that pipe:
+//  * four Planck denominators share ONE reciprocal:  r = 1/(d0 d1 d2 d3);  1/(d0 d1) = r (d2 d3);  1/d0 = d1/(d0 d1);
+//  * that reciprocal is computed on the FMA/ALU pipes: integer-subtract seed (12 % error) + three Newton steps
+//    (4e-8, the accuracy of MUFU.RCP), two reciprocals at a time in the packed lanes;
+//  * the FP32 arithmetic uses Blackwell's packed FMUL2 / FADD2 / FFMA2 (one issue slot for two lanes of work).
+// => 1 MUFU.EX2 per Planck sample and nothing else on the XU pipe.  Measured in isolation (tools/microbench/loops.cu,
+// B200, 32 warps/SM): 14.6 samples/clk/SM against 12.2 for the MUFU.RCP version and 15.7 for a bare EX2 stream.
+// Callers guarantee that the four exponents sum to <= 126 (the product of four denominators stays a normal float)
+// and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
 __device__ __forceinline__ float2 ex2m1_pair(float2 x) {                 // (2^x.x - 1, 2^x.y - 1)
     return __fadd2_rn(make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y)), make_float2(-1.f, -1.f));
 }
+__device__ __forceinline__ float rcp_newton(float x) {                   // x positive and normal
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+    float e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
+    e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
+    e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
+    return r;
+}
+__device__ __forceinline__ float2 rcp_newton2(float2 x) {
+    float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(x.x)), __int_as_float(0x7EF311C7 - __float_as_int(x.y)));
+    const float2 one = make_float2(1.f, 1.f), nx = make_float2(-x.x, -x.y);
+    float2 e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
+    e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
+    e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
+    return r;
+}
 
-// (a) two blackbodies (points A, B of one walker) x the two samples of a pair record
+// (a) two blackbodies (points A, B of one walker) x the two samples of a pair record; two records per iteration.
+//     Pointer-bumped with compile-time strides so that the loop bookkeeping is 2 adds + compare + branch (integer
+//     multiply-adds would land on the FMA pipe, which is the second-busiest one here).
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
-                                                const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
+                                                const float2 *__restrict__ tab, float &SA, float &SB) {
+    constexpr int ts = kTabStride;
     const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB);
     float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
-#pragma unroll 2
-    for (int k = 0; k < K2; ++k) {
-        float2 a, w;
+    const float4 *pb = b4, *const pe = b4 + (K2 & ~1);
+    for (; pb < pe; pb += 2) {
+        float2 a0, w0, a1, w1;
         if (TAB) {
-            a = *reinterpret_cast<const float2 *>(b4 + k);
-            w = *tab;
-            tab += ts;
+            a0 = *reinterpret_cast<const float2 *>(pb);
+            a1 = *reinterpret_cast<const float2 *>(pb + 1);
+            w0 = tab[0];
+            w1 = tab[ts];
+            tab += 2 * ts;
         } else {
-            const float4 s = b4[k];
-            a = make_float2(s.x, s.y);
-            w = make_float2(s.z, s.w);
+            const float4 s0 = pb[0], s1 = pb[1];
+            a0 = make_float2(s0.x, s0.y); w0 = make_float2(s0.z, s0.w);
+            a1 = make_float2(s1.x, s1.y); w1 = make_float2(s1.z, s1.w);
         }
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2));               // (dA0, dA1)
-        const float2 dB = ex2m1_pair(__fmul2_rn(a, iB2));
-        const float2 p = __fmul2_rn(dA, dB);                            // (dA0 dB0, dA1 dB1)
-        const float r = Mth<float>::rcp(p.x * p.y);
-        const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));  // (w0/(dA0 dB0), w1/(dA1 dB1))
-        accA = __ffma2_rn(t, dB, accA);                                 // += w/dA
-        accB = __ffma2_rn(t, dA, accB);                                 // += w/dB
+        const float2 dA0 = ex2m1_pair(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair(__fmul2_rn(a0, iB2));   // (dA(k0), dA(k1))
+        const float2 dA1 = ex2m1_pair(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair(__fmul2_rn(a1, iB2));
+        const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);                          // per sample: dA dB
+        const float2 r = rcp_newton2(make_float2(p0.x * p0.y, p1.x * p1.y));                         // one per record
+        const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));  // w/(dA dB)
+        const float2 t1 = __fmul2_rn(w1, __fmul2_rn(make_float2(r.y, r.y), make_float2(p1.y, p1.x)));
+        accA = __ffma2_rn(t0, dB0, accA);                                                            // += w/dA
+        accB = __ffma2_rn(t0, dA0, accB);                                                            // += w/dB
+        accA = __ffma2_rn(t1, dB1, accA);
+        accB = __ffma2_rn(t1, dA1, accB);
+    }
+    if (K2 & 1) {
+        float2 a, w;
+        if (TAB) { a = *reinterpret_cast<const float2 *>(pb); w = tab[0]; }
+        else { const float4 s = pb[0]; a = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
+        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2)), dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 p = __fmul2_rn(dA, dB);
+        const float r = rcp_newton(p.x * p.y);
+        const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
+        accA = __ffma2_rn(t, dB, accA);
+        accB = __ffma2_rn(t, dA, accB);
     }
     SA = accA.x + accA.y;
     SB = accB.x + accB.y;
@@ -341,14 +391,13 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
     const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB), iAs2 = make_float2(iA * c, iA * c), iBs2 = make_float2(iB * c, iB * c);
     float2 a = make_float2(0.f, 0.f), as = a, bb = a, bs = a;
 #pragma unroll 2
-    for (int k = 0; k < K2; ++k) {
-        const float4 s = b4[k];
+    for (const float4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
+        const float4 s = *pb;
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
         const float2 dA = ex2m1_pair(__fmul2_rn(x, iA2)), dAs = ex2m1_pair(__fmul2_rn(x, iAs2));
         const float2 dB = ex2m1_pair(__fmul2_rn(x, iB2)), dBs = ex2m1_pair(__fmul2_rn(x, iBs2));
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
-        const float2 pp = __fmul2_rn(pA, pB);
-        const float2 r = make_float2(Mth<float>::rcp(pp.x), Mth<float>::rcp(pp.y));
+        const float2 r = rcp_newton2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
         a = __ffma2_rn(tA, dAs, a);   as = __ffma2_rn(tA, dA, as);
         bb = __ffma2_rn(tB, dBs, bb); bs = __ffma2_rn(tB, dB, bs);
@@ -356,94 +405,39 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
     SA = a.x + a.y; SAs = as.x + as.y; SB = bb.x + bb.y; SBs = bs.x + bs.y;
 }
 
-// FP32 fastest path: the second sample of every pair record by RECURRENCE on the FMA pipe instead of MUFU.EX2,
-//     2^(a1 i) = 2^(a0 i) * 2^((a1 - a0) i),      2^y = degree-5 Taylor polynomial in u = y ln 2,
-// accurate to 4e-8 for |u| <= 0.173 because consecutive samples of a transmission curve are close in frequency.
-// Packed by POINT here ((A, B) at the same sample), so the polynomial runs as five FFMA2.  Per record of 4 Planck
-// samples: 2 MUFU.EX2 + 1 MUFU.RCP = 0.75 MUFU per sample (6 XU clk per warp-sample) against ~18 FMA-pipe instructions.
-// Callers check max|a1 - a0| * max(i) * ln2 <= 0.173, every exponent >= 1/2 and the usual overflow bound.
-__device__ __forceinline__ float2 exp2_step_m1(float2 e0, float2 u) {            // e0 * 2^(u / ln2) - 1, element-wise
-    float2 g = __ffma2_rn(u, make_float2(1.f / 120.f, 1.f / 120.f), make_float2(1.f / 24.f, 1.f / 24.f));
-    g = __ffma2_rn(u, g, make_float2(1.f / 6.f, 1.f / 6.f));
-    g = __ffma2_rn(u, g, make_float2(0.5f, 0.5f));
-    g = __ffma2_rn(u, g, make_float2(1.f, 1.f));
-    g = __ffma2_rn(u, g, make_float2(1.f, 1.f));
-    return __ffma2_rn(e0, g, make_float2(-1.f, -1.f));
-}
-
-template <bool TAB>
-__device__ __forceinline__ void planck_quad_rec_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
-                                                    const float2 *__restrict__ tab, int ts, float &SA, float &SB) {
-    const float2 iAB = make_float2(iA, iB), uAB = make_float2(iA * (float)kLn2, iB * (float)kLn2);
-    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll 2
-    for (int k = 0; k < K2; ++k) {
-        float a0, a1, w0, w1;
-        if (TAB) {
-            const float2 a = *reinterpret_cast<const float2 *>(b4 + k);
-            const float2 w = *tab;
-            tab += ts;
-            a0 = a.x; a1 = a.y; w0 = w.x; w1 = w.y;
-        } else {
-            const float4 s = b4[k];
-            a0 = s.x; a1 = s.y; w0 = s.z; w1 = s.w;
-        }
-        const float2 x0 = __fmul2_rn(iAB, make_float2(a0, a0));
-        const float2 e0 = make_float2(Mth<float>::ex2(x0.x), Mth<float>::ex2(x0.y));
-        const float2 d0 = __fadd2_rn(e0, make_float2(-1.f, -1.f));                 // (dA0, dB0)
-        const float dl = a1 - a0;
-        const float2 d1 = exp2_step_m1(e0, __fmul2_rn(uAB, make_float2(dl, dl)));  // (dA1, dB1)
-        const float p0 = d0.x * d0.y, p1 = d1.x * d1.y;
-        const float r = Mth<float>::rcp(p0 * p1);
-        const float t0 = w0 * (r * p1), t1 = w1 * (r * p0);
-        acc0 = __ffma2_rn(make_float2(t0, t0), d0, acc0);                           // .x += w0/dB0, .y += w0/dA0
-        acc1 = __ffma2_rn(make_float2(t1, t1), d1, acc1);
-    }
-    SA = acc0.y + acc1.y;
-    SB = acc0.x + acc1.x;
-}
-
-__device__ __forceinline__ void planck_quad_rec_sc4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float &SA,
-                                                        float &SAs, float &SB, float &SBs) {
-    const float c = (float)(1. / 0.74), l2 = (float)kLn2;
-    const float2 PA = make_float2(iA, iA * c), PB = make_float2(iB, iB * c);          // (T, 0.74 T) of point A, of point B
-    const float2 UA = make_float2(iA * l2, iA * c * l2), UB = make_float2(iB * l2, iB * c * l2);
-    float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
-#pragma unroll 2
-    for (int k = 0; k < K2; ++k) {
-        const float4 s = b4[k];
-        const float2 xA = __fmul2_rn(PA, make_float2(s.x, s.x)), xB = __fmul2_rn(PB, make_float2(s.x, s.x));
-        const float2 eA = make_float2(Mth<float>::ex2(xA.x), Mth<float>::ex2(xA.y));
-        const float2 eB = make_float2(Mth<float>::ex2(xB.x), Mth<float>::ex2(xB.y));
-        const float2 dA0 = __fadd2_rn(eA, make_float2(-1.f, -1.f)), dB0 = __fadd2_rn(eB, make_float2(-1.f, -1.f));
-        const float dl = s.y - s.x;
-        const float2 dA1 = exp2_step_m1(eA, __fmul2_rn(UA, make_float2(dl, dl)));
-        const float2 dB1 = exp2_step_m1(eB, __fmul2_rn(UB, make_float2(dl, dl)));
-        {
-            const float pA = dA0.x * dA0.y, pB = dB0.x * dB0.y;
-            const float r = Mth<float>::rcp(pA * pB);
-            const float tA = s.z * (r * pB), tB = s.z * (r * pA);
-            accA = __ffma2_rn(make_float2(tA, tA), dA0, accA);                      // .x += w/dAs, .y += w/dA
-            accB = __ffma2_rn(make_float2(tB, tB), dB0, accB);
-        }
-        {
-            const float pA = dA1.x * dA1.y, pB = dB1.x * dB1.y;
-            const float r = Mth<float>::rcp(pA * pB);
-            const float tA = s.w * (r * pB), tB = s.w * (r * pA);
-            accA = __ffma2_rn(make_float2(tA, tA), dA1, accA);
-            accB = __ffma2_rn(make_float2(tB, tB), dB1, accB);
-        }
-    }
-    SA = accA.y; SAs = accA.x; SB = accB.y; SBs = accB.x;
-}
-
 // ---------------------------------------------------------------------------------------
 // per-lane walker state in registers
 // ---------------------------------------------------------------------------------------
-template <typename R> struct LaneWalker {
-    R wc[kNumWC];
+// FP32 mode never converts a double on the hot path (F2F.F32.F64 shares the XU pipe with MUFU): epochs are kept
+// relative to P.tref as unevaluated hi + lo float sums, and t - t_0 = (t_hi - t0_hi) + (t_lo - t0_lo) is good to
+// one ulp of the DIFFERENCE (an MJD minus an MJD in one float would only be good to one ulp of 59000).
+template <typename R> __device__ __forceinline__ R kconst(const ProblemDev &P, int i);
+template <> __device__ __forceinline__ double kconst<double>(const ProblemDev &P, int i) { return P.dk[i]; }
+template <> __device__ __forceinline__ float kconst<float>(const ProblemDev &P, int i) { return P.fk[i]; }
+
+template <typename R> struct LaneWalker;
+template <> struct LaneWalker<double> {
+    double wc[kNumWC];
     double t0, t1;
+    __device__ __forceinline__ void set_epochs(double a, double b, double) { t0 = a; t1 = b; }
 };
+template <> struct LaneWalker<float> {
+    float wc[kNumWC];
+    float t0h, t0l, t1h, t1l;
+    __device__ __forceinline__ void set_epochs(double a, double b, double tref) {
+        const double ra = a - tref, rb = b - tref;
+        t0h = (float)ra; t0l = (float)(ra - (double)t0h);
+        t1h = (float)rb; t1l = (float)(rb - (double)t1h);
+    }
+};
+// time of photometry point p since the walker's explosion epoch (WHICH = 0) or SiFTO peak (WHICH = 1)
+template <int WHICH> __device__ __forceinline__ double since(const ProblemDev &P, const LaneWalker<double> &w, int p) {
+    return P.t[p] - (WHICH ? w.t1 : w.t0);
+}
+template <int WHICH> __device__ __forceinline__ float since(const ProblemDev &P, const LaneWalker<float> &w, int p) {
+    const float2 t = P.t32[p];
+    return __fadd_rn(__fsub_rn(t.x, WHICH ? w.t1h : w.t0h), __fsub_rn(t.y, WHICH ? w.t1l : w.t0l));
+}
 
 // SiFTO cubic spline (models.py:717, 817-826): NaN outside the knots -> 0
 template <typename R>
@@ -459,103 +453,95 @@ __device__ __forceinline__ R sifto_eval(const ProblemDev &P, int f, R tau) {
     return (v != v) ? (R)0 : v;
 }
 
-// Front end of one (walker, point): blackbody inverse temperature and amplitude, so that the
-// blackbody part of the model is  amp * S(invT)  (ShockCooling4: min(amp S(invT), amp 0.74^-4 S(invT/0.74))).
-//   state 1: needs the Planck sum; state 0: blackbody part is `amp` as is (0, or NaN to propagate)
-//   SW family (1,2,3): wc0 = K_T, wc1 = K_L, wc2 = log2(a/t_tr) | -inf, (3: wc3 = E(B-V))
+// Front end of one (walker, point): the model value is
+//      y = amp * S(invT) + add                      (ShockCooling4: min(amp S(invT), amp 0.74^-4 S(invT/0.74)))
+// with S the Planck x transmission sum of the point's filter.  invT = 0 encodes "no blackbody": y = amp + add, where amp
+// is 0 (before the explosion) or NaN (to propagate what the reference's numpy expression would produce).
+// Written branch-free (exceptional cases are selects applied in reverse order of precedence) so that the compiler
+// interleaves the MUFU chains of the unrolled items.
+//   SW family (1,2,3): wc0 = K_T, wc1 = K_L, wc2 = log2(a/t_tr) | -inf, wc4 = 1/K_T, wc5 = K_L/K_T^4 (3: wc3 = E(B-V))
 //        T = K_T t^eps_T ; L = K_L t^eps_L exp(-(a t/t_tr)^alpha) ; amp = L/T^4
-//   SC4: wc0 = T_col_br/k_B, wc1 = c3^2 L_br, wc2 = -log2(t_br), wc3 = log2(a/t_tr)
-//   CS*: wc0, wc1 Kasen T/R^2 coefficients, wc2 Kasen factor, wc3 stretch, wc4.. r_r,r_i,r_U | dt_U,dt_i
+//   SC4: wc0 = T_col_br/k_B, wc1 = c3^2 L_br, wc2 = -log2(t_br), wc3 = log2(a/t_tr), wc4/wc5 = 1/T coefficients
+//   CS*: wc0, wc1 Kasen T/R^2 coefficients, wc2 Kasen factor, wc3 stretch, wc4.. r_r,r_i,r_U | dt_U,dt_i, wc8 = 1/wc0
 //   SED: wc0 = 1/T, wc1 = R^2
+template <int MODEL, typename R>
+__device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<R> &w, int p, R &inv, R &amp, R &add) {
+    typedef Mth<R> M;
+    add = (R)0;
+    if (MODEL == 8) {
+        const bool ok = w.wc[0] > (R)0;
+        inv = ok ? w.wc[0] : (R)0;
+        amp = ok ? w.wc[1] : w.wc[1] * (R)0;
+        return;
+    }
+    const R dt = since<0>(P, w, p);
+    const bool pos = dt > (R)0;
+#ifdef LCF_X_FE_STUB   // experiment: what the kernel costs without the front-end transcendentals (results are wrong)
+    inv = w.wc[4] * (R)0.5 * (dt > (R)3 ? (R)1.1 : (R)1); amp = w.wc[5]; return;
+#endif
+    const R lt = M::lg2(pos ? dt : (R)1);
+    R i, a;
+    if (MODEL >= 1 && MODEL <= 3) {
+        // 4 transcendentals: lg2(t), (a t/t_tr)^alpha, L/T^4, 1/T
+        const R epsT = kconst<R>(P, 0), epsA = kconst<R>(P, 1), alpha = kconst<R>(P, 2);
+        const R pw_ = (w.wc[2] > -M::inf()) ? M::ex2(alpha * (lt + w.wc[2])) : (R)0;
+        a = w.wc[5] * M::ex2(epsA * lt - (R)kLog2e * pw_);
+        i = w.wc[4] * M::ex2(-epsT * lt);
+        if (!(w.wc[4] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : w.wc[1] * (R)0; }   // T <= 0
+        if (w.wc[1] < (R)0) { i = (R)0; a = M::nan(); }                       // L < 0: L ** 0.5 is NaN (models.py:268)
+        if (!pos) { i = (R)0; a = (w.wc[0] * w.wc[1]) * (R)0; }                // t <= t_exp: zero (NaN constants propagate)
+    } else if (MODEL == 4) {
+        // 6 transcendentals: lg2(t), suppression (2), two powers of ttilde for L, one for 1/T (branch selected)
+        const R A = kconst<R>(P, 0), alpha = kconst<R>(P, 1);
+        const R ltt = lt + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
+        const R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[3]))) : (R)1;
+        const R L = w.wc[1] * (M::ex2((R)(-4. / 3.) * ltt) + A * sup * M::ex2((R)(-0.17) * ltt));
+        // T = T_br min(0.97 u^-1/3, u^-0.45): the first branch is the smaller one for log2(u) < -log2(0.97)/(0.45-1/3)
+        const bool early = ltt < (R)0.37665701296944757;
+        i = (early ? w.wc[4] : w.wc[5]) * M::ex2((early ? (R)(1. / 3.) : (R)0.45) * ltt);
+        const R i2 = i * i;
+        a = L * (i2 * i2);
+        if (!(i > (R)0)) { a = (i != i) ? M::nan() : L * (R)0; i = (R)0; }
+        if (L < (R)0) { a = M::nan(); i = (R)0; }
+        if (!pos) { a = (w.wc[0] * w.wc[1]) * (R)0; i = (R)0; }
+    } else {
+        // Kasen, models.py:752-754: 3 transcendentals, then the SiFTO template and the per-filter factors
+        i = w.wc[8] * M::ex2((R)(74. / 144.) * lt);
+        a = w.wc[1] * M::ex2((R)(14. / 9.) * lt);               // = R^2 here
+        if (!(w.wc[8] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : (R)0; }
+        if (!pos) { i = (R)0; a = (R)0; }
+        const int f = P.pfilt[p];
+        const int role = P.frole[f];
+        const R tw = since<1>(P, w, p);                          // t_wrt_peak, models.py:816
+        if (MODEL == 5) {
+            const R ys = sifto_eval<R>(P, f, tw / w.wc[3]);
+            a *= (role & 1) ? w.wc[6] : (R)1;
+            add = ys * ((role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1));   // models.py:915
+        } else {
+            const R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
+            add = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
+            a *= w.wc[2];                                        // models.py:979, 1044
+        }
+    }
+    inv = i;
+    amp = a;
+}
+
 template <typename R> struct PointFE {
     R invT, amp;
     int state;
 };
 
-template <int MODEL, typename R>
-__device__ __forceinline__ PointFE<R> front_end(const ProblemDev &P, const LaneWalker<R> &w, double tp) {
-    typedef Mth<R> M;
-    PointFE<R> fe;
-    fe.invT = (R)1;
-    fe.state = 0;
-    if (MODEL == 8) {
-        fe.invT = w.wc[0];
-        fe.amp = w.wc[1];
-        if (fe.invT > (R)0) fe.state = 1; else { fe.amp = w.wc[1] * (R)0; fe.invT = (R)1; }
-        return fe;
-    }
-    const R dt = (R)(tp - w.t0);
-    R L;
-    if (MODEL >= 1 && MODEL <= 3) {
-        // 4 transcendentals: lg2(t), (a t/t_tr)^alpha, L/T^4, 1/T
-        if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }   // t <= t_exp: zero (NaN constants propagate)
-        if (w.wc[1] < (R)0) { fe.amp = M::nan(); return fe; }                  // L < 0: L ** 0.5 is NaN (models.py:268)
-        if (!(w.wc[4] > (R)0)) { fe.amp = (w.wc[0] != w.wc[0]) ? M::nan() : w.wc[1] * (R)0; return fe; }   // T <= 0
-        const R epsT = (R)(2. * P.mc[3] - 0.5), epsA = (R)(-2. * P.mc[4] - 4. * (2. * P.mc[3] - 0.5)), alpha = (R)P.mc[2];
-        const R lt = M::lg2(dt);
-        const R pw_ = (w.wc[2] > -M::inf()) ? M::ex2(alpha * (lt + w.wc[2])) : (R)0;
-        fe.amp = w.wc[5] * M::ex2(epsA * lt - (R)kLog2e * pw_);
-        fe.invT = w.wc[4] * M::ex2(-epsT * lt);
-        fe.state = 1;
-        return fe;
-    }
-    if (MODEL == 4) {
-        // 6 transcendentals: lg2(t), suppression (2), two powers of ttilde for L, one for 1/T (branch selected)
-        if (!(dt > (R)0)) { fe.amp = (w.wc[0] * w.wc[1]) * (R)0; return fe; }
-        const R A = (R)P.mc[0], alpha = (R)P.mc[2];
-        const R l0 = M::lg2(dt);
-        const R lt = l0 + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
-        const R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (l0 + w.wc[3]))) : (R)1;
-        L = w.wc[1] * (M::ex2((R)(-4. / 3.) * lt) + A * sup * M::ex2((R)(-0.17) * lt));
-        // T = T_br min(0.97 u^-1/3, u^-0.45): the first branch is the smaller one for log2(u) < -log2(0.97)/(0.45-1/3)
-        const bool early = lt < (R)0.37665701296944757;
-        const R invT = (early ? w.wc[4] : w.wc[5]) * M::ex2((early ? (R)(1. / 3.) : (R)0.45) * lt);
-        if (L < (R)0) { fe.amp = M::nan(); return fe; }
-        if (!(invT > (R)0)) { fe.amp = (invT != invT) ? M::nan() : L * (R)0; return fe; }
-        const R i2 = invT * invT;
-        fe.invT = invT;
-        fe.amp = L * (i2 * i2);
-        fe.state = 1;
-        return fe;
-    }
-    // Kasen, models.py:752-754: 3 transcendentals
-    if (!(dt > (R)0)) { fe.amp = (R)0; return fe; }
-    if (!(w.wc[8] > (R)0)) { fe.amp = (w.wc[0] != w.wc[0]) ? M::nan() : (R)0; return fe; }
-    {
-        const R lt = M::lg2(dt);
-        fe.invT = w.wc[8] * M::ex2((R)(74. / 144.) * lt);
-        fe.amp = w.wc[1] * M::ex2((R)(14. / 9.) * lt);          // = R^2 here
-        fe.state = 1;
-    }
-    return fe;
-}
-
-// Combine the blackbody part with the rest of the model (SiFTO template, per-filter factors).
-template <int MODEL, typename R>
-__device__ __forceinline__ R finish_point(const ProblemDev &P, const LaneWalker<R> &w, int f, double tp, R ybb) {
-    if (MODEL < 5 || MODEL == 8) return ybb;
-    const int role = P.frole[f];
-    const R tw = (R)(tp - w.t1);                                // t_wrt_peak, models.py:816
-    if (MODEL == 5) {
-        const R ys = sifto_eval<R>(P, f, tw / w.wc[3]);
-        const R kf = (role & 1) ? w.wc[6] : (R)1;
-        const R sf = (role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1);
-        return ybb * kf + ys * sf;                              // models.py:915
-    }
-    const R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
-    const R ys = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
-    return ybb * w.wc[2] + ys;                                  // models.py:979, 1044
-}
-
 // Blackbody part of up to two points of one filter for one walker.
 template <int MODEL, typename R>
-__device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typename Vec4<R>::type *bank, const int *s_foff, int f,
+__device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *bank, const int4 fi,
                                                const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, int ts, R &y0, R &y1) {
+                                               const typename Vec2<R>::type *tab, R &y0, R &y1) {
     typedef Mth<R> M;
     typedef typename Vec2<R>::type R2;
     typedef typename Vec4<R>::type R4;
-    const int k0 = s_foff[f] >> 1, K2 = (s_foff[f + 1] >> 1) - k0;      // pair records of this filter
+    constexpr int ts = kTabStride;
+    const int k0 = fi.x, K2 = fi.y;                                     // pair records of this filter
     const R4 *b = bank + k0;
     const R2 *tb = tab + (size_t)k0 * ts;
     const R c74 = (R)(1. / 0.74), c74_4 = (R)(1. / (0.74 * 0.74 * 0.74 * 0.74));
@@ -564,30 +550,23 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
     const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
     if (!n0 && !n1) return;
     if (sizeof(R) == 4) {
-        const float4 rng = reinterpret_cast<const float4 *>(P.frange)[f];       // (a_min, a_max, max |a1 - a0| in a record, 0)
+        const float2 rng = make_float2(__int_as_float(fi.z), __int_as_float(fi.w));   // (a_min, a_max) of the filter
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
-        const float imin = fminf(i0, i1), imax = fmaxf(i0, i1) * (MODEL == 4 ? (float)(1. / 0.74) : 1.f);
+        const float imin = fminf(i0, i1);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
         if (fast) {
-            const bool rec = kUseRecurrence && (kForceRecurrence || ((rng.z * imax <= (float)(0.173 / kLn2)) && (rng.x * imin >= 0.5f)));
             const float4 *bf = reinterpret_cast<const float4 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
             if (MODEL == 4) {
                 float S0s, S1s;
-                if (rec) planck_quad_rec_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
-                else planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) {
-                    if (rec) planck_quad_rec_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
-                    else planck_quad_f32<true>(bf, K2, i0, i1, tf, ts, S0, S1);
-                } else {
-                    if (rec) planck_quad_rec_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
-                    else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, 0, S0, S1);
-                }
+                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, S0, S1);
+                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, S0, S1);
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }
@@ -608,21 +587,41 @@ __device__ __forceinline__ void blackbody_pair(const ProblemDev &P, const typena
 }
 
 // ---------------------------------------------------------------------------------------
+// thread-block cluster helpers (a plain launch is a 1-CTA cluster: rank 0 of 1)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the same shared-memory location of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void dsmem_store_f64(double *local, uint32_t rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // shared-memory carve-up (dynamic), identical for the half-step and the chain kernels
 // ---------------------------------------------------------------------------------------
+constexpr int kMaxCluster = 8;      // portable cluster size limit
+
 template <typename R> struct SmemLayout {
-    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_flag, off_bar, total;
+    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_cpart, off_flag, off_bar, total;
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
-        off_tab = o;  o += tab ? (size_t)nsamples * wpb * sizeof(R) : 0;     // R2[nsamples/2][wpb]          o = (o + 15) & ~(size_t)15;
-        off_foff = o; o += (size_t)(nfilters + 1) * sizeof(int);                  o = (o + 15) & ~(size_t)15;
+        off_tab = o;  o += tab ? (size_t)nsamples * kTabStride * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][32]
+        off_foff = o; o += (size_t)nfilters * sizeof(int4);                       o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
         off_q = o;    o += (size_t)wpb * ndim * sizeof(double);
         off_lp = o;   o += (size_t)wpb * sizeof(double);
         off_z = o;    o += (size_t)wpb * sizeof(double);
         off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
+        off_cpart = o; o += (size_t)kMaxCluster * wpb * sizeof(double);
         off_flag = o; o += (size_t)wpb * sizeof(int);                             o = (o + 15) & ~(size_t)15;
         off_bar = o;  o += 16;
         total = o;
@@ -631,11 +630,15 @@ template <typename R> struct SmemLayout {
 
 // ---------------------------------------------------------------------------------------
 // One half-step (or one evaluation pass) for the walker group `g` of the active set.
-// Called by every thread of the CTA.  `staged` tells whether the bank is already in smem.
+// Called by every thread of the CTA.  A cluster of `csize` CTAs shares the group: CTA `crank` takes every csize-th
+// row of tiles of the light curve and rank 0 reduces the chi-square partials through DSMEM.
+// (Measured alternatives, see DESIGN.md: a chunked front-end pass through shared memory with one CTA barrier per chunk,
+// and dedicated front-end producer warps feeding the loop warps through an mbarrier ring, were both slower: the XU
+// pipe is fed best by 32 resident warps that ALL spend their time in the dense inner loop.)
 // ---------------------------------------------------------------------------------------
 template <int MODEL, typename R>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
-                                           unsigned char *smem, const SmemLayout<R> &L, uint32_t bar_parity, bool need_stage) {
+                                           unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize) {
     typedef typename Vec2<R>::type R2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int wpb = 1 << Mv.wpb_log2;
@@ -643,16 +646,18 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     typedef typename Vec4<R>::type R4;
     R4 *s_bank = reinterpret_cast<R4 *>(smem + L.off_bank);
     R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
-    int *s_foff = reinterpret_cast<int *>(smem + L.off_foff);
+    int4 *s_finfo = reinterpret_cast<int4 *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
     double *s_t = reinterpret_cast<double *>(smem + L.off_t);
     double *s_q = reinterpret_cast<double *>(smem + L.off_q);
     double *s_lp = reinterpret_cast<double *>(smem + L.off_lp);
     double *s_z = reinterpret_cast<double *>(smem + L.off_z);
     double *s_part = reinterpret_cast<double *>(smem + L.off_part);
+    double *s_cpart = reinterpret_cast<double *>(smem + L.off_cpart);
     int *s_flag = reinterpret_cast<int *>(smem + L.off_flag);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
 
+    LCF_TICK_INIT;
     // ---- phase 0: stage the packed filter bank with one TMA bulk copy -------------------
     if (need_stage) {
         if (tid == 0) {
@@ -660,10 +665,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             mbar_expect_tx(s_bar, bytes);
             tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
         }
-        for (int i = tid; i <= P.nfilters; i += blockDim.x) s_foff[i] = P.foff[i];
+        for (int i = tid; i < P.nfilters; i += blockDim.x) s_finfo[i] = P.finfo[i];
     }
 
-    // ---- phase 1: proposal + prior + model front end, one thread per walker -------------
+    // ---- phase 1: proposal + prior + per-walker model constants (FP64), one thread per walker ----
+    // (every CTA of a cluster repeats it for the same walkers: bitwise identical, no communication)
     if (tid < wpb) {
         const long long i = g * wpb + tid;
         int flag = 1;                                    // 1 = skip likelihood
@@ -713,7 +719,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         s_flag[tid] = flag;
     }
     __syncthreads();
-    if (need_stage) mbar_wait(s_bar, bar_parity);
+    LCF_TICK(0);
+    if (need_stage) mbar_wait(s_bar, 0);
+    LCF_TICK(1);
 
     // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33), pair layout
     if (MODEL == 3) {
@@ -726,10 +734,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             R2 v;
             v.x = rec.z * Mth<R>::ex2(-ebv * kap[2 * kp]);
             v.y = rec.w * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
-            s_tab[idx] = v;
+            s_tab[kp * kTabStride + wl] = v;
         }
         __syncthreads();
     }
+    LCF_TICK(2);
 
     // ---- phase 2: tiles (each lane: up to two points of the tile's filter) ----------------
     const int wl = lane & (wpb - 1), slot = lane >> Mv.wpb_log2, ppt = 32 >> Mv.wpb_log2;
@@ -738,47 +747,52 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     LaneWalker<R> lw;
 #pragma unroll
     for (int k = 0; k < kNumWC; ++k) lw.wc[k] = s_wc[wl * kNumWC + k];
-    lw.t0 = s_t[wl * 2];
-    lw.t1 = s_t[wl * 2 + 1];
-    const R *py = reinterpret_cast<const R *>(P.y);
-    const R *pe1 = reinterpret_cast<const R *>(P.e1);
-    const R *pe2 = reinterpret_cast<const R *>(P.e2);
+    lw.set_epochs(s_t[wl * 2], s_t[wl * 2 + 1], P.tref);
+    const R4 *pobs = reinterpret_cast<const R4 *>(P.obs);
+    const R2 *s_tabw = s_tab + wl;
+    const int4 *tiles = TL.tiles;
     R chi = 0;
-    for (int tile = warp; tile < TL.ntiles; tile += nw) {
-        const int4 tl = TL.tiles[tile];
+    for (int tile = crank * nw + warp; tile < TL.ntiles; tile += nw * csize) {
+        const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
         if (!skip && slot < tl.y) {
-            const int pa = tl.x + slot, pb = pa + ppt;
+            const int pa = tl.x + slot;
             const bool two = slot + ppt < tl.y;
-            const double ta = P.t[pa], tb = two ? P.t[pb] : ta;
-            const PointFE<R> fa = front_end<MODEL, R>(P, lw, ta);
-            PointFE<R> fb = fa;
-            if (two) fb = front_end<MODEL, R>(P, lw, tb);
+            const int pb = two ? pa + ppt : pa;
+            // observed values first: their (L1-resident) loads overlap the front end and the inner loop
+            const R4 oa = pobs[pa], ob = pobs[pb];
+            const int4 fi = s_finfo[tl.z];
+            PointFE<R> fa, fb;
+            R adda, addb;
+            front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda);      // branch-free: the two MUFU chains interleave
+            front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb);
+            fa.state = fa.invT > (R)0 ? 1 : 0;
+            fb.state = fb.invT > (R)0 ? 1 : 0;
             R ya, yb;
-            blackbody_pair<MODEL, R>(P, s_bank, s_foff, tl.z, fa, fb, two, s_tab + wl, wpb, ya, yb);
-            ya = finish_point<MODEL, R>(P, lw, tl.z, ta, ya);
-            if (two) yb = finish_point<MODEL, R>(P, lw, tl.z, tb, yb);
+            blackbody_pair<MODEL, R>(s_bank, fi, fa, fb, two, s_tabw, ya, yb);
+            if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
             if (Mv.mode == MODE_MODEL) {
                 Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
                 if (two) Mv.out[iw * P.npoints + pb] = (double)yb * P.scale;
             } else if (P.use_sigma) {
-                const R s2a = pe1[pa] + lw.wc[7] * pe2[pa];          // models.py:130
-                const R ra = py[pa] - ya;
+                const R s2a = oa.y + lw.wc[7] * oa.z;                // models.py:130
+                const R ra = oa.x - ya;
                 chi += Mth<R>::lg2(s2a) * (R)kLn2 + ra * ra * Mth<R>::rcp(s2a);
                 if (two) {
-                    const R s2b = pe1[pb] + lw.wc[7] * pe2[pb];
-                    const R rb = py[pb] - yb;
+                    const R s2b = ob.y + lw.wc[7] * ob.z;
+                    const R rb = ob.x - yb;
                     chi += Mth<R>::lg2(s2b) * (R)kLn2 + rb * rb * Mth<R>::rcp(s2b);
                 }
             } else {
-                const R ra = (py[pa] - ya) * pe1[pa];                 // models.py:135
+                const R ra = (oa.x - ya) * oa.y;                     // models.py:135
                 chi = fma(ra, ra, chi);
                 if (two) {
-                    const R rb = (py[pb] - yb) * pe1[pb];
+                    const R rb = (ob.x - yb) * ob.y;
                     chi = fma(rb, rb, chi);
                 }
             }
         }
     }
+    LCF_TICK(3);
     if (Mv.mode == MODE_MODEL) { __syncthreads(); return; }
 
     // ---- phase 3: reduce, accept, write back ----------------------------------------------
@@ -786,14 +800,24 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     for (int off = 16; off >= wpb; off >>= 1) chid += __shfl_xor_sync(0xffffffffu, chid, off);
     if (lane < wpb) s_part[warp * wpb + lane] = chid;
     __syncthreads();
-    if (tid < wpb) {
+    LCF_TICK(4);
+    if (csize > 1) {                                       // partial sums of the cluster -> rank 0, in rank order
+        if (tid < wpb) {
+            double tot = 0.;
+            for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid];
+            dsmem_store_f64(&s_cpart[crank * wpb + tid], 0u, tot);
+        }
+        cluster_sync_all();
+    }
+    if (crank == 0 && tid < wpb) {
         const long long i = g * wpb + tid;
         if (i < Mv.Ns) {
             double lp = s_lp[tid];
             double nlp = lp;
             if (!s_flag[tid]) {
                 double tot = 0.;
-                for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid];
+                if (csize > 1) { for (int r = 0; r < csize; ++r) tot += s_cpart[r * wpb + tid]; }
+                else { for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid]; }
                 nlp = lp + (-0.5 * (P.const_term + tot));
             }
             if (Mv.mode != MODE_MOVE) {
@@ -827,11 +851,14 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             }
         }
     }
-    __syncthreads();
+    if (csize > 1) cluster_sync_all();                     // rank 0 has read s_cpart; also orders the in-place update
+    else __syncthreads();
+    LCF_TICK(5);
 }
 
 // ---------------------------------------------------------------------------------------
 // Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
+// Grid = walker groups x cluster size (cluster dimension set by the launch attribute; 1 for large ensembles).
 // ---------------------------------------------------------------------------------------
 template <int MODEL, typename R>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
@@ -841,11 +868,12 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     __syncthreads();
+    const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
-    uint32_t parity = 0;
+    const long long nclusters = cluster_count_x();
     bool first = true;
-    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        group_pass<MODEL, R>(P, TL, Mv, g, smem, L, parity, first);
+    for (long long g = cluster_id_x(); g < ngroups; g += nclusters) {
+        group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize);
         first = false;
     }
 }
@@ -907,7 +935,7 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
         Mv.qin = Mv.coords; Mv.out = Mv.logp;
         Mv.chain_step = nullptr; Mv.lnp_step = nullptr; Mv.ctr = 0;
         const long long ng = (B.W + wpb - 1) / wpb;
-        for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, 0, first); first = false; }
+        for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
         Mv.qin = nullptr; Mv.out = nullptr;
     }
     Mv.mode = MODE_MOVE;
@@ -924,7 +952,7 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
             Mv.Nc = half ? B.n0 : n1;
             Mv.comp_base = half ? 0 : B.n0;
             const long long ng = (Mv.Ns + wpb - 1) / wpb;
-            for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, 0, first); first = false; }
+            for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
         }
     }
 }

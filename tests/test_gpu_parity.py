@@ -50,6 +50,20 @@ def test_log_posterior_parity(name, precision):
     _check_logpost(WORKLOADS[name](), precision)
 
 
+@pytest.mark.parametrize('shape', [(32, 16, 1), (32, 4, 2), (8, 4, 4), (2, 8, 8), (1, 2, 8), (16, 16, 8)])
+@pytest.mark.parametrize('name,precision', [('sc4_example', 'fp32'), ('sc3_synth_sigma', 'fp32'), ('cs3_synth', 'fp64'),
+                                            ('sc3_synth', 'fp64'), ('sed', 'fp32')])
+def test_log_posterior_parity_forced_launch_shapes(name, precision, shape):
+    """Every (walkers per CTA, warps per CTA, cluster size) decomposition gives the oracle's log-posterior: partial
+    tiles, chunks that straddle filters, clusters larger than the chunk count, DSMEM reduction of the partials."""
+    from lightcurve_fitting_b200._capi import lib, check
+    check(lib().lcf_set_tuning_ex(*shape))
+    try:
+        _check_logpost(WORKLOADS[name](), precision, n=37, seed=11, widen=0.1)
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
 @pytest.mark.parametrize('precision', ['fp64', 'fp32'])
 def test_log_posterior_outside_prior(precision):
     """-inf outside the strict prior bounds (models.py:1055-1059), likelihood skipped (fitting.py:125)."""
@@ -470,8 +484,8 @@ def test_sharded_ensemble_emulated_two_ranks_matches_single():
     nw, nsteps = 64, 6
     # pin the launch shape: in the FP32 fast path the two points a lane pairs up share one reciprocal, and which
     # points are paired depends on the tile size (walkers per CTA); with the same shape the chains are bit-identical
-    # across GPU counts, otherwise they agree to FP32 rounding
-    check(lib().lcf_set_tuning(8, 4))
+    # across GPU counts, otherwise they agree to FP32 rounding (the cluster size fixes the order of the partial sums)
+    check(lib().lcf_set_tuning_ex(8, 4, 1))
     p0 = wl.start(nw, np.random.default_rng(2))
     single = EnsembleSampler(nw, wl.ndim, prob, seed=42)
     single.run_mcmc(p0, nsteps, skip_initial_state_check=True)
