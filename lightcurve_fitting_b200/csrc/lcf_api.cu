@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -224,13 +225,15 @@ int build_tiles(lcf_problem *p, int l) {
 }
 
 // Launch shape for an active set of Ns walkers: walkers per CTA (2^l), warps per CTA and cluster size S (CTAs that
-// share one walker group and split its light curve chunk-wise).  A small cost model in SM clocks picks it:
-//   * the kernel is bound by a per-SM pipe (XU in FP32, FP64 FMA in FP64), so the busiest SM decides: CTAs are dealt
-//     to SMs in waves of `occ` CTAs per SM and a wave costs  max(pipe time of its CTAs, latency of one warp's tiles)
-//     plus the serial FP64 proposal/setup phase;
-//   * a tile is always 64 (walker, point) pairs of ONE filter, so partial tiles (few points per filter, few walkers)
-//     waste lanes: the tile count per group grows as wpb shrinks only when the light curve has enough points;
-//   * the per-CTA tables (ShockCooling3 reddening table, front-end buffers) must fit in shared memory.
+// share one walker group and split its light curve tile-wise).  A cost model in SM clocks, calibrated on B200 shape
+// sweeps of cfg1 / cfg2 / cfg4 (tools/bench_configs.py --tune, gpurun_out r2_sweep*), picks it:
+//   * XU-bound time of the busiest SM: CTAs are dealt round-robin, so it executes n = ceil(CTAs / SMs) of them; the XU
+//     pipe only saturates with ~32 resident warps (isolated loop: 71 % at 8 warps, 87 % at 16, 97 % at 24);
+//   * latency-bound time: every batch of co-resident CTAs needs the serial FP64 proposal/setup phase plus one warp's
+//     chain of tiles (a tile = one dependent pass over a transmission curve);
+//   * a tile is always 64 (walker, point) pairs of ONE filter, so small wpb wastes lanes when a filter has few points:
+//     that is in ntiles(l);
+//   * clusters and very small CTAs carry measured penalties (redundant setup per CTA, co-scheduling constraints).
 int count_tiles(const lcf_problem *p, int l) {
     const int slots = 2 * (32 >> l), N = p->dev.npoints;
     int tiles = 0, i = 0;
@@ -256,9 +259,8 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const bool f32 = p->precision == LCF_PRECISION_FP32;
     const double nbb = p->dev.model == 4 ? 2. : 1.;
     const double K = std::max(1., p->mean_samples) * nbb;            // Planck samples per (walker, point)
-    const double pipe_tile = 64. * (f32 ? (1.0 * K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
-    const double lat_tile = (f32 ? 28. : 220.) * K + 400.;           // clocks one warp needs for a tile on its own
-    const double fixed = 25000.;                                     // proposal + priors + FP64 model constants
+    const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
+    const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
     double best = 1e300;
     Shape bs = {5, 16, 1, 0};
     for (int l = 5; l >= 0; --l) {
@@ -271,18 +273,23 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
             const size_t sm = smem_bytes(p, 1 << l, nw);
             if (sm > kSmemMax) continue;
             int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
-            occ = std::max(1, std::min(occ, 16));
+            occ = std::max(1, std::min(occ, 32));
             for (int S = 1; S <= kMaxCluster; S <<= 1) {
                 if (g_tune_cluster > 0 && S != g_tune_cluster) continue;
                 if (S > 1 && (long long)nw * S > 2LL * ntiles && g_tune_cluster == 0) break;    // nothing left to split
                 const double tiles_warp = (double)((ntiles + nw * S - 1) / (nw * S));
                 const double tiles_cta = std::min<double>(ntiles, tiles_warp * nw);
                 const long long ctas = groups * S;
-                const long long per_wave = (long long)sms * occ;
-                const long long full = ctas / per_wave, rem = ctas - full * per_wave;
-                auto wave = [&](double cps) { return std::max(cps * tiles_cta * pipe_tile, tiles_warp * lat_tile) + fixed; };
-                double cost = (double)full * wave(occ);
-                if (rem > 0) cost += wave(std::ceil((double)rem / sms));
+                const double n = (double)((ctas + sms - 1) / sms);               // CTAs on the busiest SM
+                const double resident = std::min<double>(n, occ);
+                const double w = std::min(32., resident * nw);
+                const double xu_eff = w >= 8. ? 1. - 0.29 * (32. - w) * (32. - w) / 576. : 0.71 * w / 8.;
+                const double fixed = 12000. + (S > 1 ? 3000. : 0.);            // proposal + priors + FP64 model constants (+ DSMEM reduce)
+                const double t_xu = n * tiles_cta * pipe_tile / xu_eff + 0.3 * fixed;
+                const double t_lat = std::ceil(n / occ) * (fixed + tiles_warp * lat_tile);
+                double cost = std::max(t_xu, t_lat);
+                for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
+                if (nw < 8) cost *= 1.15;
                 if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; }
             }
         }
@@ -298,6 +305,9 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
+    if (getenv("LCF_DEBUG_SHAPE"))
+        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, %zu B smem (model %d, modelled %.0f clk)\n",
+                Ns, 1 << bs.l, bs.nw, bs.cluster, bs.smem, p->dev.model, best);
     *out = bs;
     return 0;
 }

@@ -313,9 +313,14 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec4<R>::type *__res
 //  * the FP32 arithmetic uses Blackwell's packed FMUL2 / FADD2 / FFMA2 (one issue slot for two lanes of work).
 // => 1 MUFU.EX2 per Planck sample and nothing else on the XU pipe.  Measured in isolation (tools/microbench/loops.cu,
 // B200, 32 warps/SM): 14.6 samples/clk/SM against 12.2 for the MUFU.RCP version and 15.7 for a bare EX2 stream.
-// Callers guarantee that the four exponents sum to <= 126 (the product of four denominators stays a normal float)
-// and that every exponent is >= 1/16 (no cancellation in 2^x - 1).
+// Callers guarantee that every exponent is >= 1/16 (no cancellation in 2^x - 1) and either that the four exponents
+// sum to <= 124 (the product of four denominators stays a normal float) or they ask for the CLAMP variant.
+// CLAMP: exponents are capped at 31 (h nu / k T = 21.5), so four denominators multiply to < 2^124 whatever the
+// temperature; a capped sample contributes w / (2^31 - 1) < 5e-10 w instead of something smaller still.
+constexpr float kXClamp = 31.f;
+template <bool CLAMP>
 __device__ __forceinline__ float2 ex2m1_pair(float2 x) {                 // (2^x.x - 1, 2^x.y - 1)
+    if (CLAMP) { x.x = fminf(x.x, kXClamp); x.y = fminf(x.y, kXClamp); }
     return __fadd2_rn(make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y)), make_float2(-1.f, -1.f));
 }
 __device__ __forceinline__ float rcp_newton(float x) {                   // x positive and normal
@@ -337,7 +342,7 @@ __device__ __forceinline__ float2 rcp_newton2(float2 x) {
 // (a) two blackbodies (points A, B of one walker) x the two samples of a pair record; two records per iteration.
 //     Pointer-bumped with compile-time strides so that the loop bookkeeping is 2 adds + compare + branch (integer
 //     multiply-adds would land on the FMA pipe, which is the second-busiest one here).
-template <bool TAB>
+template <bool TAB, bool CLAMP>
 __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, float &SA, float &SB) {
     constexpr int ts = kTabStride;
@@ -357,8 +362,8 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
             a0 = make_float2(s0.x, s0.y); w0 = make_float2(s0.z, s0.w);
             a1 = make_float2(s1.x, s1.y); w1 = make_float2(s1.z, s1.w);
         }
-        const float2 dA0 = ex2m1_pair(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair(__fmul2_rn(a0, iB2));   // (dA(k0), dA(k1))
-        const float2 dA1 = ex2m1_pair(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair(__fmul2_rn(a1, iB2));
+        const float2 dA0 = ex2m1_pair<CLAMP>(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair<CLAMP>(__fmul2_rn(a0, iB2));   // (dA(k0), dA(k1))
+        const float2 dA1 = ex2m1_pair<CLAMP>(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair<CLAMP>(__fmul2_rn(a1, iB2));
         const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);                          // per sample: dA dB
         const float2 r = rcp_newton2(make_float2(p0.x * p0.y, p1.x * p1.y));                         // one per record
         const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));  // w/(dA dB)
@@ -372,7 +377,7 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
         float2 a, w;
         if (TAB) { a = *reinterpret_cast<const float2 *>(pb); w = tab[0]; }
         else { const float4 s = pb[0]; a = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2)), dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair<CLAMP>(__fmul2_rn(a, iA2)), dB = ex2m1_pair<CLAMP>(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_newton(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -385,6 +390,7 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
 
 // (b) ShockCooling4: two points x (T, 0.74 T) (models.py:629-630); each quad = (A, A*, B, B*) at ONE sample, the two
 //     samples of the pair record are processed side by side in the packed lanes (two reciprocals per record).
+template <bool CLAMP>
 __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float &SA,
                                                     float &SAs, float &SB, float &SBs) {
     const float c = (float)(1. / 0.74);
@@ -394,8 +400,8 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
     for (const float4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
         const float4 s = *pb;
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair(__fmul2_rn(x, iA2)), dAs = ex2m1_pair(__fmul2_rn(x, iAs2));
-        const float2 dB = ex2m1_pair(__fmul2_rn(x, iB2)), dBs = ex2m1_pair(__fmul2_rn(x, iBs2));
+        const float2 dA = ex2m1_pair<CLAMP>(__fmul2_rn(x, iA2)), dAs = ex2m1_pair<CLAMP>(__fmul2_rn(x, iAs2));
+        const float2 dB = ex2m1_pair<CLAMP>(__fmul2_rn(x, iB2)), dBs = ex2m1_pair<CLAMP>(__fmul2_rn(x, iBs2));
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
         const float2 r = rcp_newton2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
@@ -554,26 +560,38 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
         const float imin = fminf(i0, i1);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
-        const bool fast = (rng.x * imin >= 0.0625f) && (xsum <= 126.f);
-        if (fast) {
+        if (rng.x * imin >= 0.0625f) {                      // no cancellation in 2^x - 1 anywhere in the filter
+            const bool clamp = xsum > 124.f;                 // the product of four denominators could overflow: cap the exponents
+#ifdef LCF_X_TIMING
+            atomicAdd(&g_phase_clk[clamp ? 7 : 6], 1ull);        // lane-tiles on the plain / clamped fast path
+#endif
             const float4 *bf = reinterpret_cast<const float4 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
             float S0, S1;
             if (MODEL == 4) {
                 float S0s, S1s;
-                planck_quad_sc4_f32(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                if (clamp) planck_quad_sc4_f32<true>(bf, K2, i0, i1, S0, S0s, S1, S1s);
+                else planck_quad_sc4_f32<false>(bf, K2, i0, i1, S0, S0s, S1, S1s);
                 if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
-                if (MODEL == 3) planck_quad_f32<true>(bf, K2, i0, i1, tf, S0, S1);
-                else planck_quad_f32<false>(bf, K2, i0, i1, nullptr, S0, S1);
+                if (MODEL == 3) {
+                    if (clamp) planck_quad_f32<true, true>(bf, K2, i0, i1, tf, S0, S1);
+                    else planck_quad_f32<true, false>(bf, K2, i0, i1, tf, S0, S1);
+                } else {
+                    if (clamp) planck_quad_f32<false, true>(bf, K2, i0, i1, nullptr, S0, S1);
+                    else planck_quad_f32<false, false>(bf, K2, i0, i1, nullptr, S0, S1);
+                }
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
             }
             return;
         }
     }
-    // careful path (FP64 always; FP32 when 2^x - 1 would cancel or the quad product would overflow)
+    // careful path (FP64 always; FP32 when 2^x - 1 would cancel: Rayleigh-Jeans regime)
+#ifdef LCF_X_TIMING
+    atomicAdd(&g_phase_clk[5], 1ull << 40);                   // lane-tiles on the careful path (upper bits of slot 5)
+#endif
     if (n0) {
         const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f0.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f0.invT, nullptr, 0);
         y0 = f0.amp * S;

@@ -41,6 +41,14 @@ def kasen_sifto_truth(t, filter_names, z):
 
 
 def emit(name, walkers, steps, ms, samples_per_eval, extra=None):
+    from lightcurve_fitting_b200 import _capi
+    L = _capi.lib()
+    if hasattr(L, 'lcf_debug_phase_clocks'):      # experiment builds (-DLCF_X_TIMING): per-phase SM clocks summed over CTAs
+        import ctypes as C
+        buf = (C.c_uint64 * 8)()
+        L.lcf_debug_phase_clocks(buf)
+        extra = dict(extra or {}, phase_clk_sum=[int(v) for v in buf[:5]] + [int(buf[5]) & ((1 << 40) - 1)],
+                     lane_tiles={'fast': int(buf[6]), 'clamped': int(buf[7]), 'careful': int(buf[5]) >> 40})
     ws = walkers * steps / (ms * 1e-3)
     out = {'config': name, 'walker_steps_per_s': ws, 'ms': ms, 'walkers': walkers, 'steps': steps,
            'planck_samples_per_eval': samples_per_eval, 'planck_samples_per_s': ws * samples_per_eval}
@@ -54,6 +62,8 @@ def main():
     ap.add_argument('--nlc', type=int, default=1250)
     ap.add_argument('--nepochs', type=int, default=500)
     ap.add_argument('--only', default='')
+    ap.add_argument('--tune', default='', help='wpb,warps,cluster launch-shape override(s), separated by ;')
+    ap.add_argument('--short', action='store_true', help='fewer steps (shape sweeps)')
     args = ap.parse_args()
     import __graft_entry__ as g
     g.build()
@@ -61,7 +71,17 @@ def main():
     from lightcurve_fitting_b200.bolometric import BatchSampler
     from lightcurve_fitting_b200.sampler import EnsembleSampler
     only = set(args.only.split(',')) if args.only else None
+    from lightcurve_fitting_b200 import _capi
+    for tune in (args.tune.split(';') if args.tune else ['']):
+        if tune:
+            _capi.check(_capi.lib().lcf_set_tuning_ex(*[int(x) for x in tune.split(',')]))
+        run_configs(args, only, tune, synthetic, BatchSampler, EnsembleSampler)
+
+
+def run_configs(args, only, tune, synthetic, BatchSampler, EnsembleSampler):
     rng = np.random.default_rng(0)
+    n1 = 100 if args.short else 1000
+    tag_t = (' [tune %s]' % tune) if tune else ''
 
     if not only or 'cfg1' in only:
         for window, tag in (((57468., 57485.), 'N=149 early window'), (None, 'N=758 full')):
@@ -69,11 +89,13 @@ def main():
             prob = wl.device_problem(args.precision)
             # (a) half-step launches (k_pass), as lightcurve_mcmc runs it
             s = EnsembleSampler(100, wl.ndim, prob, seed=1)
-            s.run_mcmc(wl.start(100, rng), 1000, store=False)
+            s.run_mcmc(wl.start(100, rng), n1, store=False)
             s.reset()
-            s.run_mcmc(None, 1000)
-            emit('cfg1 %s k_pass' % tag, 100, 1000, s.last_ms, wl.planck_samples_per_eval(),
+            s.run_mcmc(None, n1)
+            emit('cfg1 %s k_pass%s' % (tag, tag_t), 100, n1, s.last_ms, wl.planck_samples_per_eval(),
                  {'launches': s.last_launches, 'acceptance': float(s.acceptance_fraction.mean())})
+            if args.short:
+                continue
             # (b) the whole chain in one launch (k_chain)
             b = BatchSampler([prob], 100, seed=1)
             b.run(wl.start(100, rng)[None], 1000, 1000)
@@ -97,7 +119,7 @@ def main():
         s = EnsembleSampler(10_000, wl.ndim, prob, seed=3)
         s.run_mcmc(wl.start(10_000, rng), 20, store=False, skip_initial_state_check=True)
         s.run_mcmc(None, 50)
-        emit('cfg4 CompanionShocking3 N=1000, 1e4 walkers', 10_000, 50, s.last_ms, wl.planck_samples_per_eval(),
+        emit('cfg4 CompanionShocking3 N=1000, 1e4 walkers' + tag_t, 10_000, 50, s.last_ms, wl.planck_samples_per_eval(),
              {'acceptance': float(s.acceptance_fraction.mean())})
 
     if not only or 'cfg5' in only:

@@ -44,8 +44,8 @@ __device__ __forceinline__ void quad_nr(const float4 *__restrict__ b4, int k2, f
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = NR == 1 ? rcp_nr(p.x * p.y) : rcp_nr2(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -64,8 +64,8 @@ __device__ __forceinline__ void quad_nr_u4(const float4 *__restrict__ b4, int k2
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_nr(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -83,8 +83,8 @@ __device__ __forceinline__ void quad_u4(const float4 *__restrict__ b4, int k2, f
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcpf_(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -119,8 +119,8 @@ __device__ __forceinline__ void quad_nr_x2(const float4 *__restrict__ b4, int k2
             const float4 s0 = b4[k], s1 = b4[k + 1];
             a0 = make_float2(s0.x, s0.y); w0 = make_float2(s0.z, s0.w); a1 = make_float2(s1.x, s1.y); w1 = make_float2(s1.z, s1.w);
         }
-        const float2 dA0 = ex2m1_pair(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair(__fmul2_rn(a0, iB2));
-        const float2 dA1 = ex2m1_pair(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair(__fmul2_rn(a1, iB2));
+        const float2 dA0 = ex2m1_pair<false>(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair<false>(__fmul2_rn(a0, iB2));
+        const float2 dA1 = ex2m1_pair<false>(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair<false>(__fmul2_rn(a1, iB2));
         const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);
         const float2 r = rcp_nr_x2(make_float2(p0.x * p0.y, p1.x * p1.y));
         const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));
@@ -132,7 +132,7 @@ __device__ __forceinline__ void quad_nr_x2(const float4 *__restrict__ b4, int k2
         float2 a, w;
         if (TAB) { a = *reinterpret_cast<const float2 *>(b4 + k); w = tab[0]; }
         else { const float4 s = b4[k]; a = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
-        const float2 dA = ex2m1_pair(__fmul2_rn(a, iA2)), dB = ex2m1_pair(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2)), dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_nr(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -150,8 +150,8 @@ __device__ __forceinline__ void sc4_nr(const float4 *__restrict__ b4, int k2, fl
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair(__fmul2_rn(x, iA2)), dAs = ex2m1_pair(__fmul2_rn(x, iAs2));
-        const float2 dB = ex2m1_pair(__fmul2_rn(x, iB2)), dBs = ex2m1_pair(__fmul2_rn(x, iBs2));
+        const float2 dA = ex2m1_pair<false>(__fmul2_rn(x, iA2)), dAs = ex2m1_pair<false>(__fmul2_rn(x, iAs2));
+        const float2 dB = ex2m1_pair<false>(__fmul2_rn(x, iB2)), dBs = ex2m1_pair<false>(__fmul2_rn(x, iBs2));
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
         const float2 r = rcp_nr_x2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(T, 1024 / T) kloop(float *out, const float4 *b
     float accA = 0.f, accB = 0.f;
     for (int r = 0; r < REP; ++r) {
         float SA = 0, SB = 0, SAs = 0, SBs = 0;
-        if (V == 0) planck_quad_f32<false>(bank, K2, iA, iB, nullptr, 0, SA, SB);
-        if (V == 1) planck_quad_f32<true>(bank, K2, iA, iB, tab + lane, 32, SA, SB);
+        if (V == 0) planck_quad_f32<false, false>(bank, K2, iA, iB, nullptr, SA, SB);
+        if (V == 1) planck_quad_f32<true, false>(bank, K2, iA, iB, tab + lane, SA, SB);
         if (V == 2) quad_nr<1>(bank, K2, iA, iB, SA, SB);
         if (V == 3) quad_nr<2>(bank, K2, iA, iB, SA, SB);
         if (V == 4) oct_em<0>(bank, K2, iA, iB, SA, SB);
@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(T, 1024 / T) kloop(float *out, const float4 *b
         if (V == 10) quad_nr_x2<false>(bank, K2, iA, iB, nullptr, 0, SA, SB);
         if (V == 11) quad_nr_x2<true>(bank, K2, iA, iB, tab + lane, 32, SA, SB);
         if (V == 12) { sc4_nr(bank, K2, iA, iB, SA, SAs, SB, SBs); SA += SAs; SB += SBs; }
-        if (V == 7) { planck_quad_sc4_f32(bank, K2, iA, iB, SA, SAs, SB, SBs); SA += SAs; SB += SBs; }
+        if (V == 13) planck_quad_f32<true, true>(bank, K2, iA, iB, tab + lane, SA, SB);
+        if (V == 7) { planck_quad_sc4_f32<false>(bank, K2, iA, iB, SA, SAs, SB, SBs); SA += SAs; SB += SBs; }
         accA += SA; accB += SB;
         iA += 1e-6f; iB += 1e-6f;
     }
@@ -279,10 +280,10 @@ int main() {
     ms[4] = time_ms([&] { kmufu<4><<<blocks, threads>>>(out, 1.0f); });
     for (int i = 0; i < 5; ++i)
         printf("%-16s %8.3f ms -> %6.2f lane-ops/clk/SM\n", mn[i], ms[i], 2048.0 * 8 * blocks * threads / (ms[i] * 1e-3) / clk / sms);
-    const char *vn[13] = {"quad MUFU.RCP (shipped)", "quad MUFU.RCP + per-lane weight table", "quad Newton rcp (3 quadratic)", "quad Newton rcp (2 cubic)",
+    const char *vn[14] = {"quad MUFU.RCP (shipped)", "quad MUFU.RCP + per-lane weight table", "quad Newton rcp (3 quadratic)", "quad Newton rcp (2 cubic)",
                          "oct e/(1-e) MUFU.RCP", "oct e/(1-e) Newton (3 quadratic)", "oct e/(1-e) Newton (2 cubic)", "SC4 quad (T, 0.74T) MUFU.RCP",
                          "quad Newton rcp, unroll 4", "quad MUFU.RCP, unroll 4",
-                         "quad packed Newton, 2 records/iter", "quad packed Newton, 2 records/iter + table", "SC4 quad packed Newton"};
+                         "quad packed Newton, 2 records/iter", "quad packed Newton, 2 records/iter + table", "SC4 quad packed Newton", "shipped + per-sample clamp"};
     auto report = [&](int i, float ms, int nb, int nt) {
         const double samples = (double)nb * nt * REP * K2 * 4 * ((i == 7 || i == 12) ? 2 : 1);
         printf("%-40s %4d thr x %4d CTAs %8.3f ms -> %6.2f Planck samples/clk/SM\n", vn[i], nt, nb, ms, samples / (ms * 1e-3) / clk / sms);
@@ -290,7 +291,7 @@ int main() {
 #define RUN(V, T, NB) report(V, time_ms([&] { kloop<V, T><<<NB, T>>>(out, bank, 1.0f); }), NB, T)
     RUN(0, 512, blocks); RUN(1, 512, blocks); RUN(2, 512, blocks); RUN(3, 512, blocks); RUN(4, 512, blocks);
     RUN(5, 512, blocks); RUN(7, 512, blocks); RUN(8, 512, blocks); RUN(9, 512, blocks);
-    RUN(10, 512, blocks); RUN(11, 512, blocks); RUN(12, 512, blocks);
+    RUN(10, 512, blocks); RUN(11, 512, blocks); RUN(12, 512, blocks); RUN(13, 512, blocks);
     printf("-- warps per SM sweep (2 CTAs per SM; 1 CTA per SM for the last) --\n");
     RUN(0, 384, blocks); RUN(0, 256, blocks); RUN(0, 128, blocks); RUN(0, 512, sms);
     RUN(2, 384, blocks); RUN(2, 256, blocks); RUN(2, 128, blocks); RUN(2, 512, sms);
