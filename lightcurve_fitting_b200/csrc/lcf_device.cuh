@@ -194,22 +194,60 @@ struct WalkerSetup {
     double t1;     // SiFTO t_peak (CompanionShocking*)
 };
 
+// The FP64 transcendentals of a walker's constants are independent of each other, so the proposal phase computes
+// them one per THREAD (walker_term, k < kTerms) instead of one walker per thread (a double-precision pow is a
+// ~300-instruction dependent chain: ten of them back to back used to be the serial prologue of every CTA), and
+// setup_walker then only combines them with a few multiplications.
+constexpr int kMaxTerms = 8;
+template <int MODEL> struct ModelTerms { static constexpr int value = (MODEL == 1 || MODEL == 3) ? 4 : (MODEL == 4 ? 8 : ((MODEL >= 5 && MODEL <= 7) ? 3 : 0)); };
+
+// term k of a walker = pow(base, expo) [or power(): 0 for a non-positive base, models.py:42-48] [or cos(base)]:
+// ONE pow call per thread whatever k is, so the lanes of a warp never diverge into different pow instances.
+template <int MODEL>
+__device__ inline double walker_term(const ProblemDev &P, const double *p, int k) {
+    const double *mc = P.mc;
+    double base = 1., expo = 1.;
+    bool guarded = false;                                  // power() semantics
+    if (MODEL == 1 || MODEL == 3) {
+        // BaseShockCooling.temperature_radius, models.py:260-269 (kappa = 1); mc: A, a, alpha, eps1, eps2, L_0, T_0, Tph_to_Tcol
+        const double v = p[0], Menv = p[1], f = p[2], Rr = p[3];
+        if (k == 0) { base = v * v / f; expo = mc[3]; guarded = true; }
+        else if (k == 1) { base = Rr; expo = 0.25; }
+        else if (k == 2) { base = v / f; expo = -mc[4]; guarded = true; }
+        else { base = Menv / v; expo = 0.5; }
+    } else if (MODEL == 4) {
+        // ShockCooling4.temperature_radius, models.py:584-587 (kappa = 1)
+        const double v = p[0], f = p[2], Rr = p[3];
+        const double ex[8] = {1.26, -1.13, -0.13, 0.78, 2.11, 0.11, -0.32, 0.03};
+        const int which = (0x20210210 >> (4 * k)) & 3;       // k -> 0: R, 1: v, 2: f   (R v f R v f R f)
+        base = which == 0 ? Rr : (which == 1 ? v : f);
+        expo = ex[k];
+    } else if (MODEL >= 5 && MODEL <= 7) {
+        // BaseCompanionShocking.temperature_radius, models.py:752-754 (kappa = 1)
+        const double Mv7 = (MODEL == 7) ? 1. : p[2];
+        if (k == 0) { base = p[1]; expo = 36.; }
+        else if (k == 1) { base = Mv7; expo = 1. / 9.; guarded = true; }
+        else return (MODEL == 7) ? cos(p[2] * (3.14159265358979323846 / 180.)) : 0.;
+    } else {
+        return 0.;
+    }
+    if (guarded && !(base > 0.)) return 0.;
+    return pow(base, expo);
+}
 
 template <int MODEL>
-__device__ inline void setup_walker(const ProblemDev &P, const double *p, WalkerSetup &s) {
+__device__ inline void setup_walker(const ProblemDev &P, const double *p, const double *term, WalkerSetup &s) {
     const double *mc = P.mc;
     for (int i = 0; i < kNumWC; ++i) s.wc[i] = 0.;
     s.t0 = 0.; s.t1 = 0.;
     const double c3sq = P.c3sq, k_kB = P.kB;
     if (MODEL == 1 || MODEL == 3) {
-        // BaseShockCooling.temperature_radius, models.py:260-269 (kappa = 1)
-        // mc: A, a, alpha, eps1, eps2, L_0, T_0, Tph_to_Tcol
-        double v = p[0], Menv = p[1], f = p[2], Rr = p[3];
+        double v = p[0], Rr = p[3];
         double texp = (MODEL == 3) ? p[6] : p[4];
-        double KT = mc[6] * pw(v * v / f, mc[3]) * pow(Rr, 0.25) * mc[7] / k_kB;
-        double KL = c3sq * mc[5] * pw(v / f, -mc[4]) * v * v * Rr * mc[0];
+        double KT = mc[6] * term[0] * term[1] * mc[7] / k_kB;
+        double KL = c3sq * mc[5] * term[2] * v * v * Rr * mc[0];
         if (MODEL == 3) KL = KL / (p[4] * p[4]);          // flux = c4*lum/dist^2 (c4 folded into the bank)
-        double ttr = 19.5 * pow(Menv / v, 0.5);
+        double ttr = 19.5 * term[3];
         double base = mc[1] / ttr;                        // (a t / t_tr) > 0  <=>  a/t_tr > 0 for t > 0
         s.wc[0] = KT; s.wc[1] = KL;
         s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
@@ -227,13 +265,12 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
         s.wc[5] = (p[0] > 0.) ? s.wc[1] / (p[0] * p[0] * p[0] * p[0]) : 0.;
         s.t0 = p[3];
     } else if (MODEL == 4) {
-        // ShockCooling4.temperature_radius, models.py:584-587 (kappa = 1)
         // mc: A, a, alpha, L_br_0, T_col_br_0, t_br_0, t_tr_0
-        double v = p[0], Menv = p[1], f = p[2], Rr = p[3];
-        double t_br = mc[5] * pow(Rr, 1.26) * pow(v, -1.13) * pow(f, -0.13);
-        double L_br = mc[3] * pow(Rr, 0.78) * pow(v, 2.11) * pow(f, 0.11);
+        double v = p[0], Menv = p[1];
+        double t_br = mc[5] * term[0] * term[1] * term[2];
+        double L_br = mc[3] * term[3] * term[4] * term[5];
         // models.py:586 as written: v_s ** 0.58 ** f_rho_M ** 0.03 is right-associative
-        double T_br = mc[4] * pow(Rr, -0.32) * pow(v, pow(0.58, pow(f, 0.03)));
+        double T_br = mc[4] * term[6] * pow(v, pow(0.58, term[7]));
         double t_tr = mc[6] * sqrt(Menv / v);
         double base = mc[1] / t_tr;
         s.wc[0] = T_br / k_kB;
@@ -244,17 +281,15 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, Walker
         s.wc[5] = 1. / s.wc[0];                             // 1/T on the late branch:  wc5 ttilde^0.45
         s.t0 = p[4];
     } else if (MODEL == 5 || MODEL == 6 || MODEL == 7) {
-        // BaseCompanionShocking.temperature_radius, models.py:752-754 (kappa = 1)
-        double a13 = p[1];
         double Mv7 = (MODEL == 7) ? 1. : p[2];
-        double cK = pow(a13, 36.) * Mv7;
+        double cK = term[0] * Mv7;
         s.wc[0] = 25. * pw(cK, 1. / 144.);                 // T = wc0 * t^(-74/144)
-        double rk = 2.7 * pw(Mv7, 1. / 9.);
+        double rk = 2.7 * term[1];
         s.wc[1] = rk * rk;                                  // R^2 = wc1 * t^(14/9)
         s.wc[2] = 1.;
         if (MODEL == 7) {                                   // models.py:1042-1043
             double th = p[2] * (3.14159265358979323846 / 180.);
-            s.wc[2] = (0.5 * cos(th) + 0.5) * (0.14 * (th * th) - 0.4 * th + 1.);
+            s.wc[2] = (0.5 * term[2] + 0.5) * (0.14 * (th * th) - 0.4 * th + 1.);
         }
         s.wc[3] = p[4];                                     // stretch
         s.wc[8] = (s.wc[0] > 0.) ? 1. / s.wc[0] : 0.;       // 1/T = wc8 t^(74/144)
@@ -625,9 +660,10 @@ __device__ __forceinline__ void dsmem_store_f64(double *local, uint32_t rank, do
 // shared-memory carve-up (dynamic), identical for the half-step and the chain kernels
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxCluster = 8;      // portable cluster size limit
+constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model terms, prior terms, ln z, ln u
 
 template <typename R> struct SmemLayout {
-    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_part, off_cpart, off_flag, off_bar, total;
+    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
@@ -638,6 +674,7 @@ template <typename R> struct SmemLayout {
         off_q = o;    o += (size_t)wpb * ndim * sizeof(double);
         off_lp = o;   o += (size_t)wpb * sizeof(double);
         off_z = o;    o += (size_t)wpb * sizeof(double);
+        off_term = o; o += (size_t)wpb * kTermStride * sizeof(double);
         off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
         off_cpart = o; o += (size_t)kMaxCluster * wpb * sizeof(double);
         off_flag = o; o += (size_t)wpb * sizeof(int);                             o = (o + 15) & ~(size_t)15;
@@ -670,6 +707,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     double *s_q = reinterpret_cast<double *>(smem + L.off_q);
     double *s_lp = reinterpret_cast<double *>(smem + L.off_lp);
     double *s_z = reinterpret_cast<double *>(smem + L.off_z);
+    double *s_term = reinterpret_cast<double *>(smem + L.off_term);
     double *s_part = reinterpret_cast<double *>(smem + L.off_part);
     double *s_cpart = reinterpret_cast<double *>(smem + L.off_cpart);
     int *s_flag = reinterpret_cast<int *>(smem + L.off_flag);
@@ -686,12 +724,13 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         for (int i = tid; i < P.nfilters; i += blockDim.x) s_finfo[i] = P.finfo[i];
     }
 
-    // ---- phase 1: proposal + prior + per-walker model constants (FP64), one thread per walker ----
+    // ---- phase 1: proposal + prior + per-walker model constants (FP64) ------------------------------
     // (every CTA of a cluster repeats it for the same walkers: bitwise identical, no communication)
+    // 1a: one thread per walker: stretch-move draw and proposal
+    constexpr int NT = ModelTerms<MODEL>::value;
+    const bool with_prior = Mv.mode == MODE_MOVE || Mv.mode == MODE_LOGPOST;
     if (tid < wpb) {
         const long long i = g * wpb + tid;
-        int flag = 1;                                    // 1 = skip likelihood
-        double lp = 0.;
         if (i < Mv.Ns) {
             double q[kMaxDim];
             if (Mv.mode == MODE_MOVE) {
@@ -709,24 +748,53 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                     double a = u + 1.;                   // ((a-1) u + 1)^2 / a with a = 2
                     z = a * a * 0.5;
                     pr = (long long)(((unsigned long long)r[2] * (unsigned long long)Mv.Nc) >> 32);
+                    s_term[tid * kTermStride + NT + kMaxDim + 1] = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);   // u of the accept test
                 }
                 const long long crow = Mv.comp_rows ? (long long)Mv.comp_rows[pr] : Mv.comp_base + pr;
                 const double *s = Mv.coords + row * D, *c = Mv.coords + crow * D;
                 for (int d = 0; d < D; ++d)              // q = c - (c - s) z, numpy op order, no FMA
                     q[d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), z));
-                s_z[tid] = z;                            // kept for the accept test
+                s_z[tid] = z;
             } else {
                 const int nq = (Mv.mode == MODE_MODEL) ? P.nmodel : D;
                 for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * nq + d];
                 for (int d = nq; d < D; ++d) q[d] = 0.;
             }
             for (int d = 0; d < D; ++d) s_q[tid * D + d] = q[d];
-            if (Mv.mode == MODE_MOVE || Mv.mode == MODE_LOGPOST)
-                for (int d = 0; d < D; ++d) lp += prior_logp(P.prior, d, q[d]);
+        }
+    }
+    __syncthreads();
+    // 1b: one thread per (walker, term): FP64 transcendentals of the model constants, log-priors, ln z and ln u
+    {
+        const int per = NT + D + 2;
+        for (int idx = tid; idx < wpb * per; idx += blockDim.x) {
+            const int k = idx >> Mv.wpb_log2, w1 = idx & (wpb - 1);   // term-major: a warp works on one kind of term
+            if (g * wpb + w1 >= Mv.Ns) continue;
+            const double *q = s_q + w1 * D;
+            double *t = s_term + w1 * kTermStride;
+            if (k < NT) t[k] = walker_term<MODEL>(P, q, k);
+            else if (k < NT + D) { if (with_prior) t[NT + (k - NT)] = prior_logp(P.prior, k - NT, q[k - NT]); }
+            else if (Mv.mode == MODE_MOVE) {
+                if (k == NT + D) t[NT + kMaxDim] = log(s_z[w1]);
+                else if (!Mv.luin) t[NT + kMaxDim + 1] = log(t[NT + kMaxDim + 1]);
+            }
+        }
+    }
+    __syncthreads();
+    // 1c: one thread per walker: sum of the log-priors (same order as the reference's loop), model constants
+    if (tid < wpb) {
+        const long long i = g * wpb + tid;
+        int flag = 1;                                    // 1 = skip likelihood
+        double lp = 0.;
+        if (i < Mv.Ns) {
+            const double *q = s_q + tid * D;
+            const double *t = s_term + tid * kTermStride;
+            if (with_prior)
+                for (int d = 0; d < D; ++d) lp += t[NT + d];
             if (!isinf(lp)) {                            // fitting.py:125: prior -inf skips the likelihood
                 flag = 0;
                 WalkerSetup ws;
-                setup_walker<MODEL>(P, q, ws);
+                setup_walker<MODEL>(P, q, t, ws);
                 if (P.use_sigma) ws.wc[7] = q[D - 1] * q[D - 1];
                 for (int k = 0; k < kNumWC; ++k) s_wc[tid * kNumWC + k] = (R)ws.wc[k];
                 s_t[tid * 2] = ws.t0;
@@ -844,17 +912,10 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             } else {
                 const long long row = Mv.act_rows ? (long long)Mv.act_rows[i] : Mv.act_base + i;
                 const long long j = (row < Mv.n0) ? 2 * row : 2 * (row - Mv.n0) + 1;
-                double logu;
-                if (Mv.luin) {
-                    logu = Mv.luin[i];
-                } else {
-                    uint32_t r[4];
-                    philox4x32_10((uint32_t)j, Mv.ctr, (uint32_t)(j >> 32), 0u, (uint32_t)Mv.seed, (uint32_t)(Mv.seed >> 32), r);
-                    logu = log(((double)r[3] + 0.5) * (1.0 / 4294967296.0));
-                }
+                const double logu = Mv.luin ? Mv.luin[i] : s_term[tid * kTermStride + NT + kMaxDim + 1];
                 if (nlp != nlp) atomicAdd(Mv.nanflag, 1);           // emcee: "Probability function returned NaN"
                 const double old = Mv.logp[row];
-                const double lnpdiff = (double)(D - 1) * log(s_z[tid]) + nlp - old;
+                const double lnpdiff = (double)(D - 1) * s_term[tid * kTermStride + NT + kMaxDim] + nlp - old;
                 const bool acc = lnpdiff > logu;
                 double *crd = Mv.coords + row * D;
                 if (acc) {
