@@ -100,6 +100,9 @@ def oracle_truth(model_name, t, filter_names, params, z):
 
 
 MODEL = 'sc3'
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_pass<3,float> launch of this workload (ncu --set full capture
+# summarised in profiles/r02_ncu_sc3_fp32.txt); per launch, like roofline.achieved
+NCU_DRAM_BYTES_PER_LAUNCH = 6782208
 
 
 def workload(truth, npoints=NPOINTS):
@@ -286,8 +289,10 @@ def run_ours(args):
     samples_per_eval = wl.planck_samples_per_eval()
     samples_per_s_gpu = value * samples_per_eval / world
     sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
-    peak_samples = BALANCED_SAMPLES_PER_CLK_SM * SMS * sm_mhz * 1e6
-    naive_samples = MUFU_LANES_PER_CLK_SM / 2 * SMS * sm_mhz * 1e6
+    # Roofline: the XU (MUFU) pipe.  One MUFU.EX2 per Planck sample is irreducible (the reciprocal and everything else run
+    # on the FMA pipe), and the pipe issues 16 lanes/clk/SM (measured: 15.7, profiles/r02_microbench_loops.txt).
+    peak_samples = MUFU_LANES_PER_CLK_SM * SMS * sm_mhz * 1e6
+    balanced_samples = BALANCED_SAMPLES_PER_CLK_SM * SMS * sm_mhz * 1e6
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -296,20 +301,24 @@ def run_ours(args):
     chain_bytes_per_step = args.walkers * (D + 1) * 8
     hbm_gbs = chain_bytes_per_step * args.steps / (ms * 1e-3) / 1e9
     roofline = {
-        'bound': 'fp32+sfu arithmetic (the path has no dense contraction and moves ~72 B of HBM per walker-step)',
+        'bound': 'sfu (XU pipe: one MUFU.EX2 per Planck sample; no dense contraction, ~72 B of HBM per walker-step)',
         'kernel': 'lcf::k_pass<%d,%s>' % (3 if MODEL == 'sc3' else 4, 'float' if args.precision == 'fp32' else 'double'),
         'achieved': samples_per_s_gpu / 1e9, 'peak': peak_samples / 1e9, 'unit': 'GPlanck-samples/s',
         'frac': samples_per_s_gpu / peak_samples,
-        'peak_basis': '13.5 Planck samples/clk/SM (balanced FMA+MUFU bound, SURVEY.md 8(d)) x 148 SMs x %.0f MHz (SM clock '
-                      'measured during the timed region); MEASURED_PEAKS.json has no FP32/SFU entry' % sm_mhz,
-        'frac_vs_naive_mufu': samples_per_s_gpu / naive_samples,
-        'naive_mufu_peak': naive_samples / 1e9,
-        'algorithmic_per_unit': '4 FP32 flops + 2 transcendentals per Planck sample; %d samples per log-posterior' % samples_per_eval,
+        'peak_basis': '16 MUFU lanes/clk/SM x 148 SMs x %.0f MHz (SM clock measured during the timed region), 1 MUFU.EX2 per '
+                      'Planck sample; MEASURED_PEAKS.json has no SFU entry, the pipe rate is confirmed by '
+                      'tools/microbench/loops.cu (15.7 lanes/clk/SM)' % sm_mhz,
+        'samples_per_clk_sm': samples_per_s_gpu / (SMS * sm_mhz * 1e6),
+        'frac_vs_survey_balanced_bound': samples_per_s_gpu / balanced_samples,
+        'survey_balanced_bound': '13.5 samples/clk/SM (SURVEY.md 8(d))',
+        'inner_loop_in_isolation_samples_per_clk_sm': 14.3,
+        'algorithmic_per_unit': '4 FP32 flops + 2 transcendentals per Planck sample (SURVEY.md 8(d)); %d samples per '
+                                'log-posterior; shipped loop: 1 MUFU + ~6.3 FP32 lane-ops per sample' % samples_per_eval,
         'fp32_tflops': 4 * samples_per_s_gpu / 1e12,
         'fp32_peak_tflops': 2 * 128 * SMS * sm_mhz * 1e6 / 1e12,
         'kernel_avg_ms': ms / launches,
         'hbm_gbs_chain_writeback': hbm_gbs, 'hbm_peak_gbs_measured': peaks.get('hbm_gbs'),
-        'traffic': None,
+        'traffic': NCU_DRAM_BYTES_PER_LAUNCH if (MODEL == 'sc3' and args.precision == 'fp32' and args.walkers == WALKERS_PER_GPU) else None,
     }
     cpu = cpu_baseline_1core(workload(oracle_truth, args.npoints), args.cpu_budget) if world == 1 and not args.no_cpu else None
     out = {
