@@ -208,7 +208,7 @@ def run_ours(args):
     rng = np.random.default_rng(1)
     p0 = wl.start(W_total, rng)
 
-    ens = ShardedEnsemble(prob, W_total, seed=1234, rank=rank, world=world)
+    ens = ShardedEnsemble(prob, W_total, seed=1234, rank=rank, world=world, exchange=args.exchange)
     ens.set_state(p0)
 
     def barrier():
@@ -260,7 +260,7 @@ def run_ours(args):
         assert np.isfinite(lnp).all() and chain.shape == (args.steps, W_total, D)
         api = 'EnsembleSampler.run_mcmc(host start positions) + get_chain() + get_log_prob()'
     else:
-        e2 = ShardedEnsemble(prob, W_total, seed=99, rank=rank, world=world)
+        e2 = ShardedEnsemble(prob, W_total, seed=99, rank=rank, world=world, exchange=args.exchange)
         e2.set_state(pin_in.numpy())
         e2.run(1, store=False)
         e2.finish()
@@ -328,7 +328,10 @@ def run_ours(args):
         'config': {'workload': 'cfg2: %s, synthetic %d-point 8-filter light curve, %d walkers per GPU'
                                % ('ShockCooling3' if MODEL == 'sc3' else 'ShockCooling4', args.npoints, args.walkers),
                    'walkers_total': W_total, 'ndim': D, 'planck_samples_per_eval': samples_per_eval,
-                   'parallelism': 'one ensemble, half-ensembles split over %d GPU(s), all-gather per half-step' % world,
+                   'parallelism': ('one ensemble, half-ensembles split over %d GPU(s); ' % world) +
+                                  ('accepted walkers stored into the peer replicas over NVLink by the half-step kernel itself, '
+                                   'device-side half-step flags, no NCCL on the data path' if args.exchange == 'p2p' else
+                                   'NCCL all-gather of the colour block per half-step'),
                    'l2': 'working set per CTA (light curve 24 KB + bank 3 KB) is L2/SMEM resident by design; walker '
                          'state streamed once per step; no inter-iteration flush needed (compute-bound: %.0f samples '
                          'per 72 B)' % samples_per_eval},
@@ -352,6 +355,7 @@ def main():
     ap.add_argument('--model', default='sc3', choices=['sc3', 'sc4'])
     ap.add_argument('--wpb', type=int, default=0)
     ap.add_argument('--cluster', type=int, default=0)
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='multi-GPU exchange of the shared ensemble')
     ap.add_argument('--nw', type=int, default=0)
     ap.add_argument('--cpu-budget', type=float, default=15.)
     ap.add_argument('--no-cpu', action='store_true')

@@ -177,6 +177,19 @@ int  lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_pro
 /* launch on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's current stream, so that
    collectives issued by the caller are stream-ordered with the half-step kernels.           */
 int  lcf_ensemble_set_stream(lcf_ensemble *e, void *stream);
+
+/* Fused multi-GPU exchange of a shared ensemble: every rank holds a full replica of the walker
+   positions; once the peers' replicas are attached, the accept epilogue of the half-step kernel stores accepted
+   walkers straight into them over NVLink and the ranks order their half-steps through device-side flags -- no NCCL
+   call, no host round trip, lcf_ensemble_run() runs whole chains in lock-step.  Same node only (cudaIpc).
+   export: three 64-byte cudaIpc handles (coords, log_prob, flags) to send to the other ranks;
+   attach_ipc: the handles of ALL ranks, [world][3][64] bytes (entry `rank` is ignored);
+   attach_ptrs: the same with raw device pointers valid in this process (arrays of length world).          */
+int  lcf_ensemble_ipc_export(lcf_ensemble *e, unsigned char *handles /* [3][64] */);
+int  lcf_ensemble_peers_attach_ipc(lcf_ensemble *e, const unsigned char *handles /* [world][3][64] */);
+int  lcf_ensemble_peers_attach_ptrs(lcf_ensemble *e, void *const *d_coords, void *const *d_log_prob, void *const *d_flags);
+int  lcf_ensemble_peers_detach(lcf_ensemble *e);
+int  lcf_ensemble_exchange_view(lcf_ensemble *e, void **d_flags, int *npeers);
 int  lcf_ensemble_sync(lcf_ensemble *e);
 /* device time (ms) spent in the last lcf_ensemble_run* call, measured with CUDA events on the
    handle's stream; kernel launches issued by that call.                                    */

@@ -49,6 +49,11 @@ SYMBOLS = [
     ('lcf_set_device', C.c_int, [C.c_int]),
     ('lcf_set_tuning', C.c_int, [C.c_int, C.c_int]),
     ('lcf_set_tuning_ex', C.c_int, [C.c_int, C.c_int, C.c_int]),
+    ('lcf_ensemble_ipc_export', C.c_int, [_vp, C.c_char_p]),
+    ('lcf_ensemble_peers_attach_ipc', C.c_int, [_vp, C.c_char_p]),
+    ('lcf_ensemble_peers_attach_ptrs', C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ('lcf_ensemble_peers_detach', C.c_int, [_vp]),
+    ('lcf_ensemble_exchange_view', C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int)]),
     ('lcf_problem_create', C.c_int, [C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     ('lcf_problem_destroy', None, [_vp]),
     ('lcf_model_eval', C.c_int, [_vp, C.c_int64, _pd, _pd]),

@@ -119,7 +119,17 @@ struct lcf_ensemble {
     bool has_state = false;
     double last_ms = 0.;
     long long last_launches = 0;
+    // fused multi-GPU exchange (lcf_ensemble_peers_*)
+    unsigned int *d_flags = nullptr;            // [kMaxPeers + 1] published half-step counters + [kMaxPeers + 1] done counter
+    int npeers = 0;
+    double *peer_coords[kMaxPeers] = {nullptr}, *peer_logp[kMaxPeers] = {nullptr};
+    unsigned int *peer_flags[kMaxPeers] = {nullptr};
+    int peer_rank[kMaxPeers] = {0};
+    std::vector<void *> ipc_opened;             // mappings to close
+    unsigned int epoch = 0;                     // fused half-steps launched so far (identical on every rank)
     ~lcf_ensemble() {
+        for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
+        cudaFree(d_flags);
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -682,14 +692,16 @@ int lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int ran
     if ((ce = cudaMalloc(&e->d_coords, sizeof(double) * e->W * e->D)) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_logp, sizeof(double) * e->W)) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_acc, sizeof(unsigned long long) * e->W)) != cudaSuccess ||
-        (ce = cudaMalloc(&e->d_nan, sizeof(int))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_nan, 2 * sizeof(int))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_flags, 2 * (kMaxPeers + 1) * sizeof(unsigned int))) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess) {
         delete e;
         return fail(LCF_ERR_CUDA, "ensemble allocation failed: %s", cudaGetErrorString(ce));
     }
     cudaMemset(e->d_acc, 0, sizeof(unsigned long long) * e->W);
-    cudaMemset(e->d_nan, 0, sizeof(int));
+    cudaMemset(e->d_nan, 0, 2 * sizeof(int));
+    cudaMemset(e->d_flags, 0, 2 * (kMaxPeers + 1) * sizeof(unsigned int));
     *out = e;
     return 0;
 }
@@ -699,13 +711,12 @@ void lcf_ensemble_destroy(lcf_ensemble *e) { delete e; }
 static inline long long phys_row(const lcf_ensemble *e, long long j) { return (j & 1) ? e->n0 + (j >> 1) : (j >> 1); }
 
 static int check_nan(lcf_ensemble *e) {
-    int h = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h, e->d_nan, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    int h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, e->d_nan, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    if (h) {
-        cudaMemsetAsync(e->d_nan, 0, sizeof(int), e->stream);
-        return fail(LCF_ERR_NAN, "Probability function returned NaN");
-    }
+    if (h[0] || h[1]) cudaMemsetAsync(e->d_nan, 0, 2 * sizeof(int), e->stream);
+    if (h[1]) return fail(LCF_ERR_CUDA, "multi-GPU exchange timed out waiting for a peer's half-step");
+    if (h[0]) return fail(LCF_ERR_NAN, "Probability function returned NaN");
     return 0;
 }
 
@@ -808,6 +819,85 @@ static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
         mv.chain_step = e->d_chain + e->nstored * e->W * e->D;
         mv.lnp_step = e->d_lnp + e->nstored * e->W;
     }
+    if (e->npeers) {                                   // fused exchange: one epoch per half-step launch
+        mv.npeers = e->npeers;
+        mv.myrank = e->rank;
+        for (int p = 0; p < e->npeers; ++p) {
+            mv.peer_coords[p] = e->peer_coords[p];
+            mv.peer_logp[p] = e->peer_logp[p];
+            mv.peer_flags[p] = e->peer_flags[p];
+            mv.peer_rank[p] = e->peer_rank[p];
+        }
+        mv.flags = e->d_flags;
+        mv.done_count = e->d_flags + (kMaxPeers + 1);
+        mv.epoch = e->epoch++;
+        mv.xstatus = e->d_nan + 1;
+    }
+}
+
+// ---- fused multi-GPU exchange: peer replicas mapped into this process (cudaIpc) or passed as raw pointers ----------
+int lcf_ensemble_ipc_export(lcf_ensemble *e, unsigned char *out /* [3][64] */) {
+    if (!e || !out) return fail(LCF_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, e->d_coords)); memcpy(out, &h, 64);
+    CUDA_TRY(cudaIpcGetMemHandle(&h, e->d_logp));   memcpy(out + 64, &h, 64);
+    CUDA_TRY(cudaIpcGetMemHandle(&h, e->d_flags));  memcpy(out + 128, &h, 64);
+    return 0;
+}
+
+int lcf_ensemble_peers_attach_ptrs(lcf_ensemble *e, void *const *coords, void *const *log_prob, void *const *flags) {
+    if (!e || !coords || !log_prob || !flags) return fail(LCF_ERR_ARG, "null argument");
+    if (e->world < 2) return fail(LCF_ERR_ARG, "ensemble was created with world = 1");
+    if (e->world - 1 > kMaxPeers) return fail(LCF_ERR_ARG, "at most %d GPUs share one ensemble", kMaxPeers + 1);
+    int n = 0;
+    for (int r = 0; r < e->world; ++r) {
+        if (r == e->rank) continue;
+        if (!coords[r] || !log_prob[r] || !flags[r]) return fail(LCF_ERR_ARG, "null peer pointer for rank %d", r);
+        e->peer_coords[n] = reinterpret_cast<double *>(coords[r]);
+        e->peer_logp[n] = reinterpret_cast<double *>(log_prob[r]);
+        e->peer_flags[n] = reinterpret_cast<unsigned int *>(flags[r]);
+        e->peer_rank[n] = r;
+        ++n;
+    }
+    e->npeers = n;
+    return 0;
+}
+
+int lcf_ensemble_peers_attach_ipc(lcf_ensemble *e, const unsigned char *handles /* [world][3][64] */) {
+    if (!e || !handles) return fail(LCF_ERR_ARG, "null argument");
+    if (e->world < 2 || e->world - 1 > kMaxPeers) return fail(LCF_ERR_ARG, "bad world size for a shared ensemble");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    void *c[kMaxPeers + 1] = {nullptr}, *l[kMaxPeers + 1] = {nullptr}, *f[kMaxPeers + 1] = {nullptr};
+    for (int r = 0; r < e->world; ++r) {
+        if (r == e->rank) continue;
+        void **dst[3] = {&c[r], &l[r], &f[r]};
+        for (int k = 0; k < 3; ++k) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + ((size_t)r * 3 + k) * 64, 64);
+            CUDA_TRY(cudaIpcOpenMemHandle(dst[k], h, cudaIpcMemLazyEnablePeerAccess));
+            e->ipc_opened.push_back(*dst[k]);
+        }
+    }
+    return lcf_ensemble_peers_attach_ptrs(e, c, l, f);
+}
+
+int lcf_ensemble_peers_detach(lcf_ensemble *e) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->npeers = 0;
+    for (void *m : e->ipc_opened) cudaIpcCloseMemHandle(m);
+    e->ipc_opened.clear();
+    return 0;
+}
+
+int lcf_ensemble_exchange_view(lcf_ensemble *e, void **d_flags, int *npeers) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (d_flags) *d_flags = e->d_flags;
+    if (npeers) *npeers = e->npeers;
+    return 0;
 }
 
 int lcf_ensemble_reserve(lcf_ensemble *e, int64_t nsteps) {

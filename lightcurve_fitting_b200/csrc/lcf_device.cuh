@@ -29,6 +29,7 @@ __device__ unsigned long long g_phase_clk[8];
 #endif
 
 constexpr int kMaxDim = 12;
+constexpr int kMaxPeers = 7;   // one 8-GPU NVSwitch box
 constexpr int kNumWC = 10; // per-walker model constants held in registers (wc7 = sigma^2 when use_sigma)
 
 enum Mode : int { MODE_MOVE = 0, MODE_LOGPOST = 1, MODE_LOGLIKE = 2, MODE_MODEL = 3 };
@@ -88,6 +89,18 @@ struct MoveDev {
     // evaluation modes
     const double *qin;               // [Ns][D]  (nmodel columns in MODE_MODEL)
     double *out;                     // [Ns] or [Ns][npoints]
+    // fused multi-GPU exchange (npeers = 0: single GPU, or the host exchanges with NCCL): every rank holds a full replica;
+    // the accept epilogue stores accepted walkers into the peers' replicas over NVLink (peer memory mapped with cudaIpc),
+    // the last CTA publishes "half-step done" into the peers' flag arrays, the next launch waits on its own flags.
+    int npeers, myrank;
+    double *peer_coords[kMaxPeers];
+    double *peer_logp[kMaxPeers];
+    unsigned int *peer_flags[kMaxPeers];   // flag array of peer p (we write slot `myrank`)
+    int peer_rank[kMaxPeers];
+    unsigned int *flags;                   // ours: flags[r] = half-steps rank r has completed and published
+    unsigned int *done_count;              // CTAs of this launch that have finished
+    unsigned int epoch;                    // half-steps completed before this launch
+    int *xstatus;                          // set to 1 when the wait below times out (a peer died)
     // chain write-back for this iteration (NULL = not stored), logical walker order
     double *chain_step;              // [W][D]
     double *lnp_step;                // [W]
@@ -640,6 +653,44 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
 }
 
 // ---------------------------------------------------------------------------------------
+// system-scope flag helpers for the fused multi-GPU exchange
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until every peer has published `epoch` completed half-steps (bounded: ~4 s, then flag the error and go on)
+__device__ __forceinline__ void peers_wait(const MoveDev &Mv) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int p = 0; p < Mv.npeers; ++p) {
+            while ((int)(ld_acquire_sys(Mv.flags + Mv.peer_rank[p]) - Mv.epoch) < 0) {
+                if (clock64() - t0 > 8000000000LL) { atomicExch(Mv.xstatus, 1); break; }
+                __nanosleep(100);
+            }
+        }
+    }
+    __syncthreads();
+}
+// all stores of this CTA are out: count it; the last CTA of the launch tells the peers
+__device__ __forceinline__ void peers_publish(const MoveDev &Mv) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(Mv.done_count, 1u);
+        if (prev == gridDim.x - 1) {
+            *Mv.done_count = 0u;
+            __threadfence_system();
+            for (int p = 0; p < Mv.npeers; ++p) st_release_sys(Mv.peer_flags[p] + Mv.myrank, Mv.epoch + 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // thread-block cluster helpers (a plain launch is a 1-CTA cluster: rank 0 of 1)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -922,6 +973,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                     for (int d = 0; d < D; ++d) crd[d] = s_q[tid * D + d];
                     Mv.logp[row] = nlp;
                     if (Mv.accepted) Mv.accepted[j] += 1ull;
+                    for (int p = 0; p < Mv.npeers; ++p) {            // the same update in every peer's replica (NVLink stores)
+                        double *pc = Mv.peer_coords[p] + row * D;
+                        for (int d = 0; d < D; ++d) pc[d] = s_q[tid * D + d];
+                        Mv.peer_logp[p][row] = nlp;
+                    }
                 }
                 if (Mv.chain_step) {
                     for (int d = 0; d < D; ++d) Mv.chain_step[j * D + d] = acc ? s_q[tid * D + d] : crd[d];
@@ -950,11 +1006,13 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
     const long long nclusters = cluster_count_x();
+    if (Mv.npeers) peers_wait(Mv);
     bool first = true;
     for (long long g = cluster_id_x(); g < ngroups; g += nclusters) {
         group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize);
         first = false;
     }
+    if (Mv.npeers) peers_publish(Mv);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1005,6 +1063,7 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
     Mv.wpb_log2 = B.wpb_log2;
     Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
+    Mv.npeers = 0;
     Mv.seed = B.seed ^ ((unsigned long long)(prob + 1) * 0x9E3779B97F4A7C15ull);
     Mv.qin = nullptr; Mv.out = nullptr;
     bool first = true;

@@ -6,10 +6,17 @@ Two modes:
   data-path collective.
 * **one ensemble split across GPUs**: every rank keeps a full replica of the walker positions, stored
   colour-major ``[even walkers | odd walkers]``.  In half-step ``h`` a rank proposes / evaluates / accepts only
-  its contiguous slice of colour ``h`` (fused kernel), then the updated slices are exchanged with ONE in-place
-  all-gather of that colour block, stream-ordered behind the kernel (the library launches on torch's current
-  stream).  Colour ``1-h`` is never written during the half-step, so no other synchronisation is needed.
+  its contiguous slice of colour ``h`` (fused kernel).  Colour ``1-h`` is never written during the half-step.
   The device RNG is keyed by the *global* walker index: chains are independent of the number of GPUs.
+  Two ways to publish the updated slice:
+
+  - ``exchange='p2p'`` (default on CUDA): the peers' replicas are mapped into every process once (cudaIpc handles
+    exchanged through torch.distributed) and the kernel's accept epilogue stores each accepted walker straight into
+    them over NVLink; the last CTA of a launch publishes a half-step counter into the peers' flag arrays and the
+    next launch spins on its own flags.  Compute and exchange are ONE kernel, whole chains run from one C call with
+    no NCCL collective and no host round trip per half-step.
+  - ``exchange='nccl'``: ONE in-place ``all_gather_into_tensor`` of the colour block per half-step, stream-ordered
+    behind the kernel (the baseline; also what the gloo CPU tests exercise).
 
 torch is plumbing here (process group, streams, a zero-copy view of the library's device buffers).
 """
@@ -65,7 +72,7 @@ class _DevArray:
 class ShardedEnsemble:
     """One ensemble of ``nwalkers`` walkers split across the ranks of a torch.distributed group."""
 
-    def __init__(self, problem, nwalkers, seed, rank, world, group=None):
+    def __init__(self, problem, nwalkers, seed, rank, world, group=None, exchange='p2p'):
         import torch
         from .sampler import EnsembleSampler
         self.torch = torch
@@ -86,9 +93,37 @@ class ShardedEnsemble:
         self.coords = torch.as_tensor(_DevArray(dc.value, (self.nwalkers, self.ndim)), device='cuda')
         self.logp = torch.as_tensor(_DevArray(dl.value, (self.nwalkers,)), device='cuda')
         self.own = [(ob[0], oc[0]), (ob[1], oc[1])]
+        self.fused = False
+        if world > 1 and exchange == 'p2p':
+            self._attach_peers()
+
+    def _attach_peers(self):
+        """Exchange cudaIpc handles of (coords, log_prob, flags) and map every peer's replica (same node)."""
+        import torch.distributed as dist
+        torch, L, h = self.torch, lib(), self.sampler.handle
+        buf = C.create_string_buffer(192)
+        check(L.lcf_ensemble_ipc_export(h, buf))
+        mine = torch.tensor(list(buf.raw), dtype=torch.uint8, device='cuda')
+        allh = torch.empty(self.world * 192, dtype=torch.uint8, device='cuda')
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        check(L.lcf_ensemble_peers_attach_ipc(h, bytes(allh.cpu().numpy().tobytes())))
+        dist.barrier(group=self.group)
+        self.fused = True
+
+    def _quiesce(self):
+        """Every rank's kernels (which store into the other replicas) have finished."""
+        if self.world > 1:
+            import torch.distributed as dist
+            self.torch.cuda.current_stream().synchronize()
+            check(lib().lcf_ensemble_sync(self.sampler.handle))
+            dist.barrier(group=self.group)
 
     def set_state(self, coords):
+        if self.fused:
+            self._quiesce()
         self.sampler._set_initial(coords, True)
+        if self.fused:
+            self._quiesce()
 
     def reserve(self, nsteps):
         check(lib().lcf_ensemble_reserve(self.sampler.handle, int(nsteps)))
@@ -98,6 +133,11 @@ class ShardedEnsemble:
         L, h = lib(), self.sampler.handle
         if store:
             self.reserve(nsteps)
+        if self.fused:                       # compute + exchange are one kernel: the whole run is one C call
+            check(L.lcf_ensemble_run(h, int(nsteps), 1 if store else 0))
+            if store:
+                self.sampler.iteration += int(nsteps)
+            return
         blocks = (self.coords[:self.n0], self.coords[self.n0:])
         for _ in range(int(nsteps)):
             for half in (0, 1):
@@ -110,7 +150,9 @@ class ShardedEnsemble:
 
     def finish(self):
         """Make log-probabilities consistent on every rank and surface NaN errors (emcee: ValueError)."""
-        if self.world > 1:
+        if self.fused:
+            self._quiesce()                  # log-probabilities travelled with the positions
+        elif self.world > 1:
             exchange_half(self.logp[:self.n0].unsqueeze(1), self.rank, self.world, self.group)
             exchange_half(self.logp[self.n0:].unsqueeze(1), self.rank, self.world, self.group)
         self.torch.cuda.current_stream().synchronize()

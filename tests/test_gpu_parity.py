@@ -527,3 +527,54 @@ def test_sharded_ensemble_emulated_two_ranks_matches_single():
         np.testing.assert_array_equal(ch, ref[:, first:first + count])
         np.testing.assert_array_equal(lp, single.get_log_prob()[:, first:first + count])
     check(lib().lcf_set_tuning(0, 0))
+
+
+def test_fused_peer_exchange_two_ranks_one_device_matches_single():
+    """The fused exchange (accept epilogue stores into the peer replica, device-side half-step flags) on two
+    rank-ensembles of one process: chains bit-identical to the single-ensemble run, replicas identical at the end."""
+    import ctypes as C
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_sc3(npoints=96)
+    prob = wl.device_problem('fp32')
+    nw, nsteps = 64, 8
+    check(lib().lcf_set_tuning_ex(8, 4, 1))
+    try:
+        p0 = wl.start(nw, np.random.default_rng(2))
+        single = EnsembleSampler(nw, wl.ndim, prob, seed=42)
+        single.run_mcmc(p0, nsteps, skip_initial_state_check=True)
+        ranks = [EnsembleSampler(nw, wl.ndim, prob, seed=42, rank=r, world=2) for r in range(2)]
+        coords, logps, flags = (C.c_void_p * 2)(), (C.c_void_p * 2)(), (C.c_void_p * 2)()
+        for r, s in enumerate(ranks):
+            s._set_initial(p0, True)
+            dc, dl, st, fl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            n0 = C.c_int64()
+            ob, oc = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+            check(lib().lcf_ensemble_device_view(s.handle, C.byref(dc), C.byref(dl), C.byref(st), C.byref(n0), ob, oc))
+            check(lib().lcf_ensemble_exchange_view(s.handle, C.byref(fl), None))
+            coords[r], logps[r], flags[r] = dc.value, dl.value, fl.value
+        for s in ranks:
+            check(lib().lcf_ensemble_peers_attach_ptrs(s.handle, coords, logps, flags))
+            check(lib().lcf_ensemble_reserve(s.handle, nsteps))
+        for _ in range(nsteps):                      # launches interleaved rank by rank; no host synchronisation at all
+            for half in (0, 1):
+                for s in ranks:
+                    check(lib().lcf_ensemble_half_step(s.handle, half, 1))
+            for s in ranks:
+                check(lib().lcf_ensemble_end_step(s.handle, 1))
+        for s in ranks:
+            check(lib().lcf_ensemble_sync(s.handle))
+        ref, ref_lp = single.get_chain(), single.get_log_prob()
+        states = []
+        for r, s in enumerate(ranks):
+            own = np.zeros(nw, bool)
+            own[r * (nw // 2):(r + 1) * (nw // 2)] = True          # walkers 2b..2b+2c of this rank's colour slices
+            ch, lp = s.get_chain(), s.get_log_prob()
+            np.testing.assert_array_equal(ch[:, own], ref[:, own])
+            np.testing.assert_array_equal(lp[:, own], ref_lp[:, own])
+            states.append(s._state())
+        np.testing.assert_array_equal(states[0].coords, states[1].coords)       # both replicas complete and identical
+        np.testing.assert_array_equal(states[0].log_prob, states[1].log_prob)
+        np.testing.assert_array_equal(states[0].coords, ref[-1])
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
