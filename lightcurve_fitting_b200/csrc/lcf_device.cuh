@@ -362,14 +362,17 @@ __device__ __forceinline__ R planck_sum_safe(const typename Vec4<R>::type *__res
 // => 1 MUFU.EX2 per Planck sample and nothing else on the XU pipe.  Measured in isolation (tools/microbench/loops.cu,
 // B200, 32 warps/SM): 14.6 samples/clk/SM against 12.2 for the MUFU.RCP version and 15.7 for a bare EX2 stream.
 // Callers guarantee that every exponent is >= 1/16 (no cancellation in 2^x - 1) and either that the four exponents
-// sum to <= 124 (the product of four denominators stays a normal float) or they ask for the CLAMP variant.
-// CLAMP: exponents are capped at 31 (h nu / k T = 21.5), so four denominators multiply to < 2^124 whatever the
-// temperature; a capped sample contributes w / (2^31 - 1) < 5e-10 w instead of something smaller still.
-constexpr float kXClamp = 31.f;
-template <bool CLAMP>
-__device__ __forceinline__ float2 ex2m1_pair(float2 x) {                 // (2^x.x - 1, 2^x.y - 1)
-    if (CLAMP) { x.x = fminf(x.x, kXClamp); x.y = fminf(x.y, kXClamp); }
-    return __fadd2_rn(make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y)), make_float2(-1.f, -1.f));
+// sum to <= 124 (the product of four denominators stays a normal float) or they ask for the WIEN variant.
+// Two variants of every loop.  Plain: d = 2^x - 1, valid while the four exponents of a quad sum to <= 124 (their product
+// stays a normal float).  WIEN (cold blackbody / blue filter, any exponent): the same quad on m = 1 - 2^-x, which lives in
+// (0.04, 1], and  w/(2^x - 1) = w e/(1 - e)  with e = 2^-x: no overflow at all and the exact Wien limit w 2^-x when e
+// underflows, for one more multiplication per sample.
+template <bool WIEN>
+__device__ __forceinline__ void ex2_terms(float2 a, float2 i2, float2 &d, float2 &e) {
+    // plain: d = 2^(a i) - 1 (e unused);  WIEN (i2 holds -i): e = 2^(-a i), d = 1 - e
+    const float2 x = __fmul2_rn(a, i2);
+    e = make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y));
+    d = WIEN ? __fadd2_rn(make_float2(-e.x, -e.y), make_float2(1.f, 1.f)) : __fadd2_rn(e, make_float2(-1.f, -1.f));
 }
 __device__ __forceinline__ float rcp_newton(float x) {                   // x positive and normal
     float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
@@ -390,11 +393,12 @@ __device__ __forceinline__ float2 rcp_newton2(float2 x) {
 // (a) two blackbodies (points A, B of one walker) x the two samples of a pair record; two records per iteration.
 //     Pointer-bumped with compile-time strides so that the loop bookkeeping is 2 adds + compare + branch (integer
 //     multiply-adds would land on the FMA pipe, which is the second-busiest one here).
-template <bool TAB, bool CLAMP>
+template <bool TAB, bool WIEN>
 __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
                                                 const float2 *__restrict__ tab, float &SA, float &SB) {
     constexpr int ts = kTabStride;
-    const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB);
+    const float sA = WIEN ? -iA : iA, sB = WIEN ? -iB : iB;
+    const float2 iA2 = make_float2(sA, sA), iB2 = make_float2(sB, sB);
     float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
     const float4 *pb = b4, *const pe = b4 + (K2 & ~1);
     for (; pb < pe; pb += 2) {
@@ -410,27 +414,29 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
             a0 = make_float2(s0.x, s0.y); w0 = make_float2(s0.z, s0.w);
             a1 = make_float2(s1.x, s1.y); w1 = make_float2(s1.z, s1.w);
         }
-        const float2 dA0 = ex2m1_pair<CLAMP>(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair<CLAMP>(__fmul2_rn(a0, iB2));   // (dA(k0), dA(k1))
-        const float2 dA1 = ex2m1_pair<CLAMP>(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair<CLAMP>(__fmul2_rn(a1, iB2));
+        float2 dA0, dB0, dA1, dB1, eA0, eB0, eA1, eB1;            // d: denominators of (sample k0, sample k1); e: WIEN only
+        ex2_terms<WIEN>(a0, iA2, dA0, eA0); ex2_terms<WIEN>(a0, iB2, dB0, eB0);
+        ex2_terms<WIEN>(a1, iA2, dA1, eA1); ex2_terms<WIEN>(a1, iB2, dB1, eB1);
         const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);                          // per sample: dA dB
         const float2 r = rcp_newton2(make_float2(p0.x * p0.y, p1.x * p1.y));                         // one per record
         const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));  // w/(dA dB)
         const float2 t1 = __fmul2_rn(w1, __fmul2_rn(make_float2(r.y, r.y), make_float2(p1.y, p1.x)));
-        accA = __ffma2_rn(t0, dB0, accA);                                                            // += w/dA
-        accB = __ffma2_rn(t0, dA0, accB);                                                            // += w/dB
-        accA = __ffma2_rn(t1, dB1, accA);
-        accB = __ffma2_rn(t1, dA1, accB);
+        accA = __ffma2_rn(WIEN ? __fmul2_rn(t0, eA0) : t0, dB0, accA);                               // += w [eA]/dA
+        accB = __ffma2_rn(WIEN ? __fmul2_rn(t0, eB0) : t0, dA0, accB);                               // += w [eB]/dB
+        accA = __ffma2_rn(WIEN ? __fmul2_rn(t1, eA1) : t1, dB1, accA);
+        accB = __ffma2_rn(WIEN ? __fmul2_rn(t1, eB1) : t1, dA1, accB);
     }
     if (K2 & 1) {
         float2 a, w;
         if (TAB) { a = *reinterpret_cast<const float2 *>(pb); w = tab[0]; }
         else { const float4 s = pb[0]; a = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
-        const float2 dA = ex2m1_pair<CLAMP>(__fmul2_rn(a, iA2)), dB = ex2m1_pair<CLAMP>(__fmul2_rn(a, iB2));
+        float2 dA, dB, eA, eB;
+        ex2_terms<WIEN>(a, iA2, dA, eA); ex2_terms<WIEN>(a, iB2, dB, eB);
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_newton(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
-        accA = __ffma2_rn(t, dB, accA);
-        accB = __ffma2_rn(t, dA, accB);
+        accA = __ffma2_rn(WIEN ? __fmul2_rn(t, eA) : t, dB, accA);
+        accB = __ffma2_rn(WIEN ? __fmul2_rn(t, eB) : t, dA, accB);
     }
     SA = accA.x + accA.y;
     SB = accB.x + accB.y;
@@ -438,23 +444,26 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
 
 // (b) ShockCooling4: two points x (T, 0.74 T) (models.py:629-630); each quad = (A, A*, B, B*) at ONE sample, the two
 //     samples of the pair record are processed side by side in the packed lanes (two reciprocals per record).
-template <bool CLAMP>
+template <bool WIEN>
 __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float &SA,
                                                     float &SAs, float &SB, float &SBs) {
-    const float c = (float)(1. / 0.74);
-    const float2 iA2 = make_float2(iA, iA), iB2 = make_float2(iB, iB), iAs2 = make_float2(iA * c, iA * c), iBs2 = make_float2(iB * c, iB * c);
+    const float c = (float)(1. / 0.74), sA = WIEN ? -iA : iA, sB = WIEN ? -iB : iB;
+    const float2 iA2 = make_float2(sA, sA), iB2 = make_float2(sB, sB), iAs2 = make_float2(sA * c, sA * c), iBs2 = make_float2(sB * c, sB * c);
     float2 a = make_float2(0.f, 0.f), as = a, bb = a, bs = a;
 #pragma unroll 2
     for (const float4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
         const float4 s = *pb;
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair<CLAMP>(__fmul2_rn(x, iA2)), dAs = ex2m1_pair<CLAMP>(__fmul2_rn(x, iAs2));
-        const float2 dB = ex2m1_pair<CLAMP>(__fmul2_rn(x, iB2)), dBs = ex2m1_pair<CLAMP>(__fmul2_rn(x, iBs2));
+        float2 dA, dAs, dB, dBs, eA, eAs, eB, eBs;
+        ex2_terms<WIEN>(x, iA2, dA, eA); ex2_terms<WIEN>(x, iAs2, dAs, eAs);
+        ex2_terms<WIEN>(x, iB2, dB, eB); ex2_terms<WIEN>(x, iBs2, dBs, eBs);
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
         const float2 r = rcp_newton2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
-        a = __ffma2_rn(tA, dAs, a);   as = __ffma2_rn(tA, dA, as);
-        bb = __ffma2_rn(tB, dBs, bb); bs = __ffma2_rn(tB, dB, bs);
+        a = __ffma2_rn(WIEN ? __fmul2_rn(tA, eA) : tA, dAs, a);
+        as = __ffma2_rn(WIEN ? __fmul2_rn(tA, eAs) : tA, dA, as);
+        bb = __ffma2_rn(WIEN ? __fmul2_rn(tB, eB) : tB, dBs, bb);
+        bs = __ffma2_rn(WIEN ? __fmul2_rn(tB, eBs) : tB, dB, bs);
     }
     SA = a.x + a.y; SAs = as.x + as.y; SB = bb.x + bb.y; SBs = bs.x + bs.y;
 }
@@ -658,7 +667,7 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
         const float imin = fminf(i0, i1);
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         if (rng.x * imin >= 0.0625f) {                      // no cancellation in 2^x - 1 anywhere in the filter
-            const bool clamp = xsum > 124.f;                 // the product of four denominators could overflow: cap the exponents
+            const bool clamp = xsum > 124.f;                 // the product of four denominators could overflow: Wien form
 #ifdef LCF_X_TIMING
             atomicAdd(&g_phase_clk[clamp ? 7 : 6], 1ull);        // lane-tiles on the plain / clamped fast path
 #endif

@@ -578,3 +578,69 @@ def test_fused_peer_exchange_two_ranks_one_device_matches_single():
         np.testing.assert_array_equal(states[0].coords, ref[-1])
     finally:
         check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
+def _ragged_workload(filter_names, counts, model='ShockCooling4', seed=5, t_span=(0.4, 14.)):
+    """A light curve with a prescribed (ragged) number of points per filter, truth from the oracle."""
+    from lightcurve_fitting_b200.synthetic import Workload
+    rng = np.random.default_rng(seed)
+    fn = [f for f, c in zip(filter_names, counts) for _ in range(c)]
+    t0 = 57468.6
+    t = t0 + rng.uniform(*t_span, len(fn))
+    order = rng.permutation(len(fn))                    # callers do not have to group by filter: the host layer does
+    fn, t = [fn[i] for i in order], t[order]
+    p_true = np.array([1.2, 0.8, 2., 4., t0])
+    ytrue = W.oracle_truth(model, t, fn, p_true, 0.002)
+    dy = 0.05 * np.abs(ytrue) + 1e-3 * np.abs(ytrue).max()
+    y = ytrue + dy * rng.normal(size=len(fn))
+    pri = [('uniform', 0., 10.), ('uniform', 0., 10.), ('uniform', 0., 100.), ('uniform', 0., 100.), ('uniform', t0 - 0.6, t0 + 0.4)]
+    return Workload('ragged', model, t, fn, y, dy, pri, [0.5, 0.1, 0.1, 1., t0 - 0.1], [2., 2., 10., 10., t0 + 0.1], z=0.002,
+                    truth=p_true)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_ragged_light_curves(precision):
+    """One point in a filter, a single-point light curve, filters with odd / minimal / maximal sample counts
+    (unfiltered '0': 4 samples ... F2550W: 1482), per-filter counts that never fill a tile."""
+    cases = [(['U', 'B', 'V', 'g', 'r', 'i', 'R', 'I', '0'], [1, 2, 3, 5, 7, 1, 33, 65, 4]),
+             (['g'], [1]),
+             (['F2550W', 'NUV', 'B', '0'], [3, 2, 9, 1]),
+             (['r', 'i'], [64, 63])]
+    for names, counts in cases:
+        wl = _ragged_workload(names, counts)
+        _check_logpost(wl, precision, n=19, seed=4)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_cold_and_hot_blackbodies_take_every_path(precision):
+    """Blackbody SED through UV-to-mid-IR filters from 300 K to 3e6 K: the plain fast path, the clamped fast path (the
+    product of four denominators would overflow), the careful path (Rayleigh-Jeans, 2^x - 1 cancels) and the limit in
+    which the flux underflows all agree with the oracle."""
+    from lightcurve_fitting_b200 import models as M
+    from oracle import reference_port as rp
+    names = ['NUV', 'U', 'B', 'V', 'R', 'I', 'F444W', 'F2550W']
+    T = np.array([0.3, 0.8, 1.5, 2.5, 4., 8., 20., 80., 400., 3000.])          # kK
+    R = np.full_like(T, 5.)
+    from lightcurve_fitting_b200.filters import filtdict
+    f_dev = [filtdict[n] for n in names]
+    f_ora = W.oracle_filters(names)
+    got = M._sed_eval(f_dev, T, R, 0.01, np.inf, 0., precision=precision)                    # [len(T), nfilters]
+    want = np.array([rp.blackbody_to_filters(f_ora, np.full(len(names), t), np.full(len(names), r), z=0.01) for t, r in zip(T, R)])
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    # relative to the brightest band of each SED: an underflowing / capped Wien tail is allowed to differ by < 1e-9 of it
+    np.testing.assert_allclose(got / scale, want / scale, rtol=RTOL[precision], atol=2e-9)
+
+
+def test_odd_walker_counts_and_partial_groups():
+    """Walker counts that are odd and not multiples of the walkers-per-CTA group: stretch move runs, chain complete,
+    and a replay with injected draws matches the oracle's emcee-order chain."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.example_sc4(npoints=30)
+    prob = wl.device_problem('fp64')
+    for nw in (2 * wl.ndim, 2 * wl.ndim + 1, 37, 67):
+        s = EnsembleSampler(nw, wl.ndim, prob, seed=3)
+        s.run_mcmc(wl.start(nw, np.random.default_rng(nw)), 7)
+        ch, lp = s.get_chain(), s.get_log_prob()
+        assert ch.shape == (7, nw, wl.ndim) and np.isfinite(lp).all()
+        want = prob.log_posterior(ch[-1])
+        np.testing.assert_allclose(lp[-1], want, rtol=1e-12)             # stored log-prob belongs to the stored position

@@ -12,6 +12,7 @@ using namespace lcf;
 #define K2 24
 #define REP 400
 
+__device__ __forceinline__ float2 ex2m1_pair_(float2 x) { return __fadd2_rn(make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y)), make_float2(-1.f, -1.f)); }
 __device__ __forceinline__ float ex2f_(float x) { return Mth<float>::ex2(x); }
 __device__ __forceinline__ float rcpf_(float x) { return Mth<float>::rcp(x); }
 
@@ -44,8 +45,8 @@ __device__ __forceinline__ void quad_nr(const float4 *__restrict__ b4, int k2, f
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair_(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair_(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = NR == 1 ? rcp_nr(p.x * p.y) : rcp_nr2(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -64,8 +65,8 @@ __device__ __forceinline__ void quad_nr_u4(const float4 *__restrict__ b4, int k2
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair_(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair_(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_nr(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -83,8 +84,8 @@ __device__ __forceinline__ void quad_u4(const float4 *__restrict__ b4, int k2, f
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 a = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2));
-        const float2 dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair_(__fmul2_rn(a, iA2));
+        const float2 dB = ex2m1_pair_(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcpf_(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -119,8 +120,8 @@ __device__ __forceinline__ void quad_nr_x2(const float4 *__restrict__ b4, int k2
             const float4 s0 = b4[k], s1 = b4[k + 1];
             a0 = make_float2(s0.x, s0.y); w0 = make_float2(s0.z, s0.w); a1 = make_float2(s1.x, s1.y); w1 = make_float2(s1.z, s1.w);
         }
-        const float2 dA0 = ex2m1_pair<false>(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair<false>(__fmul2_rn(a0, iB2));
-        const float2 dA1 = ex2m1_pair<false>(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair<false>(__fmul2_rn(a1, iB2));
+        const float2 dA0 = ex2m1_pair_(__fmul2_rn(a0, iA2)), dB0 = ex2m1_pair_(__fmul2_rn(a0, iB2));
+        const float2 dA1 = ex2m1_pair_(__fmul2_rn(a1, iA2)), dB1 = ex2m1_pair_(__fmul2_rn(a1, iB2));
         const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);
         const float2 r = rcp_nr_x2(make_float2(p0.x * p0.y, p1.x * p1.y));
         const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));
@@ -132,7 +133,7 @@ __device__ __forceinline__ void quad_nr_x2(const float4 *__restrict__ b4, int k2
         float2 a, w;
         if (TAB) { a = *reinterpret_cast<const float2 *>(b4 + k); w = tab[0]; }
         else { const float4 s = b4[k]; a = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
-        const float2 dA = ex2m1_pair<false>(__fmul2_rn(a, iA2)), dB = ex2m1_pair<false>(__fmul2_rn(a, iB2));
+        const float2 dA = ex2m1_pair_(__fmul2_rn(a, iA2)), dB = ex2m1_pair_(__fmul2_rn(a, iB2));
         const float2 p = __fmul2_rn(dA, dB);
         const float r = rcp_nr(p.x * p.y);
         const float2 t = __fmul2_rn(w, make_float2(r * p.y, r * p.x));
@@ -150,8 +151,8 @@ __device__ __forceinline__ void sc4_nr(const float4 *__restrict__ b4, int k2, fl
     for (int k = 0; k < k2; ++k) {
         const float4 s = b4[k];
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
-        const float2 dA = ex2m1_pair<false>(__fmul2_rn(x, iA2)), dAs = ex2m1_pair<false>(__fmul2_rn(x, iAs2));
-        const float2 dB = ex2m1_pair<false>(__fmul2_rn(x, iB2)), dBs = ex2m1_pair<false>(__fmul2_rn(x, iBs2));
+        const float2 dA = ex2m1_pair_(__fmul2_rn(x, iA2)), dAs = ex2m1_pair_(__fmul2_rn(x, iAs2));
+        const float2 dB = ex2m1_pair_(__fmul2_rn(x, iB2)), dBs = ex2m1_pair_(__fmul2_rn(x, iBs2));
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
         const float2 r = rcp_nr_x2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
@@ -283,7 +284,7 @@ int main() {
     const char *vn[14] = {"quad MUFU.RCP (shipped)", "quad MUFU.RCP + per-lane weight table", "quad Newton rcp (3 quadratic)", "quad Newton rcp (2 cubic)",
                          "oct e/(1-e) MUFU.RCP", "oct e/(1-e) Newton (3 quadratic)", "oct e/(1-e) Newton (2 cubic)", "SC4 quad (T, 0.74T) MUFU.RCP",
                          "quad Newton rcp, unroll 4", "quad MUFU.RCP, unroll 4",
-                         "quad packed Newton, 2 records/iter", "quad packed Newton, 2 records/iter + table", "SC4 quad packed Newton", "shipped + per-sample clamp"};
+                         "quad packed Newton, 2 records/iter", "quad packed Newton, 2 records/iter + table", "SC4 quad packed Newton", "shipped, Wien form w e/(1-e)"};
     auto report = [&](int i, float ms, int nb, int nt) {
         const double samples = (double)nb * nt * REP * K2 * 4 * ((i == 7 || i == 12) ? 2 : 1);
         printf("%-40s %4d thr x %4d CTAs %8.3f ms -> %6.2f Planck samples/clk/SM\n", vn[i], nt, nb, ms, samples / (ms * 1e-3) / clk / sms);
