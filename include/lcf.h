@@ -170,6 +170,11 @@ int  lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob /* [nstored][nw
    (either may be NULL).  A rank of a sharded ensemble owns the contiguous walkers [2*own_begin, 2*(own_begin+own_count)). */
 int  lcf_ensemble_get_chain_slice(lcf_ensemble *e, int64_t first, int64_t count, double *chain, double *log_prob);
 int  lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted /* [nwalkers] */);
+/* Convergence diagnostics computed on the device-resident chain, steps [discard, nstored) (no reference equivalent;
+   definitions: emcee.autocorr.integrated_time (c = 5 there) and the split Gelman-Rubin statistic).  tau/window/rhat are
+   [ndim] and may be NULL; max_lag <= 0 means all lags; window[d] = -1 when no automatic window exists in range.      */
+int  lcf_ensemble_diagnostics(lcf_ensemble *e, int64_t discard, double c, int64_t max_lag, double *tau, int64_t *window,
+                              double *rhat);
 /* device-side view for the multi-GPU exchange (torch.distributed wraps these raw pointers):
    coords are stored colour-major: rows [0, n0) even walkers, [n0, nwalkers) odd walkers.    */
 int  lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream,

@@ -6,6 +6,7 @@
 // implementation of the hot path in this library.
 #include "../../include/lcf.h"
 #include "lcf_device.cuh"
+#include "lcf_diag.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1059,6 +1060,84 @@ int lcf_ensemble_get_accepted(lcf_ensemble *e, int64_t *accepted) {
     CUDA_TRY(cudaMemcpy(accepted, e->d_acc, sizeof(unsigned long long) * e->W, cudaMemcpyDeviceToHost));
     return 0;
 }
+// ---- convergence diagnostics on the device-resident chain ----------------------------------
+// tau[d]: integrated autocorrelation time with emcee's definition (emcee.autocorr.integrated_time: normalised ACF of every
+// walker averaged over walkers, tau(M) = 2 sum_{k<=M} f(k) - 1, Sokal's automatic window = first M with M >= c tau(M)),
+// window[d]: that M (or -1 when no window exists inside max_lag: the estimate is then taken at the last lag); walkers that
+// never moved in the range (exactly constant series, for which emcee returns NaN) are left out of the average;
+// rhat[d]: split Gelman-Rubin statistic over the 2 W half-chains.  Steps [discard, nstored) are used.
+int lcf_ensemble_diagnostics(lcf_ensemble *e, int64_t discard, double c, int64_t max_lag, double *tau, int64_t *window,
+                             double *rhat) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (e->world != 1) return fail(LCF_ERR_ARG, "diagnostics need the whole chain on one GPU");
+    const long long n = e->nstored - discard, W = e->W;
+    const int D = e->D;
+    if (discard < 0 || n < 4) return fail(LCF_ERR_STATE, "need at least 4 stored steps after discard");
+    if (!(c > 0.)) return fail(LCF_ERR_ARG, "c must be positive");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    long long nlag = n;
+    if (max_lag > 0) nlag = std::min<long long>(n, max_lag + 1);
+    double *d_mom = nullptr, *d_f = nullptr;
+    CUDA_TRY(cudaMalloc(&d_mom, sizeof(double) * W * D * 6));
+    CUDA_TRY(cudaMalloc(&d_f, sizeof(double) * D * nlag));
+    const long long ns = W * D;
+    k_series_moments<<<(unsigned)((ns + 255) / 256), 256, 0, e->stream>>>(e->d_chain, discard, n, W, D, d_mom);
+    if (tau || window) {
+        dim3 grid((unsigned)((nlag + kLagBlock - 1) / kLagBlock), (unsigned)D);
+        k_mean_acf<<<grid, 256, 0, e->stream>>>(e->d_chain, discard, n, W, D, d_mom, nlag, d_f);
+    }
+    cudaError_t ce = cudaGetLastError();
+    std::vector<double> mom((size_t)ns * 6), f((size_t)D * nlag);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(mom.data(), d_mom, sizeof(double) * mom.size(), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && (tau || window))
+        ce = cudaMemcpyAsync(f.data(), d_f, sizeof(double) * f.size(), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_mom);
+    cudaFree(d_f);
+    if (ce != cudaSuccess) return fail(LCF_ERR_CUDA, "diagnostics failed: %s", cudaGetErrorString(ce));
+    if (tau || window) {
+        for (int d = 0; d < D; ++d) {
+            long long moving = 0;                                       // walkers that contributed (stuck ones are left out)
+            for (long long w = 0; w < W; ++w) moving += mom[(size_t)(w * D + d) * 6 + 1] > 0.;
+            const double renorm = moving ? (double)W / (double)moving : NAN;
+            double cum = 0., t_at = 0.;
+            long long win = -1;
+            for (long long k = 0; k < nlag; ++k) {
+                cum += f[(size_t)d * nlag + k] * renorm;
+                const double tk = 2. * cum - 1.;
+                t_at = tk;
+                if (!((double)k < c * tk)) { win = k; break; }        // emcee auto_window: first k with k >= c tau(k)
+            }
+            if (tau) tau[d] = t_at;
+            if (window) window[d] = win;
+        }
+    }
+    if (rhat) {
+        const long long h = n / 2;
+        for (int d = 0; d < D; ++d) {
+            // 2 W chains of h steps: B/h = variance of the chain means, Wv = mean within-chain variance
+            double mm = 0., wv = 0.;
+            for (long long w = 0; w < W; ++w) {
+                const double *o = &mom[(size_t)(w * D + d) * 6];
+                mm += o[2] + o[4];
+                wv += (o[3] + o[5]) / (double)(h - 1);
+            }
+            const double M = 2. * (double)W;
+            mm /= M;
+            wv /= M;
+            double b = 0.;
+            for (long long w = 0; w < W; ++w) {
+                const double *o = &mom[(size_t)(w * D + d) * 6];
+                b += (o[2] - mm) * (o[2] - mm) + (o[4] - mm) * (o[4] - mm);
+            }
+            b /= (M - 1.);                                             // variance of the means = B / h
+            const double var_plus = (double)(h - 1) / (double)h * wv + b;
+            rhat[d] = std::sqrt(var_plus / wv);
+        }
+    }
+    return 0;
+}
+
 int lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream, int64_t *n0, int64_t *own_begin,
                              int64_t *own_count) {
     if (!e) return fail(LCF_ERR_ARG, "null argument");

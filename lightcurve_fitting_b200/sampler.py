@@ -12,6 +12,14 @@ import numpy as np
 from ._capi import lib, check, dptr, iptr, f64, i32
 
 
+class AutocorrError(Exception):
+    """Raised when the chain is too short for a reliable autocorrelation time (emcee.autocorr.AutocorrError)."""
+
+    def __init__(self, tau, *args, **kwargs):
+        self.tau = tau
+        super().__init__(*args, **kwargs)
+
+
 class State:
     """Minimal ``emcee.State``: unpacks to ``(coords, log_prob, random_state)``."""
 
@@ -181,6 +189,31 @@ class EnsembleSampler:
     @property
     def flatlnprobability(self):
         return self.get_log_prob(flat=True)
+
+    def get_autocorr_time(self, discard=0, c=5, tol=50, quiet=False, max_lag=0, return_window=False):
+        """Integrated autocorrelation time per dimension, ``emcee.EnsembleSampler.get_autocorr_time`` semantics (Sokal's
+        automatic window with constant ``c``; ``AutocorrError`` unless the chain is longer than ``tol`` times the estimate
+        or ``quiet``), computed on the device-resident chain."""
+        tau = np.empty(self.ndim)
+        win = np.empty(self.ndim, np.int64)
+        check(lib().lcf_ensemble_diagnostics(self.handle, int(discard), float(c), int(max_lag), dptr(tau),
+                                             win.ctypes.data_as(C.POINTER(C.c_int64)), None))
+        n = lib().lcf_ensemble_nstored(self.handle) - int(discard)
+        if tol > 0 and np.any(tol * tau > n):
+            msg = ('The chain is shorter than {0} times the integrated autocorrelation time for {1} parameter(s). Use this '
+                   'estimate with caution and run a longer chain!\nN/{0} = {2:.0f};\ntau: {3}').format(
+                       tol, int(np.sum(tol * tau > n)), n / tol, tau)
+            if not quiet:
+                raise AutocorrError(tau, msg)
+            import warnings
+            warnings.warn(msg)
+        return (tau, win) if return_window else tau
+
+    def get_split_rhat(self, discard=0):
+        """Split Gelman-Rubin statistic per dimension over the 2 x nwalkers half-chains (device-side moments)."""
+        rhat = np.empty(self.ndim)
+        check(lib().lcf_ensemble_diagnostics(self.handle, int(discard), 5., 0, None, None, dptr(rhat)))
+        return rhat
 
     @property
     def acceptance_fraction(self):

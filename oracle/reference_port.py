@@ -619,3 +619,60 @@ def median_and_unc(x, perc_contained=68.):
     percentiles = np.percentile(x, q, axis=0)
     lower, upper = np.diff(percentiles, axis=0)
     return percentiles[1], lower, upper
+
+
+# ---------------------------------------------------------------------------------------------------
+# Convergence diagnostics.  Not called by the reference; definitions restated from memory of
+# emcee 3.1.x ``emcee/autocorr.py`` (function_1d, auto_window, integrated_time) -- parity unpinned -- and the usual
+# split Gelman-Rubin statistic.  Test infrastructure like the rest of this file.
+# ---------------------------------------------------------------------------------------------------
+def _next_pow_two(n):
+    i = 1
+    while i < n:
+        i = i << 1
+    return i
+
+
+def autocorr_function_1d(x):
+    """Normalised autocorrelation function of a 1-D series via zero-padded FFT (emcee.autocorr.function_1d)."""
+    x = np.atleast_1d(x)
+    n = _next_pow_two(len(x))
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[:len(x)].real
+    acf /= acf[0]
+    return acf
+
+
+def autocorr_auto_window(taus, c):
+    m = np.arange(len(taus)) < c * taus
+    if np.any(m):
+        return int(np.argmin(m))
+    return len(taus) - 1
+
+
+def integrated_time(x, c=5):
+    """Integrated autocorrelation time per dimension of a chain [n_t, n_w, n_d] (emcee.autocorr.integrated_time without
+    the tolerance check).  Returns (tau [n_d], window [n_d])."""
+    x = np.asarray(x, float)
+    n_t, n_w, n_d = x.shape
+    tau, win = np.empty(n_d), np.empty(n_d, int)
+    for d in range(n_d):
+        f = np.zeros(n_t)
+        for k in range(n_w):
+            f += autocorr_function_1d(x[:, k, d])
+        f /= n_w
+        taus = 2.0 * np.cumsum(f) - 1.0
+        win[d] = autocorr_auto_window(taus, c)
+        tau[d] = taus[win[d]]
+    return tau, win
+
+
+def split_rhat(x):
+    """Split Gelman-Rubin statistic per dimension: every walker's chain is cut into two halves of floor(n_t/2) steps."""
+    x = np.asarray(x, float)
+    h = x.shape[0] // 2
+    halves = np.concatenate([x[:h], x[h:2 * h]], axis=1)          # [h, 2 n_w, n_d]
+    means = halves.mean(axis=0)
+    wv = halves.var(axis=0, ddof=1).mean(axis=0)
+    b_over_h = means.var(axis=0, ddof=1)
+    return np.sqrt(((h - 1) / h * wv + b_over_h) / wv)

@@ -644,3 +644,27 @@ def test_odd_walker_counts_and_partial_groups():
         assert ch.shape == (7, nw, wl.ndim) and np.isfinite(lp).all()
         want = prob.log_posterior(ch[-1])
         np.testing.assert_allclose(lp[-1], want, rtol=1e-12)             # stored log-prob belongs to the stored position
+
+
+def test_device_convergence_diagnostics_match_oracle():
+    """Integrated autocorrelation time (emcee's definition), automatic window and split R-hat computed on the
+    device-resident chain equal the oracle's numpy versions on the same chain."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler, AutocorrError
+    from oracle import reference_port as rp
+    wl = W.example_sc4(npoints=24)
+    prob = wl.device_problem('fp32')
+    nw, nsteps = 24, 600
+    s = EnsembleSampler(nw, wl.ndim, prob, seed=11)
+    s.run_mcmc(wl.start(nw, np.random.default_rng(1)), nsteps)
+    for discard in (0, 101):
+        chain = s.get_chain()[discard:]
+        moving = (chain != chain[0]).any(axis=(0, 2))        # a stuck walker makes emcee's estimate NaN; the device leaves it out
+        tau_o, win_o = rp.integrated_time(chain[:, moving])
+        tau, win = s.get_autocorr_time(discard=discard, tol=0, return_window=True)
+        np.testing.assert_array_equal(win, win_o)
+        np.testing.assert_allclose(tau, tau_o, rtol=1e-8)
+        np.testing.assert_allclose(s.get_split_rhat(discard=discard), rp.split_rhat(chain), rtol=1e-9)
+    tau_l, win_l = s.get_autocorr_time(tol=0, max_lag=3, return_window=True)       # window cannot exist within 3 lags
+    assert (win_l == -1).all()
+    with pytest.raises(AutocorrError):
+        s.get_autocorr_time(tol=1e6)

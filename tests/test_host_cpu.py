@@ -267,3 +267,27 @@ def test_sharded_exchange_two_ranks_gloo():
         results[world] = dict(out)
     np.testing.assert_array_equal(results[2][0], results[2][1])
     np.testing.assert_array_equal(results[2][0], results[1][0])
+
+
+def test_oracle_autocorrelation_fft_equals_direct_lag_products():
+    """The oracle's FFT autocorrelation (emcee's definition) is the plain lag-product sum the device kernel evaluates;
+    an AR(1) chain with coefficient 0.9 has integrated time (1 + 0.9) / (1 - 0.9) = 19."""
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(0)
+    n_t, n_w = 4000, 24
+    x = np.zeros((n_t, n_w, 2))
+    e = rng.normal(size=(n_t, n_w, 2))
+    for t in range(1, n_t):
+        x[t] = np.array([0.9, 0.5]) * x[t - 1] + e[t]
+    s = x[:, 3, 0]
+    acf = rp.autocorr_function_1d(s)
+    m = s - s.mean()
+    direct = np.array([np.dot(m[:n_t - k], m[k:]) for k in range(50)]) / np.dot(m, m)
+    np.testing.assert_allclose(acf[:50], direct, rtol=1e-9, atol=1e-12)
+    tau, win = rp.integrated_time(x)
+    assert abs(tau[0] - 19.) < 3. and abs(tau[1] - 3.) < 0.5 and (win > 0).all()
+    rh = rp.split_rhat(x)
+    assert np.all(np.abs(rh - 1.) < 0.02)
+    y = x.copy()
+    y[:, :12, 0] += 5.                                  # half of the walkers sit elsewhere: not converged
+    assert rp.split_rhat(y)[0] > 1.3
