@@ -184,8 +184,69 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// ---------------------------------------------------------------------------------------
+// Lean FP64 pow for the per-walker model constants.  libm's pow is a ~300-instruction dependent chain (it carries
+// log2(x) in extended precision to be correctly rounded for any exponent); the constants here need ~1e-12 (the FP64
+// parity tolerance is 1e-9 on the log-posterior) and have |y log2 x| < 400, so  x^y = 2^(y log2 x)  with a plain
+// double log2 is good to ~1e-13: log2 by the atanh series on the mantissa in [sqrt(1/2), sqrt 2), 2^t by range
+// reduction and a degree-12 polynomial.  ~65 dependent operations.  Anything unusual (non-positive, subnormal or
+// non-finite base, huge result) goes to libm, so the special-case semantics are libm's.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp2_core(double t) {               // |t| < 1000
+    const double magic = 6755399441055744.0;                           // 1.5 * 2^52
+    const double r = t + magic;
+    const int n = __double2loint(r);
+    const double f = t - (r - magic);
+    double p = 2.56784359934881958e-11;
+    p = fma(p, f, 4.44553827187081007e-10);
+    p = fma(p, f, 7.05491162080112088e-09);
+    p = fma(p, f, 1.01780860092396960e-07);
+    p = fma(p, f, 1.32154867901443053e-06);
+    p = fma(p, f, 1.52527338040598377e-05);
+    p = fma(p, f, 1.54035303933816061e-04);
+    p = fma(p, f, 1.33335581464284411e-03);
+    p = fma(p, f, 9.61812910762847688e-03);
+    p = fma(p, f, 5.55041086648215762e-02);
+    p = fma(p, f, 2.40226506959100694e-01);
+    p = fma(p, f, 6.93147180559945286e-01);
+    p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+__device__ __forceinline__ double log2_normal(double x) {             // x positive, finite, normal
+    int hi = __double2hiint(x);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }                   // [sqrt(1/2), sqrt 2)
+    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;                  // |s| <= 0.1716
+    double p = 1. / 23.;
+    p = fma(p, s2, 1. / 21.);
+    p = fma(p, s2, 1. / 19.);
+    p = fma(p, s2, 1. / 17.);
+    p = fma(p, s2, 1. / 15.);
+    p = fma(p, s2, 1. / 13.);
+    p = fma(p, s2, 1. / 11.);
+    p = fma(p, s2, 1. / 9.);
+    p = fma(p, s2, 1. / 7.);
+    p = fma(p, s2, 1. / 5.);
+    p = fma(p, s2, 1. / 3.);
+    p = fma(p, s2, 1.);
+    return fma(2.8853900817779268 * s, p, (double)e);                   // e + (2 / ln 2) atanh(s)
+}
+__device__ __forceinline__ double pow_fast(double b, double e) {
+    const int hi = __double2hiint(b);
+    if (hi >= 0x00100000 && hi < 0x7ff00000) {                          // positive, normal, finite
+        const double t = e * log2_normal(b);
+        if (fabs(t) < 1000.) return exp2_core(t);
+    }
+    return pow(b, e);
+}
+__device__ __forceinline__ double log2_fast(double x) {
+    const int hi = __double2hiint(x);
+    return (hi >= 0x00100000 && hi < 0x7ff00000) ? log2_normal(x) : log2(x);
+}
+
 // power() of models.py:42-48: zero for any non-positive (or NaN) base
-__device__ __forceinline__ double pw(double b, double e) { return b > 0. ? pow(b, e) : 0.; }
+__device__ __forceinline__ double pw(double b, double e) { return b > 0. ? pow_fast(b, e) : 0.; }
 
 // log-prior of one parameter (models.py:1055-1098): strict bounds, -inf outside
 __device__ __forceinline__ double prior_logp(const PriorDev &pr, int d, double p) {
@@ -245,7 +306,7 @@ __device__ inline double walker_term(const ProblemDev &P, const double *p, int k
         return 0.;
     }
     if (guarded && !(base > 0.)) return 0.;
-    return pow(base, expo);
+    return pow_fast(base, expo);
 }
 
 template <int MODEL>
@@ -263,7 +324,7 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, const 
         double ttr = 19.5 * term[3];
         double base = mc[1] / ttr;                        // (a t / t_tr) > 0  <=>  a/t_tr > 0 for t > 0
         s.wc[0] = KT; s.wc[1] = KL;
-        s.wc[2] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.wc[2] = (base > 0.) ? log2_fast(base) : -Mth<double>::inf();
         if (MODEL == 3) s.wc[3] = p[5];                   // E(B-V)
         s.wc[4] = (KT > 0.) ? 1. / KT : 0.;               // 1/T = wc4 t^-eps_T
         s.wc[5] = (KT > 0.) ? KL / (KT * KT * KT * KT) : 0.;   // L/T^4 = wc5 t^(eps_L - 4 eps_T) exp(-(a t/t_tr)^alpha)
@@ -283,13 +344,13 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, const 
         double t_br = mc[5] * term[0] * term[1] * term[2];
         double L_br = mc[3] * term[3] * term[4] * term[5];
         // models.py:586 as written: v_s ** 0.58 ** f_rho_M ** 0.03 is right-associative
-        double T_br = mc[4] * term[6] * pow(v, pow(0.58, term[7]));
+        double T_br = mc[4] * term[6] * pow_fast(v, pow_fast(0.58, term[7]));
         double t_tr = mc[6] * sqrt(Menv / v);
         double base = mc[1] / t_tr;
         s.wc[0] = T_br / k_kB;
         s.wc[1] = c3sq * L_br;
-        s.wc[2] = (t_br > 0.) ? -log2(t_br) : Mth<double>::nan();   // log2(ttilde) = log2(t) + wc2
-        s.wc[3] = (base > 0.) ? log2(base) : -Mth<double>::inf();
+        s.wc[2] = (t_br > 0.) ? -log2_fast(t_br) : Mth<double>::nan();   // log2(ttilde) = log2(t) + wc2
+        s.wc[3] = (base > 0.) ? log2_fast(base) : -Mth<double>::inf();
         s.wc[4] = 1. / (0.97 * s.wc[0]);                    // 1/T on the early branch: wc4 ttilde^(1/3)
         s.wc[5] = 1. / s.wc[0];                             // 1/T on the late branch:  wc5 ttilde^0.45
         s.t0 = p[4];
@@ -473,28 +534,7 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
 // (h nu / k T = 173: such a sample is 1e-75 of its weight) so that four denominators multiply to < 2^1000; one division per
 // four samples.  ~21 FP64 pipe operations per Planck sample instead of ~55 (libm exp2 + one division each).
 // Callers guarantee every exponent >= 2^-10 (2^x - 1 then keeps 1e-13 relative accuracy).
-__device__ __forceinline__ double ex2m1_f64(double x) {
-    x = fmin(x, 250.);
-    const double magic = 6755399441055744.0;                    // 1.5 * 2^52: adding it rounds x to the nearest integer
-    const double t = x + magic;
-    const int n = __double2loint(t);
-    const double f = x - (t - magic);
-    double p = 2.56784359934881958e-11;
-    p = fma(p, f, 4.44553827187081007e-10);
-    p = fma(p, f, 7.05491162080112088e-09);
-    p = fma(p, f, 1.01780860092396960e-07);
-    p = fma(p, f, 1.32154867901443053e-06);
-    p = fma(p, f, 1.52527338040598377e-05);
-    p = fma(p, f, 1.54035303933816061e-04);
-    p = fma(p, f, 1.33335581464284411e-03);
-    p = fma(p, f, 9.61812910762847688e-03);
-    p = fma(p, f, 5.55041086648215762e-02);
-    p = fma(p, f, 2.40226506959100694e-01);
-    p = fma(p, f, 6.93147180559945286e-01);
-    p = fma(p, f, 1.0);
-    const double e = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-    return e - 1.0;
-}
+__device__ __forceinline__ double ex2m1_f64(double x) { return exp2_core(fmin(x, 250.)) - 1.0; }
 
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, int K2, double iA, double iB,
@@ -668,7 +708,7 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
         const float xsum = rng.y * (i0 + i1) * (MODEL == 4 ? (float)(1. + 1. / 0.74) : 2.f);   // sum of the 4 exponents
         if (rng.x * imin >= 0.0625f) {                      // no cancellation in 2^x - 1 anywhere in the filter
             const bool clamp = xsum > 124.f;                 // the product of four denominators could overflow: Wien form
-#ifdef LCF_X_TIMING
+#ifdef LCF_X_PATHCOUNT
             atomicAdd(&g_phase_clk[clamp ? 7 : 6], 1ull);        // lane-tiles on the plain / clamped fast path
 #endif
             const float4 *bf = reinterpret_cast<const float4 *>(b);
@@ -716,7 +756,7 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
         }
     }
     // careful path (cancellation in 2^x - 1: Rayleigh-Jeans regime, either precision)
-#ifdef LCF_X_TIMING
+#ifdef LCF_X_PATHCOUNT
     atomicAdd(&g_phase_clk[5], 1ull << 40);                   // lane-tiles on the careful path (upper bits of slot 5)
 #endif
     if (n0) {
@@ -894,6 +934,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         }
     }
     __syncthreads();
+    LCF_TICK(6);
     // 1b: one thread per (walker, term): FP64 transcendentals of the model constants, log-priors, ln z and ln u
     {
         const int per = NT + D + 2;
@@ -911,6 +952,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         }
     }
     __syncthreads();
+    LCF_TICK(7);
     // 1c: one thread per walker: sum of the log-priors (same order as the reference's loop), model constants
     if (tid < wpb) {
         const long long i = g * wpb + tid;
