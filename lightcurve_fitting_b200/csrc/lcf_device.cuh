@@ -534,19 +534,36 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
 // (h nu / k T = 173: such a sample is 1e-75 of its weight) so that four denominators multiply to < 2^1000; one division per
 // four samples.  ~21 FP64 pipe operations per Planck sample instead of ~55 (libm exp2 + one division each).
 // Callers guarantee every exponent >= 2^-10 (2^x - 1 then keeps 1e-13 relative accuracy).
-__device__ __forceinline__ double ex2m1_f64(double x) { return exp2_core(fmin(x, 250.)) - 1.0; }
+// 2^x - 1 for the FP64 loop, x in [0, 256): x = n + j/16 + f with |f| <= 1/32, 2^(j/16) from a 16-entry shared-memory
+// table (distinct j hit distinct banks), 2^f by a degree-6 polynomial (truncation 4e-16): 7 FP64 operations fewer than
+// the table-free exp2_core.
+__device__ __forceinline__ double ex2m1_f64(double x, const double *__restrict__ e2t) {
+    const double magic = 422212465065984.0;                              // 1.5 * 2^48: adding it rounds x to a multiple of 1/16
+    const double r = x + magic;
+    const int k = __double2loint(r);                                     // 16 n + j
+    const double f = x - (r - magic);
+    double p = 1.54035303933816061e-04;
+    p = fma(p, f, 1.33335581464284411e-03);
+    p = fma(p, f, 9.61812910762847688e-03);
+    p = fma(p, f, 5.55041086648215762e-02);
+    p = fma(p, f, 2.40226506959100694e-01);
+    p = fma(p, f, 6.93147180559945286e-01);
+    const double t = e2t[k & 15];
+    p = fma(t * f, p, t);                                                // 2^(j/16) (1 + f q(f))
+    return __hiloint2double(__double2hiint(p) + ((k >> 4) << 20), __double2loint(p)) - 1.0;
+}
 
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, int K2, double iA, double iB,
-                                                const double2 *__restrict__ tab, double &SA, double &SB) {
+                                                const double2 *__restrict__ tab, const double *__restrict__ e2t, double &SA, double &SB) {
     constexpr int ts = kTabStride;
     double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
     for (const double4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
         const double4 s = *pb;
         double w0 = s.z, w1 = s.w;
         if (TAB) { const double2 t = *tab; tab += ts; w0 = t.x; w1 = t.y; }
-        const double dA0 = ex2m1_f64(s.x * iA), dA1 = ex2m1_f64(s.y * iA);
-        const double dB0 = ex2m1_f64(s.x * iB), dB1 = ex2m1_f64(s.y * iB);
+        const double dA0 = ex2m1_f64(s.x * iA, e2t), dA1 = ex2m1_f64(s.y * iA, e2t);
+        const double dB0 = ex2m1_f64(s.x * iB, e2t), dB1 = ex2m1_f64(s.y * iB, e2t);
         const double p0 = dA0 * dB0, p1 = dA1 * dB1;
         const double r = 1.0 / (p0 * p1);
         const double t0 = w0 * (r * p1), t1 = w1 * (r * p0);       // w/(dA dB) of each sample
@@ -688,7 +705,7 @@ template <typename R> struct PointFE {
 template <int MODEL, typename R>
 __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *bank, const int4 fi,
                                                const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, R &y0, R &y1) {
+                                               const typename Vec2<R>::type *tab, const double *e2t, R &y0, R &y1) {
     typedef Mth<R> M;
     typedef typename Vec2<R>::type R2;
     typedef typename Vec4<R>::type R4;
@@ -736,16 +753,21 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
     }
     if (sizeof(R) == 8) {
         const double amin = (double)__int_as_float(fi.z) * (1. - 1e-6);      // float copy of the filter's smallest a, rounded down
-        const double i0 = n0 ? (double)f0.invT : (double)f1.invT, i1 = n1 ? (double)f1.invT : i0;
+        double i0 = n0 ? (double)f0.invT : (double)f1.invT, i1 = n1 ? (double)f1.invT : i0;
         if (amin * fmin(i0, i1) >= 0.0009765625) {
+            // exponents capped at 250 per POINT (h nu / k T = 173 at the filter's bluest sample: every sample of such a point is
+            // below 2^-190 of its weight), so four denominators multiply to < 2^1000
+            const double icap = 250. / ((double)__int_as_float(fi.w) * (MODEL == 4 ? (double)c74 : 1.) * (1. + 1e-6));
+            i0 = fmin(i0, icap);
+            i1 = fmin(i1, icap);
             const double4 *bd = reinterpret_cast<const double4 *>(b);
             const double2 *td = reinterpret_cast<const double2 *>(tb);
             double S0, S1;
-            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, S0, S1);
-            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, S0, S1);
+            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, e2t, S0, S1);
+            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, e2t, S0, S1);
             if (MODEL == 4) {
                 double S0s, S1s;
-                planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, S0s, S1s);
+                planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, e2t, S0s, S1s);
                 if (n0) y0 = (R)fmin((double)f0.amp * S0, (double)f0.amp * (double)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fmin((double)f1.amp * S1, (double)f1.amp * (double)c74_4 * S1s);
             } else {
@@ -833,9 +855,10 @@ constexpr int kMaxCluster = 8;      // portable cluster size limit
 constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model terms, prior terms, ln z, ln u
 
 template <typename R> struct SmemLayout {
-    size_t off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
+    size_t off_e2t, off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
         size_t o = 0;
+        off_e2t = o;  o += sizeof(R) == 8 ? 16 * sizeof(double) : 0;             // 2^(j/16), FP64 loop
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_tab = o;  o += tab ? (size_t)nsamples * kTabStride * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][32]
         off_foff = o; o += (size_t)nfilters * sizeof(int4);                       o = (o + 15) & ~(size_t)15;
@@ -871,6 +894,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     typedef typename Vec4<R>::type R4;
     R4 *s_bank = reinterpret_cast<R4 *>(smem + L.off_bank);
     R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
+    const double *s_e2t = reinterpret_cast<const double *>(smem + L.off_e2t);
     int4 *s_finfo = reinterpret_cast<int4 *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
     double *s_t = reinterpret_cast<double *>(smem + L.off_t);
@@ -1026,7 +1050,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             fa.state = fa.invT > (R)0 ? 1 : 0;
             fb.state = fb.invT > (R)0 ? 1 : 0;
             R ya, yb;
-            blackbody_pair<MODEL, R>(s_bank, fi, fa, fb, two, s_tabw, ya, yb);
+            blackbody_pair<MODEL, R>(s_bank, fi, fa, fb, two, s_tabw, s_e2t, ya, yb);
             if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
             if (Mv.mode == MODE_MODEL) {
                 Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
@@ -1123,6 +1147,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
     __syncthreads();
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
@@ -1172,6 +1197,7 @@ __global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
     SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
     __syncthreads();
     const int D = sP.ndim;
     MoveDev Mv;
