@@ -553,6 +553,15 @@ __device__ __forceinline__ double ex2m1_f64(double x, const double *__restrict__
     return __hiloint2double(__double2hiint(p) + ((k >> 4) << 20), __double2loint(p)) - 1.0;
 }
 
+// 1/x for a positive normal double: MUFU.RCP64H seed (20 bits) + two Newton steps; no special-case handling
+__device__ __forceinline__ double rcp_f64(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, int K2, double iA, double iB,
                                                 const double2 *__restrict__ tab, const double *__restrict__ e2t, double &SA, double &SB) {
@@ -565,7 +574,7 @@ __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, 
         const double dA0 = ex2m1_f64(s.x * iA, e2t), dA1 = ex2m1_f64(s.y * iA, e2t);
         const double dB0 = ex2m1_f64(s.x * iB, e2t), dB1 = ex2m1_f64(s.y * iB, e2t);
         const double p0 = dA0 * dB0, p1 = dA1 * dB1;
-        const double r = 1.0 / (p0 * p1);
+        const double r = rcp_f64(p0 * p1);
         const double t0 = w0 * (r * p1), t1 = w1 * (r * p0);       // w/(dA dB) of each sample
         a0 = fma(t0, dB0, a0); b0 = fma(t0, dA0, b0);
         a1 = fma(t1, dB1, a1); b1 = fma(t1, dA1, b1);
