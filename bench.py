@@ -246,6 +246,7 @@ def run_ours(args):
     pin_in = torch.from_numpy(np.ascontiguousarray(p0)).pin_memory()
     pin_chain = torch.empty((args.steps, W_total, D), dtype=torch.float64).pin_memory()
     pin_lnp = torch.empty((args.steps, W_total), dtype=torch.float64).pin_memory()
+    ens.close()
     del ens
     if world == 1:
         s = EnsembleSampler(W_total, D, prob, seed=99)
@@ -276,6 +277,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         api = 'ShardedEnsemble.set_state(host) + run(store) + get_chain() + get_log_prob() on every rank'
+        e2.close()
     e2e = {'value': W_total * args.steps / dt, 'unit': 'walker-steps/s',
            'h2d_bytes_per_step': int(pin_in.numel() * 8 / args.steps),
            'd2h_bytes_per_step': int(W_total * (D + 1) * 8),

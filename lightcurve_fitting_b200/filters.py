@@ -228,6 +228,9 @@ for _f in all_filters:
         filtdict[_n] = _f
 
 
+_PACK_CACHE = {}
+
+
 def pack_bank(filters, z=0., cutoff_freq=np.inf, ebv=0.):
     """Pack unique ``filters`` into the flat device bank.
 
@@ -238,14 +241,21 @@ def pack_bank(filters, z=0., cutoff_freq=np.inf, ebv=0.):
     """
     offs, al, ws, ks = [0], [], [], []
     for f in filters:
-        nu, tnw = f.packed()
-        nup = nu * (1. + z)
-        kap = fitzpatrick99(K.c_AA_THz / nup, 3.1, 3.1)
-        w = K.c2 * nup ** 3 * np.minimum(1., cutoff_freq / nup) * tnw
+        key = (f, float(z), float(cutoff_freq))
+        hit = _PACK_CACHE.get(key)                        # survey batches pack the same few filters 10^4 times
+        if hit is None:
+            nu, tnw = f.packed()
+            nup = nu * (1. + z)
+            kap = fitzpatrick99(K.c_AA_THz / nup, 3.1, 3.1)
+            w0 = K.c2 * nup ** 3 * np.minimum(1., cutoff_freq / nup) * tnw
+            hit = (K.c1 * nup, w0, kap)
+            if len(_PACK_CACHE) < 4096:
+                _PACK_CACHE[key] = hit
+        alpha, w, kap = hit
         if np.any(np.asarray(ebv) != 0.):
             w = w * 10. ** (-0.4 * float(ebv) * kap)
-        al.append(K.c1 * nup)
+        al.append(alpha)
         ws.append(w)
         ks.append(kap)
-        offs.append(offs[-1] + len(nu))
+        offs.append(offs[-1] + len(alpha))
     return (np.asarray(offs, np.int32), np.concatenate(al), np.concatenate(ws), np.concatenate(ks))

@@ -118,6 +118,15 @@ class ShardedEnsemble:
             check(lib().lcf_ensemble_sync(self.sampler.handle))
             dist.barrier(group=self.group)
 
+    def close(self):
+        """Unmap the peers' replicas on every rank before any rank frees its own (collective when fused)."""
+        if self.fused:
+            import torch.distributed as dist
+            self._quiesce()
+            check(lib().lcf_ensemble_peers_detach(self.sampler.handle))
+            self.fused = False
+            dist.barrier(group=self.group)
+
     def set_state(self, coords):
         if self.fused:
             self._quiesce()

@@ -49,6 +49,7 @@ def main():
         print('[rank %d] %s: own chain identical to single-GPU: %s; full replica identical: %s (fused=%s)'
               % (rank, exchange, same, same_state, ens.fused), flush=True)
         ok = ok and same and same_state
+        ens.close()
         del ens
         dist.barrier()
     t = torch.tensor([1 if ok else 0], device='cuda')
