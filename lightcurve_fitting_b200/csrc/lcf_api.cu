@@ -146,6 +146,7 @@ struct lcf_batch {
     unsigned long long seed = 0;
     ProblemDev *d_probs = nullptr;
     TileDev *d_tiles = nullptr;
+    int *d_order = nullptr;
     double *d_coords = nullptr, *d_logp = nullptr, *d_chain = nullptr, *d_lnp = nullptr;
     unsigned long long *d_acc = nullptr;
     int *d_status = nullptr;
@@ -155,7 +156,7 @@ struct lcf_batch {
     double last_ms = 0.;
     long long last_launches = 0;
     ~lcf_batch() {
-        cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
+        cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_order); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
         cudaFree(d_acc); cudaFree(d_status);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -1208,7 +1209,7 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     int max_tiles = 1;
     for (;;) {
         smem = 0;
-        for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 16));
+        for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 8));
         if (smem <= kSmemMax / 2 || l == 0) break;
         --l;
     }
@@ -1221,7 +1222,7 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
         max_tiles = std::max(max_tiles, ht[i].ntiles);
     }
     int nw = g_tune_nw > 0 ? g_tune_nw : std::min(8, max_tiles);
-    nw = std::max(1, std::min(nw, 16));
+    nw = std::max(1, std::min(nw, 8));                    // k_chain is compiled for <= 256 threads
     smem = 0;
     for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw));
     if (smem > kSmemMax) { delete b; return fail(LCF_ERR_ARG, "filter bank does not fit in shared memory"); }
@@ -1233,6 +1234,17 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     b->d_probs = reinterpret_cast<ProblemDev *>(dp);
     if ((rc = upload(ht, &dp))) { delete b; return rc; }
     b->d_tiles = reinterpret_cast<TileDev *>(dp);
+    {   // every CTA runs a whole chain, so the grid's makespan is a scheduling problem: longest processing time first
+        std::vector<int> order(nproblems);
+        std::vector<double> work(nproblems);
+        for (long long i = 0; i < nproblems; ++i) {
+            order[i] = (int)i;
+            work[i] = (double)b->probs[i]->dev.npoints * std::max(1., b->probs[i]->mean_samples);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return work[x] > work[y]; });
+        if ((rc = upload(order, &dp))) { delete b; return rc; }
+        b->d_order = reinterpret_cast<int *>(dp);
+    }
     cudaError_t ce;
     if ((ce = cudaMalloc(&b->d_coords, sizeof(double) * nproblems * b->W * b->D)) != cudaSuccess ||
         (ce = cudaMalloc(&b->d_logp, sizeof(double) * nproblems * b->W)) != cudaSuccess ||
@@ -1280,7 +1292,7 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     CUDA_TRY(cudaMemsetAsync(b->d_acc, 0, sizeof(unsigned long long) * b->nprob * b->W, b->stream));
     BatchDev B;
     memset(&B, 0, sizeof(B));
-    B.probs = b->d_probs; B.tiles = b->d_tiles;
+    B.probs = b->d_probs; B.tiles = b->d_tiles; B.order = b->d_order;
     B.coords = b->d_coords; B.logp = b->d_logp; B.accepted = b->d_acc; B.status = b->d_status;
     B.chain = b->d_chain; B.lnp = b->d_lnp;
     B.W = b->W; B.n0 = b->n0; B.nproblems = b->nprob;

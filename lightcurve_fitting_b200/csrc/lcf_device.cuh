@@ -1177,6 +1177,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
 struct BatchDev {
     const ProblemDev *probs;         // [nproblems]
     const TileDev *tiles;            // [nproblems]
+    const int *order;                // [nproblems] CTA -> problem, by decreasing work (NULL: identity)
     double *coords;                  // [nproblems][W][D] colour-major
     double *logp;                    // [nproblems][W]
     unsigned long long *accepted;    // [nproblems][W]
@@ -1189,12 +1190,13 @@ struct BatchDev {
     int wpb_log2, init_logp;
 };
 
+// at most 8 warps per CTA; FP32: 64 registers so that four CTAs (32 warps) share an SM, as in k_pass
 template <int MODEL, typename R>
-__global__ void __launch_bounds__(512) k_chain(const BatchDev B) {
+__global__ void __launch_bounds__(256, (sizeof(R) == 4 ? 4 : 2)) k_chain(const BatchDev B) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ProblemDev sP;
     __shared__ TileDev sT;
-    const long long prob = blockIdx.x;
+    const long long prob = B.order ? B.order[blockIdx.x] : blockIdx.x;   // longest problems first: the tail of the grid is short ones
     {
         const int *src = reinterpret_cast<const int *>(B.probs + prob);
         int *dst = reinterpret_cast<int *>(&sP);
