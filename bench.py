@@ -254,12 +254,12 @@ def run_ours(args):
         s.reset()
         barrier()
         t0 = time.perf_counter()
-        s.run_mcmc(pin_in.numpy(), args.steps, skip_initial_state_check=True)       # H2D start positions + K steps
-        chain = s.get_chain(out=pin_chain.numpy())                                    # D2H chain
-        lnp = s.get_log_prob(out=pin_lnp.numpy())                                     # D2H log-probabilities
+        chain, lnp = pin_chain.numpy(), pin_lnp.numpy()
+        # H2D start positions + K steps; every finished step is streamed D2H into the pinned buffers while the next ones run
+        s.run_mcmc(pin_in.numpy(), args.steps, skip_initial_state_check=True, chain_out=chain, log_prob_out=lnp)
         dt = time.perf_counter() - t0
         assert np.isfinite(lnp).all() and chain.shape == (args.steps, W_total, D)
-        api = 'EnsembleSampler.run_mcmc(host start positions) + get_chain() + get_log_prob()'
+        api = 'EnsembleSampler.run_mcmc(host start positions, chain_out=pinned, log_prob_out=pinned): chain streamed to the host'
     else:
         e2 = ShardedEnsemble(prob, W_total, seed=99, rank=rank, world=world, exchange=args.exchange)
         e2.set_state(pin_in.numpy())

@@ -152,6 +152,10 @@ int  lcf_ensemble_reset(lcf_ensemble *e);
 /* nsteps stretch-move iterations with device counter-based RNG (Philox4x32-10 keyed by
    (seed, iteration, half, walker)); store != 0 appends to the HBM-resident chain.          */
 int  lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store);
+/* run(store = 1) that also streams every finished step into host buffers (ideally page-locked) on a copy stream,
+   overlapping the device-to-host transfer of the chain with the sampling of the next steps.               */
+int  lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host /* [nsteps][nwalkers][ndim] */,
+                              double *log_prob_host /* [nsteps][nwalkers] */);
 /* the same iterations driven by caller-supplied draws, in emcee's order:
    split[s][w] in {0,1}; for each step the Ns0 entries for split 0 (ascending walker index)
    then the Ns1 entries for split 1: z (stretch factors), partner (index into the

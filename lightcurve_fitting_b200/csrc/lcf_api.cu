@@ -114,9 +114,9 @@ struct lcf_ensemble {
     int *d_nan = nullptr;
     double *d_chain = nullptr, *d_lnp = nullptr;
     long long cap = 0, nstored = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = true;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_step = nullptr;
     bool has_state = false;
     double last_ms = 0.;
     long long last_launches = 0;
@@ -134,6 +134,8 @@ struct lcf_ensemble {
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_step) cudaEventDestroy(ev_step);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (stream && own_stream) cudaStreamDestroy(stream);
     }
 };
@@ -951,6 +953,45 @@ int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
     }
     CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->last_ms = ms;
+    return check_nan(e);
+}
+
+// Like lcf_ensemble_run(store = 1), and every finished step is copied to the caller's host buffers on a second stream
+// while the next steps compute (event-ordered; page-locked host memory makes the copies truly asynchronous).  The chain
+// also stays in HBM (lcf_ensemble_get_chain, diagnostics).  chain_host [nsteps][nwalkers][ndim], log_prob_host [nsteps][nwalkers].
+int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host, double *log_prob_host) {
+    if (!e || !chain_host || !log_prob_host) return fail(LCF_ERR_ARG, "null argument");
+    if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    int rc = ensure_capacity(e, e->nstored + nsteps);
+    if (rc) return rc;
+    if (!e->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+    }
+    e->last_launches = 0;
+    const size_t cw = (size_t)e->W * e->D, lw = (size_t)e->W;
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    for (long long s = 0; s < nsteps; ++s) {
+        for (int half = 0; half < 2; ++half) {
+            MoveDev mv;
+            fill_move(e, half, 1, mv);
+            rc = launch_pass(e->p, mv, e->stream, &e->last_launches);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(e->ev_step, e->stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_step, 0));
+        CUDA_TRY(cudaMemcpyAsync(chain_host + s * cw, e->d_chain + e->nstored * cw, sizeof(double) * cw, cudaMemcpyDeviceToHost, e->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(log_prob_host + s * lw, e->d_lnp + e->nstored * lw, sizeof(double) * lw, cudaMemcpyDeviceToHost, e->copy_stream));
+        e->iteration += 1;
+        e->nstored += 1;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->copy_stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->last_ms = ms;

@@ -115,12 +115,24 @@ class EnsembleSampler:
         self.last_ms, self.last_launches = ms.value, n.value
 
     def run_mcmc(self, initial_state, nsteps, progress=False, progress_kwargs=None, skip_initial_state_check=False,
-                 store=True, **kwargs):
+                 store=True, chain_out=None, log_prob_out=None, **kwargs):
         """Iterate the stretch move ``nsteps`` times from ``initial_state`` ([nwalkers, ndim] or a State; ``None``
-        continues from the current position).  Returns a State that unpacks to (coords, log_prob, random_state)."""
+        continues from the current position).  Returns a State that unpacks to (coords, log_prob, random_state).
+
+        ``chain_out`` [nsteps, nwalkers, ndim] and ``log_prob_out`` [nsteps, nwalkers] (C-contiguous float64, ideally
+        page-locked) make the run stream every finished step to the host while the next ones are sampled."""
         if initial_state is not None:
             self._set_initial(initial_state, skip_initial_state_check)
-        check(lib().lcf_ensemble_run(self.handle, int(nsteps), 1 if store else 0))
+        if chain_out is not None or log_prob_out is not None:
+            if chain_out is None or log_prob_out is None or not store:
+                raise ValueError('chain_out and log_prob_out go together and imply store=True')
+            if (chain_out.shape != (int(nsteps), self.nwalkers, self.ndim) or log_prob_out.shape != (int(nsteps), self.nwalkers)
+                    or chain_out.dtype != np.float64 or log_prob_out.dtype != np.float64
+                    or not chain_out.flags.c_contiguous or not log_prob_out.flags.c_contiguous):
+                raise ValueError('chain_out / log_prob_out must be C-contiguous float64 [nsteps, nwalkers(, ndim)]')
+            check(lib().lcf_ensemble_run_to_host(self.handle, int(nsteps), dptr(chain_out), dptr(log_prob_out)))
+        else:
+            check(lib().lcf_ensemble_run(self.handle, int(nsteps), 1 if store else 0))
         self._timing()
         self.iteration += int(nsteps) if store else 0
         return self._state()

@@ -668,3 +668,22 @@ def test_device_convergence_diagnostics_match_oracle():
     assert (win_l == -1).all()
     with pytest.raises(AutocorrError):
         s.get_autocorr_time(tol=1e6)
+
+
+def test_run_streams_chain_to_host_buffers():
+    """run_mcmc(chain_out=, log_prob_out=) delivers the same chain as get_chain()/get_log_prob() of an identical run."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.example_sc4(npoints=30)
+    prob = wl.device_problem('fp32')
+    nw, nsteps = 32, 9
+    p0 = wl.start(nw, np.random.default_rng(5))
+    a = EnsembleSampler(nw, wl.ndim, prob, seed=8)
+    a.run_mcmc(p0, nsteps)
+    b = EnsembleSampler(nw, wl.ndim, prob, seed=8)
+    ch, lp = np.full((nsteps, nw, wl.ndim), np.nan), np.full((nsteps, nw), np.nan)
+    b.run_mcmc(p0, nsteps, chain_out=ch, log_prob_out=lp)
+    np.testing.assert_array_equal(ch, a.get_chain())
+    np.testing.assert_array_equal(lp, a.get_log_prob())
+    np.testing.assert_array_equal(b.get_chain(), ch)                 # the chain also stays on the device
+    with pytest.raises(ValueError):
+        b.run_mcmc(None, 3, chain_out=ch, log_prob_out=lp)            # wrong shape
