@@ -268,15 +268,24 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         e2.set_state(pin_in.numpy())                                                  # H2D start positions
-        e2.run(args.steps, store=True)
-        e2.finish()
-        chain, lnp = e2.get_own_chain(pin_chain.numpy(), pin_lnp.numpy())                # D2H of this rank's walkers
+        first, count = e2.own_walkers()
+        if e2.fused:      # this rank's walkers streamed D2H into pinned buffers while the next steps run
+            chain = pin_chain.numpy().reshape(-1)[:args.steps * count * D].reshape(args.steps, count, D)
+            lnp = pin_lnp.numpy().reshape(-1)[:args.steps * count].reshape(args.steps, count)
+            e2.run(args.steps, store=True, chain_out=chain, log_prob_out=lnp)
+            e2.finish()
+        else:
+            e2.run(args.steps, store=True)
+            e2.finish()
+            chain, lnp = e2.get_own_chain(pin_chain.numpy(), pin_lnp.numpy())            # D2H of this rank's walkers
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        api = 'ShardedEnsemble.set_state(host) + run(store) + get_chain() + get_log_prob() on every rank'
+        api = ('ShardedEnsemble.set_state(host) + run(store, chain_out=pinned, log_prob_out=pinned) on every rank: own walkers '
+               'streamed to the host' if e2.fused else
+               'ShardedEnsemble.set_state(host) + run(store) + get_own_chain() on every rank')
         e2.close()
     e2e = {'value': W_total * args.steps / dt, 'unit': 'walker-steps/s',
            'h2d_bytes_per_step': int(pin_in.numel() * 8 / args.steps),

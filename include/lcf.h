@@ -156,6 +156,9 @@ int  lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store);
    overlapping the device-to-host transfer of the chain with the sampling of the next steps.               */
 int  lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host /* [nsteps][nwalkers][ndim] */,
                               double *log_prob_host /* [nsteps][nwalkers] */);
+/* the same for the walkers [first, first + count) only (a rank's own walkers of a shared ensemble)        */
+int  lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t first, int64_t count,
+                                    double *chain_host /* [nsteps][count][ndim] */, double *log_prob_host /* [nsteps][count] */);
 /* the same iterations driven by caller-supplied draws, in emcee's order:
    split[s][w] in {0,1}; for each step the Ns0 entries for split 0 (ascending walker index)
    then the Ns1 entries for split 1: z (stretch factors), partner (index into the

@@ -67,6 +67,7 @@ SYMBOLS = [
     ('lcf_ensemble_reset', C.c_int, [_vp]),
     ('lcf_ensemble_run', C.c_int, [_vp, C.c_int64, C.c_int]),
     ('lcf_ensemble_run_to_host', C.c_int, [_vp, C.c_int64, _pd, _pd]),
+    ('lcf_ensemble_run_to_host_slice', C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _pd, _pd]),
     ('lcf_ensemble_run_replay', C.c_int, [_vp, C.c_int64, C.c_int, _pi, _pd, _pi, _pd]),
     ('lcf_ensemble_reserve', C.c_int, [_vp, C.c_int64]),
     ('lcf_ensemble_half_step', C.c_int, [_vp, C.c_int, C.c_int]),

@@ -962,9 +962,11 @@ int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
 // Like lcf_ensemble_run(store = 1), and every finished step is copied to the caller's host buffers on a second stream
 // while the next steps compute (event-ordered; page-locked host memory makes the copies truly asynchronous).  The chain
 // also stays in HBM (lcf_ensemble_get_chain, diagnostics).  chain_host [nsteps][nwalkers][ndim], log_prob_host [nsteps][nwalkers].
-int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host, double *log_prob_host) {
+int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t first, int64_t count, double *chain_host,
+                                   double *log_prob_host) {
     if (!e || !chain_host || !log_prob_host) return fail(LCF_ERR_ARG, "null argument");
     if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
+    if (first < 0 || count < 0 || first + count > e->W) return fail(LCF_ERR_ARG, "walker range out of bounds");
     CUDA_TRY(cudaSetDevice(e->p->device));
     int rc = ensure_capacity(e, e->nstored + nsteps);
     if (rc) return rc;
@@ -973,7 +975,7 @@ int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
     }
     e->last_launches = 0;
-    const size_t cw = (size_t)e->W * e->D, lw = (size_t)e->W;
+    const size_t D = e->D, cw = (size_t)e->W * D, lw = (size_t)e->W;
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     for (long long s = 0; s < nsteps; ++s) {
         for (int half = 0; half < 2; ++half) {
@@ -984,8 +986,10 @@ int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host
         }
         CUDA_TRY(cudaEventRecord(e->ev_step, e->stream));
         CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_step, 0));
-        CUDA_TRY(cudaMemcpyAsync(chain_host + s * cw, e->d_chain + e->nstored * cw, sizeof(double) * cw, cudaMemcpyDeviceToHost, e->copy_stream));
-        CUDA_TRY(cudaMemcpyAsync(log_prob_host + s * lw, e->d_lnp + e->nstored * lw, sizeof(double) * lw, cudaMemcpyDeviceToHost, e->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(chain_host + s * count * D, e->d_chain + e->nstored * cw + first * D, sizeof(double) * count * D,
+                                 cudaMemcpyDeviceToHost, e->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(log_prob_host + s * count, e->d_lnp + e->nstored * lw + first, sizeof(double) * count,
+                                 cudaMemcpyDeviceToHost, e->copy_stream));
         e->iteration += 1;
         e->nstored += 1;
     }
@@ -996,6 +1000,11 @@ int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->last_ms = ms;
     return check_nan(e);
+}
+
+int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host, double *log_prob_host) {
+    if (!e) return fail(LCF_ERR_ARG, "null argument");
+    return lcf_ensemble_run_to_host_slice(e, nsteps, 0, e->W, chain_host, log_prob_host);
 }
 
 int lcf_ensemble_run_replay(lcf_ensemble *e, int64_t nsteps, int store, const int32_t *split, const double *z,

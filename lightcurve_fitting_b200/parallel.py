@@ -130,18 +130,43 @@ class ShardedEnsemble:
     def set_state(self, coords):
         if self.fused:
             self._quiesce()
-        self.sampler._set_initial(coords, True)
+        if self.world > 1 and self.coords.is_cuda and self._even():
+            # initial log-probabilities: every rank evaluates its own walkers only, one all-gather completes them
+            import torch.distributed as dist
+            from .sampler import State
+            coords = np.ascontiguousarray(coords, float)
+            first, count = self.own_walkers()
+            mine = self.torch.from_numpy(self.sampler.problem.log_posterior(coords[first:first + count], raise_nan=True)).cuda()
+            full = self.torch.empty(self.nwalkers, dtype=self.torch.float64, device='cuda')
+            dist.all_gather_into_tensor(full, mine, group=self.group)
+            self.sampler._set_initial(State(coords, full.cpu().numpy(), None), True)
+        else:
+            self.sampler._set_initial(coords, True)
         if self.fused:
             self._quiesce()
+
+    def _even(self):
+        (b0, c0), (b1, c1) = self.own
+        return (b0, c0) == (b1, c1) and c0 * 2 * self.world == self.nwalkers
 
     def reserve(self, nsteps):
         check(lib().lcf_ensemble_reserve(self.sampler.handle, int(nsteps)))
 
-    def run(self, nsteps, store=False):
-        """``nsteps`` stretch-move iterations; one fused kernel + one all-gather per half-step."""
+    def run(self, nsteps, store=False, chain_out=None, log_prob_out=None):
+        """``nsteps`` stretch-move iterations.  Fused exchange: one C call for the whole run; ``chain_out``
+        [nsteps, own count, ndim] / ``log_prob_out`` [nsteps, own count] (page-locked) then receive this rank's walkers
+        step by step while the next steps are sampled.  NCCL exchange: one kernel + one all-gather per half-step."""
         L, h = lib(), self.sampler.handle
         if store:
             self.reserve(nsteps)
+        if self.fused and chain_out is not None:
+            from ._capi import dptr
+            first, count = self.own_walkers()
+            if chain_out.shape != (int(nsteps), count, self.ndim) or log_prob_out.shape != (int(nsteps), count):
+                raise ValueError('chain_out / log_prob_out must be [nsteps, own walkers(, ndim)]')
+            check(L.lcf_ensemble_run_to_host_slice(h, int(nsteps), first, count, dptr(chain_out), dptr(log_prob_out)))
+            self.sampler.iteration += int(nsteps)
+            return
         if self.fused:                       # compute + exchange are one kernel: the whole run is one C call
             check(L.lcf_ensemble_run(h, int(nsteps), 1 if store else 0))
             if store:
