@@ -1251,28 +1251,33 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     b->model = p0->dev.model;
     b->precision = p0->precision;
     b->seed = seed;
-    // shape: walkers per CTA pass = smallest power of two covering a half-ensemble (<= 32)
+    // shape: walkers per CTA pass = smallest power of two covering a half-ensemble: <= 32 (narrow groups), or 64..256
+    // ("wide" groups: wpb/32 walker columns of warps, one proposal phase for the whole half-ensemble) when the model
+    // has no per-walker weight table and the per-CTA tables still let four CTAs share an SM
     int l = 0;
     if (g_tune_wpb > 0) { while ((1 << l) < g_tune_wpb && l < 5) ++l; }
-    else { while ((1 << l) < b->n0 && l < 5) ++l; }
+    else { while ((1 << l) < b->n0 && l < 8) ++l; }
+    if (p0->dev.model == 3) l = std::min(l, 5);
     size_t smem = 0;
     int max_tiles = 1;
     for (;;) {
         smem = 0;
         for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 8));
-        if (smem <= kSmemMax / 2 || l == 0) break;
+        if (smem <= (l > 5 ? kSmemMax / 4 : kSmemMax / 2) || l == 0) break;
         --l;
     }
     std::vector<ProblemDev> hp(nproblems);
     std::vector<TileDev> ht(nproblems);
     for (long long i = 0; i < nproblems; ++i) {
-        if ((rc = build_tiles(b->probs[i], l))) { delete b; return rc; }
+        const int lt = std::min(l, 5);                   // wide groups use the 32-walker tiles (two points per lane)
+        if ((rc = build_tiles(b->probs[i], lt))) { delete b; return rc; }
         hp[i] = b->probs[i]->dev;
-        ht[i] = b->probs[i]->tiles[l];
+        ht[i] = b->probs[i]->tiles[lt];
         max_tiles = std::max(max_tiles, ht[i].ntiles);
     }
     int nw = g_tune_nw > 0 ? g_tune_nw : std::min(8, max_tiles);
     nw = std::max(1, std::min(nw, 8));                    // k_chain is compiled for <= 256 threads
+    if (l > 5) nw = 8;                                    // wide groups: 2^(l-5) walker columns of warps must divide nw
     smem = 0;
     for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw));
     if (smem > kSmemMax) { delete b; return fail(LCF_ERR_ARG, "filter bank does not fit in shared memory"); }

@@ -1032,7 +1032,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     LCF_TICK(2);
 
     // ---- phase 2: tiles (each lane: up to two points of the tile's filter) ----------------
-    const int wl = lane & (wpb - 1), slot = lane >> Mv.wpb_log2, ppt = 32 >> Mv.wpb_log2;
+    // narrow groups (wpb <= 32): lane = (walker, point slot).  Wide groups (wpb = 64..256, chain kernel): the warps form
+    // wpb/32 walker columns x nw/(wpb/32) tile stripes, so ONE proposal phase serves up to 256 walkers.
+    const int ncol = wpb > 32 ? wpb >> 5 : 1, col = warp % ncol, stripe = warp / ncol, nstripes = nw / ncol;
+    const int wl = wpb > 32 ? col * 32 + lane : lane & (wpb - 1);
+    const int slot = wpb > 32 ? 0 : lane >> Mv.wpb_log2, ppt = wpb > 32 ? 1 : 32 >> Mv.wpb_log2;
     const long long iw = g * wpb + wl;
     const bool skip = s_flag[wl] != 0;
     LaneWalker<R> lw;
@@ -1043,7 +1047,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const R2 *s_tabw = s_tab + wl;
     const int4 *tiles = TL.tiles;
     R chi = 0;
-    for (int tile = crank * nw + warp; tile < TL.ntiles; tile += nw * csize) {
+    for (int tile = crank * nstripes + stripe; tile < TL.ntiles; tile += nstripes * csize) {
         const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
         if (!skip && slot < tl.y) {
             const int pa = tl.x + slot;
@@ -1089,15 +1093,19 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // ---- phase 3: reduce, accept, write back ----------------------------------------------
     double chid = (double)chi;
     for (int off = 16; off >= wpb; off >>= 1) chid += __shfl_xor_sync(0xffffffffu, chid, off);
-    if (lane < wpb) s_part[warp * wpb + lane] = chid;
+    const int pw = wpb < 32 ? wpb : 32;                    // walkers per warp
+    if (lane < pw) s_part[warp * pw + lane] = chid;
     __syncthreads();
     LCF_TICK(4);
+    // partial sums of walker `tid`: over all warps (narrow) or over the stripes of its column (wide), in warp order
+    auto cta_total = [&](int w) {
+        double tot = 0.;
+        if (wpb > 32) { for (int st = 0; st < nstripes; ++st) tot += s_part[(st * ncol + (w >> 5)) * 32 + (w & 31)]; }
+        else { for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + w]; }
+        return tot;
+    };
     if (csize > 1) {                                       // partial sums of the cluster -> rank 0, in rank order
-        if (tid < wpb) {
-            double tot = 0.;
-            for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid];
-            dsmem_store_f64(&s_cpart[crank * wpb + tid], 0u, tot);
-        }
+        if (tid < wpb) dsmem_store_f64(&s_cpart[crank * wpb + tid], 0u, cta_total(tid));
         cluster_sync_all();
     }
     if (crank == 0 && tid < wpb) {
@@ -1108,7 +1116,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             if (!s_flag[tid]) {
                 double tot = 0.;
                 if (csize > 1) { for (int r = 0; r < csize; ++r) tot += s_cpart[r * wpb + tid]; }
-                else { for (int w2 = 0; w2 < nw; ++w2) tot += s_part[w2 * wpb + tid]; }
+                else tot = cta_total(tid);
                 nlp = lp + (-0.5 * (P.const_term + tot));
             }
             if (Mv.mode != MODE_MOVE) {
