@@ -709,3 +709,28 @@ def test_run_streams_chain_to_host_buffers():
     np.testing.assert_array_equal(b.get_chain(), ch)                 # the chain also stays on the device
     with pytest.raises(ValueError):
         b.run_mcmc(None, 3, chain_out=ch, log_prob_out=lp)            # wrong shape
+
+
+def test_stretch_move_with_cluster_split_matches_unsplit():
+    """The stretch move (proposal, accept, in-place update, chain write-back) under a thread-block-cluster split of the
+    walker groups gives the chain of the unsplit launch (FP64: the partial sums only differ in grouping)."""
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_sc3(npoints=120)
+    prob = wl.device_problem('fp64')
+    nw, nsteps = 40, 12
+    p0 = wl.start(nw, np.random.default_rng(21))
+    chains = {}
+    try:
+        for shape in ((8, 4, 1), (8, 4, 4), (2, 2, 8), (32, 8, 2)):
+            check(lib().lcf_set_tuning_ex(*shape))
+            s = EnsembleSampler(nw, wl.ndim, prob, seed=13)
+            s.run_mcmc(p0, nsteps)
+            chains[shape] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction)
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+    ref = chains[(8, 4, 1)]
+    assert 0.05 < ref[2].mean() < 0.95
+    for shape, (ch, lp, acc) in chains.items():
+        np.testing.assert_allclose(ch, ref[0], rtol=1e-9, err_msg=str(shape))
+        np.testing.assert_allclose(lp, ref[1], rtol=1e-9, err_msg=str(shape))
