@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 WALKERS_PER_GPU = 100_000
 NPOINTS = 2000
 MUFU_LANES_PER_CLK_SM = 16
+FP64_OPS_PER_SAMPLE = 17.75
 BALANCED_SAMPLES_PER_CLK_SM = 13.5    # FMA+MUFU balanced bound of the Planck-sample formulation
 SMS = 148
 
@@ -303,6 +304,9 @@ def run_ours(args):
     # Roofline: the XU (MUFU) pipe.  One MUFU.EX2 per Planck sample is irreducible (the reciprocal and everything else run
     # on the FMA pipe), and the pipe issues 16 lanes/clk/SM (measured: 15.7, profiles/r02_microbench_loops.txt).
     peak_samples = MUFU_LANES_PER_CLK_SM * SMS * sm_mhz * 1e6
+    fp64 = args.precision == 'fp64'
+    if fp64:        # FP64 mode has no MUFU for doubles: bound = FP64 pipe, 64 lanes/clk/SM over the loop's FP64 operations per sample
+        peak_samples = 64. / FP64_OPS_PER_SAMPLE * SMS * sm_mhz * 1e6
     balanced_samples = BALANCED_SAMPLES_PER_CLK_SM * SMS * sm_mhz * 1e6
     peaks = {}
     try:
@@ -312,13 +316,18 @@ def run_ours(args):
     chain_bytes_per_step = args.walkers * (D + 1) * 8
     hbm_gbs = chain_bytes_per_step * args.steps / (ms * 1e-3) / 1e9
     roofline = {
-        'bound': 'sfu (XU pipe: one MUFU.EX2 per Planck sample; no dense contraction, ~72 B of HBM per walker-step)',
+        'bound': ('fp64 pipe (no dense contraction, ~72 B of HBM per walker-step)' if fp64 else
+                  'sfu (XU pipe: one MUFU.EX2 per Planck sample; no dense contraction, ~72 B of HBM per walker-step)'),
         'kernel': 'lcf::k_pass<%d,%s>' % (3 if MODEL == 'sc3' else 4, 'float' if args.precision == 'fp32' else 'double'),
         'achieved': samples_per_s_gpu / 1e9, 'peak': peak_samples / 1e9, 'unit': 'GPlanck-samples/s',
         'frac': samples_per_s_gpu / peak_samples,
-        'peak_basis': '16 MUFU lanes/clk/SM x 148 SMs x %.0f MHz (SM clock measured during the timed region), 1 MUFU.EX2 per '
-                      'Planck sample; MEASURED_PEAKS.json has no SFU entry, the pipe rate is confirmed by '
-                      'tools/microbench/loops.cu (15.7 lanes/clk/SM)' % sm_mhz,
+        'peak_basis': (('64 FP64 lanes/clk/SM / %.2f FP64 operations per Planck sample of the shipped loop (table exp2 7 + range '
+                        'reduction 3 + x 1 + minus-one 1 + quad-shared reciprocal and sums 5.75) x 148 SMs x %.0f MHz; '
+                        'MEASURED_PEAKS.json has no FP64 entry (tools/microbench/pipes.cu: DFMA 57 lanes/clk/SM)'
+                        % (FP64_OPS_PER_SAMPLE, sm_mhz)) if fp64 else
+                       ('16 MUFU lanes/clk/SM x 148 SMs x %.0f MHz (SM clock measured during the timed region), 1 MUFU.EX2 per '
+                        'Planck sample; MEASURED_PEAKS.json has no SFU entry, the pipe rate is confirmed by '
+                        'tools/microbench/loops.cu (15.7 lanes/clk/SM)' % sm_mhz)),
         'samples_per_clk_sm': samples_per_s_gpu / (SMS * sm_mhz * 1e6),
         'frac_vs_survey_balanced_bound': samples_per_s_gpu / balanced_samples,
         'survey_balanced_bound': '13.5 samples/clk/SM (SURVEY.md 8(d))',
