@@ -567,6 +567,7 @@ __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, 
                                                 const double2 *__restrict__ tab, const double *__restrict__ e2t, double &SA, double &SB) {
     constexpr int ts = kTabStride;
     double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
+#pragma unroll 2                                         // eight independent exp2 chains per lane: the FP64 pipe's latency needs them at 16 warps/SM
     for (const double4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
         const double4 s = *pb;
         double w0 = s.z, w1 = s.w;
