@@ -1,17 +1,22 @@
 // lcf_device.cuh -- device code of the fused log-posterior + stretch-move kernels (sm_100a).
 //
 // Work decomposition:
-//   CTA      = one group of WPB walkers of the active half-ensemble (WPB = 2^k <= 32)
+//   CTA      = one group of WPB walkers of the active half-ensemble (WPB = 2^k <= 32; the chain kernel also runs
+//              "wide" groups of 64..256 walkers: WPB/32 walker columns of warps); a thread-block cluster of S CTAs
+//              can share one group and split its light curve (partials to rank 0 through DSMEM)
 //   lane     = (walker-in-group wl = lane % WPB, point slot = lane / WPB); a lane serves the
 //              SAME walker for the whole kernel, so the per-walker model constants live in
 //              registers and the chi-square partial sums need no atomics
-//   tile     = 32/WPB photometry points that share one filter (points are grouped by filter
-//              on the host), so every lane of a warp walks the same transmission curve and the
-//              shared-memory reads of (alpha_k, w_k) are pure broadcasts
+//   tile     = 2 * 32/WPB photometry points that share one filter (points are grouped by filter
+//              on the host), two per lane, so every lane of a warp walks the same transmission curve and the
+//              shared-memory reads of (a_k, w_k) are pure broadcasts
 //   warp     = strides over the tiles of the light curve
 // The packed filter bank is staged into shared memory once per CTA with a 1-D TMA bulk copy
-// (cp.async.bulk + mbarrier).  Inner loop per Planck sample (FP32 mode):
-//   FMUL x=a_k*invT ; MUFU.EX2 ; FADD -1 ; MUFU.RCP ; FFMA acc+=w_k*r
+// (cp.async.bulk + mbarrier).  Inner loop per quad of Planck samples (two points x two samples, FP32 mode):
+//   FMUL2 x = a_k invT ; MUFU.EX2 x4 ; FADD2 -1 ; products ; Newton reciprocal on the FMA pipe (packed) ; FFMA2 sums
+// -- one MUFU per sample, everything else off the XU pipe (section "FP32 fast paths" below).
+// Multi-GPU: the accept epilogue stores accepted walkers into the peers' replicas (NVLink peer memory) and half-steps
+// are ordered by device-side flags (peers_wait / peers_publish).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
