@@ -68,6 +68,27 @@ template <typename T> int upload(const std::vector<T> &h, void **d) {
     return 0;
 }
 
+// All device arrays of one problem live in ONE allocation filled by ONE copy: survey batches create 10^4 problems, and ten
+// cudaMalloc + cudaMemcpy pairs each were most of the host time per light curve.
+struct Arena {
+    std::vector<unsigned char> host;
+    std::vector<std::pair<const void **, size_t>> slots;        // pointer field to patch, offset
+    template <typename T> void add(const std::vector<T> &v, const void **slot) {
+        size_t off = (host.size() + 255) & ~(size_t)255;
+        host.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+        if (!v.empty()) memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+        slots.push_back({slot, off});
+    }
+    int commit(std::vector<void *> &allocs) {
+        void *d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, std::max<size_t>(host.size(), 16)));
+        allocs.push_back(d);
+        CUDA_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+        for (auto &s : slots) *s.first = reinterpret_cast<const unsigned char *>(d) + s.second;
+        return 0;
+    }
+};
+
 int model_nparams(int model) {
     switch (model) {
         case 1: return 5;
@@ -366,7 +387,7 @@ int check_device() {
 }
 
 template <typename R>
-int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale) {
+int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale, Arena &arena) {
     const int F = d->nfilters, N = d->npoints;
     // every filter padded to an even number of samples (pad: a = last a, w = 0): the kernels consume sample
     // pairs and the TMA bulk copy moves multiples of 16 bytes
@@ -412,13 +433,11 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
         }
         obs[i].w = (R)0;
     }
-    void *dp;
-    int rc;
     ProblemDev &P = p->dev;
-    if ((rc = upload(bank, &dp))) return rc;  p->allocs.push_back(dp); P.bank = dp;
-    if ((rc = upload(kap, &dp))) return rc;   p->allocs.push_back(dp); P.kappa = dp;
-    if ((rc = upload(finfo, &dp))) return rc; p->allocs.push_back(dp); P.finfo = reinterpret_cast<const int4 *>(dp);
-    if ((rc = upload(obs, &dp))) return rc;   p->allocs.push_back(dp); P.obs = dp;
+    arena.add(bank, &P.bank);
+    arena.add(kap, &P.kappa);
+    arena.add(finfo, reinterpret_cast<const void **>(&P.finfo));
+    arena.add(obs, &P.obs);
     P.nsamples = ns_pad;
     if (d->sifto_coef && d->sifto_nknots >= 2) {
         const int nint = d->sifto_nknots - 1;
@@ -430,9 +449,7 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
             spl[i].z = (R)(d->sifto_coef[4 * i + 2] / scale);
             spl[i].w = (R)(d->sifto_coef[4 * i + 3] / scale);
         }
-        if ((rc = upload(spl, &dp))) return rc;
-        p->allocs.push_back(dp);
-        P.spl = dp;
+        arena.add(spl, &P.spl);
         P.spl_nint = nint;
         P.spl_x0 = d->sifto_x0;
         P.spl_dx = d->sifto_dx;
@@ -576,14 +593,12 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
     P.const_term = ct;
     p->h_point_filter.assign(d->point_filter, d->point_filter + d->npoints);
 
-    void *dp;
+    Arena arena;
     std::vector<int> role(d->nfilters, 0);
     if (d->filter_role) role.assign(d->filter_role, d->filter_role + d->nfilters);
     std::vector<double> t(d->t, d->t + d->npoints);
-    if ((rc = upload(role, &dp))) { delete p; return rc; }
-    p->allocs.push_back(dp); P.frole = reinterpret_cast<const int *>(dp);
-    if ((rc = upload(t, &dp))) { delete p; return rc; }
-    p->allocs.push_back(dp); P.t = reinterpret_cast<const double *>(dp);
+    arena.add(role, reinterpret_cast<const void **>(&P.frole));
+    arena.add(t, reinterpret_cast<const void **>(&P.t));
     {   // FP32 epochs: t - tref as hi + lo floats (see LaneWalker<float>), tref = first finite epoch
         P.tref = 0.;
         for (int i = 0; i < d->npoints; ++i) if (std::isfinite(d->t[i])) { P.tref = d->t[i]; break; }
@@ -593,15 +608,14 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
             t32[i].x = (float)r;
             t32[i].y = (float)(r - (double)t32[i].x);
         }
-        if ((rc = upload(t32, &dp))) { delete p; return rc; }
-        p->allocs.push_back(dp); P.t32 = reinterpret_cast<const float2 *>(dp);
-        if ((rc = upload(p->h_point_filter, &dp))) { delete p; return rc; }
-        p->allocs.push_back(dp); P.pfilt = reinterpret_cast<const int *>(dp);
+        arena.add(t32, reinterpret_cast<const void **>(&P.t32));
+        arena.add(p->h_point_filter, reinterpret_cast<const void **>(&P.pfilt));
         double sk = 0.;
         for (int i = 0; i < d->npoints; ++i) sk += d->bank_offsets[d->point_filter[i] + 1] - d->bank_offsets[d->point_filter[i]];
         p->mean_samples = sk / d->npoints;
     }
-    rc = (d->precision == LCF_PRECISION_FP32) ? build_problem_arrays<float>(d, p, scale) : build_problem_arrays<double>(d, p, scale);
+    rc = (d->precision == LCF_PRECISION_FP32) ? build_problem_arrays<float>(d, p, scale, arena) : build_problem_arrays<double>(d, p, scale, arena);
+    if (!rc) rc = arena.commit(p->allocs);
     if (rc) { delete p; return rc; }
     *out = p;
     return 0;
