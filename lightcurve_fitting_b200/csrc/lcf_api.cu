@@ -363,13 +363,22 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     cfg.blockDim = dim3((unsigned)(sh.nw * 32), 1, 1);
     cfg.dynamicSmemBytes = sh.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)sh.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (!getenv("LCF_NO_PDL")) {           // overlap this launch with the tail of the previous kernel (griddepcontrol.wait in k_pass)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (sh.cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)sh.cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = sh.cluster > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], mv));
     if (launches) ++*launches;
     return 0;

@@ -1172,6 +1172,10 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
     __syncthreads();
+    // Programmatic dependent launch: this grid may have been scheduled while the previous half-step was still running
+    // (its launch latency and the prologue above are hidden); nothing the previous kernel wrote is read before this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
     const long long nclusters = cluster_count_x();
