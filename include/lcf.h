@@ -223,6 +223,14 @@ int  lcf_batch_get_accepted(lcf_batch *b, int64_t *accepted /* [nproblems][nwalk
 int  lcf_batch_get_status(lcf_batch *b, int32_t *status /* [nproblems]: 0 ok, LCF_ERR_NAN */);
 int  lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches);
 
+/* Batched box-bounded least-squares fits of planck_fast(nu; T, R) to SEDs, one thread per epoch (replaces the per-epoch
+   scipy.optimize.curve_fit of bolometric.py:483-531).  offsets[nepochs+1] delimit each epoch's points in nu [THz, already
+   multiplied by (1+z)] and lum; c1, c2 are the constants of models.py:1101-1102; p0/lower/upper are (T, R).
+   popt [nepochs][2], pcov [nepochs][2][2] (curve_fit's (J^T J)^-1 RSS/(n-2); inf when n <= 2), status 0 = converged.   */
+int  lcf_blackbody_lstsq_batch(int64_t nepochs, const int32_t *offsets, const double *nu, const double *lum, double c1, double c2,
+                               double cutoff_freq, const double *p0, const double *lower, const double *upper, double *popt,
+                               double *pcov, int32_t *status);
+
 /* launch-shape overrides for tuning (0 = heuristic): walkers per CTA (power of two <= 32)
    and warps per CTA.                                                                       */
 int  lcf_set_tuning(int walkers_per_cta, int warps_per_cta);

@@ -1,7 +1,7 @@
 """Bolometric light curves from batched per-epoch blackbody MCMC fits -- drop-ins for the MCMC branch of the
 reference's ``bolometric.py`` (``spectrum_mcmc`` :87-190, ``calculate_bolometric`` :648-832, ``pseudo`` :32-59,
 ``stefan_boltzmann`` :422-453, ``median_and_unc`` :456-480, ``group_by_epoch`` :383-416, ``blackbody_lstsq``
-:483-531, ``integrate_sed`` :537-557, ``calc_colors`` :560-607).
+:483-531 (here a batched device kernel, ``blackbody_lstsq_batch``), ``integrate_sed`` :537-557, ``calc_colors`` :560-607).
 
 B200 design: the reference loops over epochs serially, creating one emcee sampler per epoch.  Here every
 epoch becomes one independent ensemble and ALL epochs run in a single kernel launch (one CTA per epoch, the
@@ -90,36 +90,47 @@ def group_by_epoch(lc, res=1., also_group_by=()):
     return [groups[i] for i in np.argsort(mjdavg, kind='stable')]
 
 
-def blackbody_lstsq(epoch1, z, p0=None, T_range=(1., 100.), R_range=(0.01, 1000.), cutoff_freq=np.inf):
-    """Chi-square blackbody fit at the effective frequencies (bolometric.py:483-531).
+def blackbody_lstsq_batch(epochs, z, p0=None, T_range=(1., 100.), R_range=(0.01, 1000.), cutoff_freq=np.inf):
+    """Chi-square blackbody fits of MANY single-epoch SEDs in one kernel launch (one thread per epoch).
 
-    ``scipy.optimize.curve_fit`` drives the optimisation on the host; every model evaluation is one launch of the
-    Planck kernel on a persistent device problem.
+    Same model, bounds, starting point and covariance as the reference's per-epoch ``curve_fit`` call
+    (bolometric.py:483-531).  Returns arrays ``temp, radius, dtemp, drad, lum, dlum, L_opt, status`` of length
+    ``len(epochs)``; ``status != 0`` marks an epoch whose fit did not converge (the reference catches the
+    ``RuntimeError`` curve_fit raises in that case and stores NaN).
     """
-    from scipy.optimize import curve_fit, OptimizeWarning
     if p0 is None:
         p0 = [10., 10.]
-    nu = np.asarray(epoch1['freq'].data, float) * (1. + z)
-    n = len(nu)
-    alpha = np.repeat(K.c1 * nu, 2)
-    w = np.zeros(2 * n)
-    w[0::2] = K.c2 * nu ** 3 * np.minimum(1., cutoff_freq / nu)
-    bank = (np.arange(0, 2 * n + 1, 2, dtype=np.int32), alpha, w, np.zeros(2 * n))
-    prob = DeviceProblem(MODEL_IDS['BlackbodySED'], np.zeros(n), np.arange(n), np.ones(n), np.ones(n), ndim=2, bank=bank)
+    n = len(epochs)
+    off = np.zeros(n + 1, np.int32)
+    nus, lums = [], []
+    for i, e in enumerate(epochs):
+        nus.append(np.asarray(e['freq'].data, float) * (1. + z))
+        lums.append(np.asarray(e['lum'].data, float))
+        off[i + 1] = off[i] + len(nus[-1])
+    nu = np.ascontiguousarray(np.concatenate(nus)) if n else np.zeros(0)
+    lum_obs = np.ascontiguousarray(np.concatenate(lums)) if n else np.zeros(0)
+    popt, pcov = np.empty((n, 2)), np.empty((n, 2, 2))
+    status = np.zeros(n, np.int32)
+    lo = np.array([T_range[0], R_range[0]], float)
+    hi = np.array([T_range[1], R_range[1]], float)
+    if n:
+        check(lib().lcf_blackbody_lstsq_batch(n, off.ctypes.data_as(C.POINTER(C.c_int32)), dptr(nu), dptr(lum_obs), K.c1, K.c2,
+                                              float(cutoff_freq), dptr(np.asarray(p0, float)), dptr(lo), dptr(hi), dptr(popt),
+                                              dptr(pcov), status.ctypes.data_as(C.POINTER(C.c_int32))))
+    temp, radius = popt[:, 0].copy(), popt[:, 1].copy()
+    with np.errstate(invalid='ignore'):
+        dtemp, drad = np.sqrt(pcov[:, 0, 0]), np.sqrt(pcov[:, 1, 1])
+        lum, dlum = stefan_boltzmann(temp, radius, dtemp, drad, pcov[:, 0, 1])
+    L_opt = pseudo(temp, radius, z, cutoff_freq=cutoff_freq) if n else np.zeros(0)
+    return temp, radius, dtemp, drad, lum, dlum, L_opt, status
 
-    def planck_cutoff(_nu, T, R):
-        return prob.model_eval(np.array([[T, R]]))[0]
 
-    with warnings.catch_warnings():
-        if len(epoch1) <= 2:
-            warnings.simplefilter('ignore', OptimizeWarning)
-        p0, cov = curve_fit(planck_cutoff, nu, np.asarray(epoch1['lum'].data, float), p0=p0,
-                            bounds=([T_range[0], R_range[0]], [T_range[1], R_range[1]]))
-    temp, radius = p0
-    dtemp, drad = np.sqrt(np.diag(cov))
-    lum, dlum = stefan_boltzmann(temp, radius, dtemp, drad, cov[0, 1])
-    L_opt = pseudo(temp, radius, z, cutoff_freq=cutoff_freq)
-    return temp, radius, dtemp, drad, lum, dlum, L_opt
+def blackbody_lstsq(epoch1, z, p0=None, T_range=(1., 100.), R_range=(0.01, 1000.), cutoff_freq=np.inf):
+    """Chi-square blackbody fit at the effective frequencies (bolometric.py:483-531): a batch of one."""
+    temp, radius, dtemp, drad, lum, dlum, L_opt, status = blackbody_lstsq_batch([epoch1], z, p0, T_range, R_range, cutoff_freq)
+    if status[0]:
+        raise RuntimeError('Optimal parameters not found: the least-squares fit did not converge')   # what curve_fit raises
+    return temp[0], radius[0], dtemp[0], drad[0], lum[0], dlum[0], L_opt[0]
 
 
 def integrate_sed(epoch1):
@@ -303,27 +314,31 @@ def calculate_bolometric(lc, z=0., outpath='.', res=1., nwalkers=10, burnin_step
         nfilt = len(filts)
         if nfilt < min_nfilt or nfilt <= 1:
             continue                        # single-filter epochs need the KDE prior (bolometric.py:753-759)
-        p0 = np.array([10., 10.])
         mjdavg, dmjd0, dmjd1 = median_and_unc(epoch1['MJD'].data, 100.)
         filtstr = ''.join([f.char for f in sorted(filts)])
-        T_range = (priors[0].p_min, priors[0].p_max)
-        R_range = (priors[1].p_min, priors[1].p_max)
-        try:
-            temp, radius, dtemp, drad, L_bol, dL_bol, L = blackbody_lstsq(epoch1, z, p0, T_range, R_range, cutoff_freq)
-            p0 = np.array([temp, radius])
-        except RuntimeError:
-            temp = radius = dtemp = drad = L_bol = dL_bol = L = np.nan
+        L_int = integrate_sed(epoch1)
+        color_mags, color_dmags, color_lolims, color_uplims = calc_colors(epoch1, colors)
+        rows.append(dict(MJD=mjdavg, dMJD0=dmjd0, dMJD1=dmjd1, L_int=L_int, npoints=nfilt, filts=filtstr,
+                         colors=(color_mags, color_dmags, color_lolims, color_uplims),
+                         source=epoch1['source'][0] if use_src and 'source' in epoch1.colnames else None))
+        epochs.append(epoch1)
+
+    # least-squares blackbody of every epoch in ONE launch (the reference: one curve_fit per epoch, bolometric.py:768)
+    T_range = (priors[0].p_min, priors[0].p_max)
+    R_range = (priors[1].p_min, priors[1].p_max)
+    temp, radius, dtemp, drad, L_bol, dL_bol, L, fit_status = blackbody_lstsq_batch(epochs, z, [10., 10.], T_range, R_range,
+                                                                                    cutoff_freq)
+    for i, row in enumerate(rows):
+        p0 = np.array([10., 10.])
+        if fit_status[i]:                                  # bolometric.py:769-770: RuntimeError -> NaN, default start
+            row.update(temp=np.nan, radius=np.nan, dtemp=np.nan, dradius=np.nan, L_bol=np.nan, dL_bol=np.nan, L=np.nan)
+        else:
+            row.update(temp=temp[i], radius=radius[i], dtemp=dtemp[i], dradius=drad[i], L_bol=L_bol[i], dL_bol=dL_bol[i], L=L[i])
+            p0 = np.array([temp[i], radius[i]])
         sg = rng.normal(size=(nwalkers, 2)) + p0
         sg[sg <= 0.] = 1.
         if use_sigma:
             sg = np.append(sg, np.abs(rng.normal(size=(nwalkers, 1))), axis=1)
-        L_int = integrate_sed(epoch1)
-        color_mags, color_dmags, color_lolims, color_uplims = calc_colors(epoch1, colors)
-        rows.append(dict(MJD=mjdavg, dMJD0=dmjd0, dMJD1=dmjd1, temp=temp, radius=radius, dtemp=dtemp, dradius=drad,
-                         L_bol=L_bol, dL_bol=dL_bol, L=L, L_int=L_int, npoints=nfilt, filts=filtstr,
-                         colors=(color_mags, color_dmags, color_lolims, color_uplims),
-                         source=epoch1['source'][0] if use_src and 'source' in epoch1.colnames else None))
-        epochs.append(epoch1)
         guesses.append(sg)
 
     mc_cols = ['temp_mcmc', 'radius_mcmc', 'dtemp_mcmc0', 'dtemp_mcmc1', 'dradius_mcmc0', 'dradius_mcmc1',

@@ -1212,6 +1212,39 @@ int lcf_ensemble_diagnostics(lcf_ensemble *e, int64_t discard, double c, int64_t
     return 0;
 }
 
+// ---- batched blackbody least squares (replaces the per-epoch scipy curve_fit of bolometric.py:483-531) ----
+int lcf_blackbody_lstsq_batch(int64_t nepochs, const int32_t *offsets, const double *nu, const double *lum, double c1, double c2,
+                              double cutoff_freq, const double *p0, const double *lower, const double *upper, double *popt,
+                              double *pcov, int32_t *status) {
+    if (!offsets || !nu || !lum || !p0 || !lower || !upper || !popt || !pcov || !status) return fail(LCF_ERR_ARG, "null argument");
+    if (nepochs <= 0) return 0;
+    int rc = check_device();
+    if (rc) return rc;
+    const long long npts = offsets[nepochs];
+    for (long long e = 0; e < nepochs; ++e)
+        if (offsets[e + 1] < offsets[e] + 1) return fail(LCF_ERR_ARG, "epoch %lld has no photometry point", e);
+    int *d_off = nullptr, *d_st = nullptr;
+    double *d_nu = nullptr, *d_lum = nullptr, *d_p = nullptr, *d_c = nullptr;
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; return ce == cudaSuccess; };
+    ok(cudaMalloc(&d_off, sizeof(int) * (nepochs + 1))) && ok(cudaMalloc(&d_st, sizeof(int) * nepochs)) &&
+        ok(cudaMalloc(&d_nu, sizeof(double) * npts)) && ok(cudaMalloc(&d_lum, sizeof(double) * npts)) &&
+        ok(cudaMalloc(&d_p, sizeof(double) * 2 * nepochs)) && ok(cudaMalloc(&d_c, sizeof(double) * 4 * nepochs)) &&
+        ok(cudaMemcpy(d_off, offsets, sizeof(int) * (nepochs + 1), cudaMemcpyHostToDevice)) &&
+        ok(cudaMemcpy(d_nu, nu, sizeof(double) * npts, cudaMemcpyHostToDevice)) &&
+        ok(cudaMemcpy(d_lum, lum, sizeof(double) * npts, cudaMemcpyHostToDevice));
+    if (ce == cudaSuccess) {
+        k_bb_lstsq<<<(unsigned)((nepochs + 63) / 64), 64>>>(nepochs, d_off, d_nu, d_lum, c1, c2, cutoff_freq, p0[0], p0[1], lower[0],
+                                                            upper[0], lower[1], upper[1], d_p, d_c, d_st);
+        ok(cudaGetLastError()) && ok(cudaMemcpy(popt, d_p, sizeof(double) * 2 * nepochs, cudaMemcpyDeviceToHost)) &&
+            ok(cudaMemcpy(pcov, d_c, sizeof(double) * 4 * nepochs, cudaMemcpyDeviceToHost)) &&
+            ok(cudaMemcpy(status, d_st, sizeof(int) * nepochs, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_off); cudaFree(d_st); cudaFree(d_nu); cudaFree(d_lum); cudaFree(d_p); cudaFree(d_c);
+    if (ce != cudaSuccess) return fail(LCF_ERR_CUDA, "blackbody least squares failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 int lcf_ensemble_device_view(lcf_ensemble *e, void **d_coords, void **d_log_prob, void **stream, int64_t *n0, int64_t *own_begin,
                              int64_t *own_count) {
     if (!e) return fail(LCF_ERR_ARG, "null argument");

@@ -610,8 +610,14 @@ def pseudo(temp, radius, z, filter0=None, filter1=None, cutoff_freq=np.inf):
     return _trapz(y_optical) * 1e12
 
 
-def stefan_boltzmann(temp, radius):
-    return 4 * np.pi * radius ** 2 * sigma_sb * temp ** 4
+def stefan_boltzmann(temp, radius, dtemp=None, drad=None, covTR=None):   # bolometric.py:422-453
+    lum = 4 * np.pi * radius ** 2 * sigma_sb * temp ** 4
+    if dtemp is None or drad is None or covTR is None:
+        return lum
+    dlum = 8 * np.pi * sigma_sb * (radius ** 2 * temp ** 8 * drad ** 2
+                                   + 4 * radius ** 4 * temp ** 6 * dtemp ** 2
+                                   + 4 * radius ** 3 * temp ** 7 * covTR) ** 0.5
+    return lum, dlum
 
 
 def median_and_unc(x, perc_contained=68.):
@@ -676,3 +682,26 @@ def split_rhat(x):
     wv = halves.var(axis=0, ddof=1).mean(axis=0)
     b_over_h = means.var(axis=0, ddof=1)
     return np.sqrt(((h - 1) / h * wv + b_over_h) / wv)
+
+
+def blackbody_lstsq(freq, lum, z, p0=None, T_range=(1., 100.), R_range=(0.01, 1000.), cutoff_freq=np.inf):
+    """Chi-square blackbody fit of one SED with scipy's curve_fit, as bolometric.py:483-531 does it (``freq``/``lum`` are
+    the epoch's ``freq`` and ``lum`` columns).  Returns (temp, radius, dtemp, drad, lum, dlum, L_opt)."""
+    import warnings
+    from scipy.optimize import curve_fit, OptimizeWarning
+    if p0 is None:
+        p0 = [10., 10.]
+
+    def planck_cutoff(nu, T, R):
+        return planck_fast(nu, T, R, cutoff_freq)
+
+    with warnings.catch_warnings():
+        if len(freq) <= 2:
+            warnings.simplefilter('ignore', OptimizeWarning)
+        p0, cov = curve_fit(planck_cutoff, np.asarray(freq, float) * (1. + z), np.asarray(lum, float), p0=p0,
+                            bounds=([T_range[0], R_range[0]], [T_range[1], R_range[1]]))
+    temp, radius = p0
+    dtemp, drad = np.sqrt(np.diag(cov))
+    lum_bb, dlum = stefan_boltzmann(temp, radius, dtemp, drad, cov[0, 1])
+    L_opt = pseudo(temp, radius, z, cutoff_freq=cutoff_freq)
+    return temp, radius, dtemp, drad, lum_bb, dlum, L_opt

@@ -734,3 +734,44 @@ def test_stretch_move_with_cluster_split_matches_unsplit():
     for shape, (ch, lp, acc) in chains.items():
         np.testing.assert_allclose(ch, ref[0], rtol=1e-9, err_msg=str(shape))
         np.testing.assert_allclose(lp, ref[1], rtol=1e-9, err_msg=str(shape))
+
+
+def test_batched_blackbody_lstsq_matches_curve_fit():
+    """The device's batched bounded Levenberg-Marquardt fits == the reference's per-epoch scipy curve_fit
+    (bolometric.py:483-531) to curve_fit's own tolerance: interior optima, optima on the temperature bound, modified
+    blackbodies (cutoff), two-point SEDs (covariance undefined -> inf, like curve_fit)."""
+    import warnings
+    from lightcurve_fitting_b200 import bolometric as B
+    from lightcurve_fitting_b200.filters import filtdict
+    from lightcurve_fitting_b200.lightcurve import LC
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(12)
+    names = ['U', 'B', 'V', 'R', 'I', 'g', 'r', 'i', 'UVW1', 'z']
+    for cutoff in (np.inf, 900.):
+        epochs, truths = [], []
+        for k in range(60):
+            n = int(rng.integers(2, 9))
+            fl = [filtdict[x] for x in rng.choice(names, n, replace=False)]
+            freq = np.array([f.freq_eff for f in fl])
+            T = rng.uniform(4., 60.) if k % 5 else rng.uniform(80., 300.)        # every fifth hotter than the 100 kK bound
+            R = 10. ** rng.uniform(0., 1.5)
+            lum = rp.planck_fast(freq * 1.003, T, R, cutoff) * (1. + 0.05 * rng.normal(size=n))
+            e = LC({'freq': freq, 'lum': lum})
+            epochs.append(e)
+        temp, radius, dtemp, drad, L, dL, Lopt, status = B.blackbody_lstsq_batch(epochs, 0.003, cutoff_freq=cutoff)
+        assert np.all(status == 0)
+        nbound = 0
+        for i, e in enumerate(epochs):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                want = rp.blackbody_lstsq(e['freq'].data, e['lum'].data, 0.003, cutoff_freq=cutoff)
+            np.testing.assert_allclose([temp[i], radius[i]], want[:2], rtol=1e-5, err_msg='epoch %d' % i)
+            np.testing.assert_allclose([L[i], Lopt[i]], [want[4], want[6]], rtol=1e-4)
+            if len(e) > 2:
+                np.testing.assert_allclose([dtemp[i], drad[i], dL[i]], [want[2], want[3], want[5]], rtol=1e-3)
+            else:
+                assert np.isinf(dtemp[i]) and np.isinf(want[2])
+            nbound += temp[i] > 99.999
+        assert nbound >= 3
+    one = B.blackbody_lstsq(epochs[0], 0.003, cutoff_freq=900.)
+    np.testing.assert_allclose(one, [temp[0], radius[0], dtemp[0], drad[0], L[0], dL[0], Lopt[0]], rtol=1e-12)
