@@ -8,6 +8,8 @@
 #include "lcf_device.cuh"
 #include "lcf_diag.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, free otherwise
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -20,6 +22,11 @@
 using namespace lcf;
 
 namespace {
+
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 int g_tune_wpb = 0, g_tune_nw = 0, g_tune_cluster = 0;
@@ -634,6 +641,7 @@ void lcf_problem_destroy(lcf_problem *p) { delete p; }
 
 static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, const double *params, double *out, size_t out_per_set,
                        long long *nan_count) {
+    NvtxRange r("lcf_eval");
     if (!p || !params || !out) return fail(LCF_ERR_ARG, "null argument");
     if (nsets <= 0) return 0;
     int rc = check_device();
@@ -955,6 +963,7 @@ int lcf_ensemble_end_step(lcf_ensemble *e, int store) {
 }
 
 int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
+    NvtxRange r("lcf_ensemble_run");
     if (!e) return fail(LCF_ERR_ARG, "null argument");
     if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
     CUDA_TRY(cudaSetDevice(e->p->device));
@@ -987,6 +996,7 @@ int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
 // also stays in HBM (lcf_ensemble_get_chain, diagnostics).  chain_host [nsteps][nwalkers][ndim], log_prob_host [nsteps][nwalkers].
 int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t first, int64_t count, double *chain_host,
                                    double *log_prob_host) {
+    NvtxRange r("lcf_ensemble_run_to_host");
     if (!e || !chain_host || !log_prob_host) return fail(LCF_ERR_ARG, "null argument");
     if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
     if (first < 0 || count < 0 || first + count > e->W) return fail(LCF_ERR_ARG, "walker range out of bounds");
@@ -1392,6 +1402,7 @@ int lcf_batch_set_state(lcf_batch *b, const double *coords) {
 }
 
 int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
+    NvtxRange r("lcf_batch_run");
     if (!b) return fail(LCF_ERR_ARG, "null argument");
     if (!b->has_state) return fail(LCF_ERR_STATE, "batch has no initial state");
     if (nburn < 0 || nsteps < 0) return fail(LCF_ERR_ARG, "negative step count");
