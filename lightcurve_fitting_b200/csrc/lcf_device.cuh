@@ -1209,8 +1209,11 @@ struct BatchDev {
 };
 
 // at most 8 warps per CTA; FP32: 64 registers so that four CTAs (32 warps) share an SM, as in k_pass
+#ifndef LCF_CHAIN_MINBLOCKS
+#define LCF_CHAIN_MINBLOCKS 4
+#endif
 template <int MODEL, typename R>
-__global__ void __launch_bounds__(256, (sizeof(R) == 4 ? 4 : 2)) k_chain(const BatchDev B) {
+__global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2)) k_chain(const BatchDev B) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ProblemDev sP;
     __shared__ TileDev sT;
