@@ -205,20 +205,20 @@ typedef void (*ChainKernel)(const BatchDev);
 // LCF_DEV_ONLY_MODEL=<id> (tools/microbench builds): instantiate the FP32 half-step kernel of one model only, so that a
 // kernel experiment compiles in seconds.  Never defined for the shipped library.
 #ifdef LCF_DEV_ONLY_MODEL
-template <typename R> PassKernel pass_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_pass<LCF_DEV_ONLY_MODEL, R> : nullptr; }
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1) {
+    if (model != LCF_DEV_ONLY_MODEL) return nullptr;
+    return l == 5 ? k_pass<LCF_DEV_ONLY_MODEL, R, 5> : k_pass<LCF_DEV_ONLY_MODEL, R, -1>;
+}
 template <typename R> ChainKernel chain_kernel_for(int) { return nullptr; }
 #else
-template <typename R> PassKernel pass_kernel_for(int model) {
+// l = walkers-per-CTA exponent of the launch: 5 (32 walkers, every large ensemble) has its own instantiation
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1) {
+#define LCF_PASS_CASE(M) case M: return l == 5 ? k_pass<M, R, 5> : k_pass<M, R, -1>;
     switch (model) {
-        case 1: return k_pass<1, R>;
-        case 2: return k_pass<2, R>;
-        case 3: return k_pass<3, R>;
-        case 4: return k_pass<4, R>;
-        case 5: return k_pass<5, R>;
-        case 6: return k_pass<6, R>;
-        case 7: return k_pass<7, R>;
-        case 8: return k_pass<8, R>;
+        LCF_PASS_CASE(1) LCF_PASS_CASE(2) LCF_PASS_CASE(3) LCF_PASS_CASE(4)
+        LCF_PASS_CASE(5) LCF_PASS_CASE(6) LCF_PASS_CASE(7) LCF_PASS_CASE(8)
     }
+#undef LCF_PASS_CASE
     return nullptr;
 }
 template <typename R> ChainKernel chain_kernel_for(int model) {
@@ -342,7 +342,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     }
     int rc = build_tiles(p, bs.l);
     if (rc) return rc;
-    PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
+    PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l) : pass_kernel_for<double>(p->dev.model, bs.l);
     if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
     if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
@@ -361,7 +361,7 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     int rc = choose_shape(p, mv.Ns, &sh);
     if (rc) return rc;
     mv.wpb_log2 = sh.l;
-    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model) : pass_kernel_for<double>(p->dev.model);
+    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l) : pass_kernel_for<double>(p->dev.model, sh.l);
     const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
     const long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
     cudaLaunchConfig_t cfg;

@@ -899,12 +899,15 @@ template <typename R> struct SmemLayout {
 // and dedicated front-end producer warps feeding the loop warps through an mbarrier ring, were both slower: the XU
 // pipe is fed best by 32 resident warps that ALL spend their time in the dense inner loop.)
 // ---------------------------------------------------------------------------------------
-template <int MODEL, typename R>
+// WL >= 0: walkers-per-CTA exponent known at compile time (k_pass instantiates WL = 5, the shape of every large ensemble:
+// the lane arithmetic slot / ppt / wl and the tile guards fold to constants); WL = -1: read from Mv.wpb_log2.
+template <int MODEL, typename R, int WL = -1>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
                                            unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize) {
     typedef typename Vec2<R>::type R2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const int wpb = 1 << Mv.wpb_log2;
+    const int wl2 = WL >= 0 ? WL : Mv.wpb_log2;
+    const int wpb = 1 << wl2;
     const int D = P.ndim;
     typedef typename Vec4<R>::type R4;
     R4 *s_bank = reinterpret_cast<R4 *>(smem + L.off_bank);
@@ -978,7 +981,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     {
         const int per = NT + D + 2;
         for (int idx = tid; idx < wpb * per; idx += blockDim.x) {
-            const int k = idx >> Mv.wpb_log2, w1 = idx & (wpb - 1);   // term-major: a warp works on one kind of term
+            const int k = idx >> wl2, w1 = idx & (wpb - 1);   // term-major: a warp works on one kind of term
             if (g * wpb + w1 >= Mv.Ns) continue;
             const double *q = s_q + w1 * D;
             double *t = s_term + w1 * kTermStride;
@@ -1025,7 +1028,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         const R *kap = reinterpret_cast<const R *>(P.kappa);
         const int n = (P.nsamples >> 1) * wpb;
         for (int idx = tid; idx < n; idx += blockDim.x) {
-            const int kp = idx >> Mv.wpb_log2, wl = idx & (wpb - 1);
+            const int kp = idx >> wl2, wl = idx & (wpb - 1);
             const R ebv = s_wc[wl * kNumWC + 3];
             const R4 rec = s_bank[kp];
             R2 v;
@@ -1042,7 +1045,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // wpb/32 walker columns x nw/(wpb/32) tile stripes, so ONE proposal phase serves up to 256 walkers.
     const int ncol = wpb > 32 ? wpb >> 5 : 1, col = warp % ncol, stripe = warp / ncol, nstripes = nw / ncol;
     const int wl = wpb > 32 ? col * 32 + lane : lane & (wpb - 1);
-    const int slot = wpb > 32 ? 0 : lane >> Mv.wpb_log2, ppt = wpb > 32 ? 1 : 32 >> Mv.wpb_log2;
+    const int slot = wpb > 32 ? 0 : lane >> wl2, ppt = wpb > 32 ? 1 : 32 >> wl2;
     const long long iw = g * wpb + wl;
     const bool skip = s_flag[wl] != 0;
     LaneWalker<R> lw;
@@ -1163,10 +1166,10 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
 // Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
 // Grid = walker groups x cluster size (cluster dimension set by the launch attribute; 1 for large ensembles).
 // ---------------------------------------------------------------------------------------
-template <int MODEL, typename R>
+template <int MODEL, typename R, int WL>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int wpb = 1 << Mv.wpb_log2;
+    const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
     SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
@@ -1182,7 +1185,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     if (Mv.npeers) peers_wait(Mv);
     bool first = true;
     for (long long g = cluster_id_x(); g < ngroups; g += nclusters) {
-        group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize);
+        group_pass<MODEL, R, WL>(P, TL, Mv, g, smem, L, first, crank, csize);
         first = false;
     }
     if (Mv.npeers) peers_publish(Mv);
