@@ -205,15 +205,17 @@ typedef void (*ChainKernel)(const BatchDev);
 // LCF_DEV_ONLY_MODEL=<id> (tools/microbench builds): instantiate the FP32 half-step kernel of one model only, so that a
 // kernel experiment compiles in seconds.  Never defined for the shipped library.
 #ifdef LCF_DEV_ONLY_MODEL
-template <typename R> PassKernel pass_kernel_for(int model, int l = -1) {
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false) {
     if (model != LCF_DEV_ONLY_MODEL) return nullptr;
-    return l == 5 ? k_pass<LCF_DEV_ONLY_MODEL, R, 5> : k_pass<LCF_DEV_ONLY_MODEL, R, -1>;
+    if (l == 5) return plain ? k_pass<LCF_DEV_ONLY_MODEL, R, 5, true> : k_pass<LCF_DEV_ONLY_MODEL, R, 5, false>;
+    return k_pass<LCF_DEV_ONLY_MODEL, R, -1, false>;
 }
 template <typename R> ChainKernel chain_kernel_for(int) { return nullptr; }
 #else
 // l = walkers-per-CTA exponent of the launch: 5 (32 walkers, every large ensemble) has its own instantiation
-template <typename R> PassKernel pass_kernel_for(int model, int l = -1) {
-#define LCF_PASS_CASE(M) case M: return l == 5 ? k_pass<M, R, 5> : k_pass<M, R, -1>;
+// and, for it, one more without the per-tile mode / use_sigma branches (plain = no intrinsic scatter, not a model evaluation)
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false) {
+#define LCF_PASS_CASE(M) case M: return l == 5 ? (plain ? k_pass<M, R, 5, true> : k_pass<M, R, 5, false>) : k_pass<M, R, -1, false>;
     switch (model) {
         LCF_PASS_CASE(1) LCF_PASS_CASE(2) LCF_PASS_CASE(3) LCF_PASS_CASE(4)
         LCF_PASS_CASE(5) LCF_PASS_CASE(6) LCF_PASS_CASE(7) LCF_PASS_CASE(8)
@@ -342,9 +344,11 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     }
     int rc = build_tiles(p, bs.l);
     if (rc) return rc;
-    PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l) : pass_kernel_for<double>(p->dev.model, bs.l);
-    if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
-    if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
+    for (int plain = 0; plain < 2; ++plain) {
+        PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
+        if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
+        if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
+    }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
     if (getenv("LCF_DEBUG_SHAPE"))
@@ -361,7 +365,9 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     int rc = choose_shape(p, mv.Ns, &sh);
     if (rc) return rc;
     mv.wpb_log2 = sh.l;
-    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l) : pass_kernel_for<double>(p->dev.model, sh.l);
+    const bool plain = mv.mode != MODE_MODEL && !p->dev.use_sigma;
+    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain)
+                                                        : pass_kernel_for<double>(p->dev.model, sh.l, plain);
     const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
     const long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
     cudaLaunchConfig_t cfg;

@@ -901,7 +901,9 @@ template <typename R> struct SmemLayout {
 // ---------------------------------------------------------------------------------------
 // WL >= 0: walkers-per-CTA exponent known at compile time (k_pass instantiates WL = 5, the shape of every large ensemble:
 // the lane arithmetic slot / ppt / wl and the tile guards fold to constants); WL = -1: read from Mv.wpb_log2.
-template <int MODEL, typename R, int WL = -1>
+// PLAIN: the launch is a move / log-posterior / log-likelihood pass without the intrinsic-scatter term (the reference's default):
+// the per-tile mode and use_sigma branches are compiled out.
+template <int MODEL, typename R, int WL = -1, bool PLAIN = false>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
                                            unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize) {
     typedef typename Vec2<R>::type R2;
@@ -1074,10 +1076,10 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             R ya, yb;
             blackbody_pair<MODEL, R>(s_bank, fi, fa, fb, two, s_tabw, s_e2t, ya, yb);
             if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
-            if (Mv.mode == MODE_MODEL) {
+            if (!PLAIN && Mv.mode == MODE_MODEL) {
                 Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
                 if (two) Mv.out[iw * P.npoints + pb] = (double)yb * P.scale;
-            } else if (P.use_sigma) {
+            } else if (!PLAIN && P.use_sigma) {
                 const R s2a = oa.y + lw.wc[7] * oa.z;                // models.py:130
                 const R ra = oa.x - ya;
                 chi += Mth<R>::lg2(s2a) * (R)kLn2 + ra * ra * Mth<R>::rcp(s2a);
@@ -1097,7 +1099,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         }
     }
     LCF_TICK(3);
-    if (Mv.mode == MODE_MODEL) { __syncthreads(); return; }
+    if (!PLAIN && Mv.mode == MODE_MODEL) { __syncthreads(); return; }
 
     // ---- phase 3: reduce, accept, write back ----------------------------------------------
     double chid = (double)chi;
@@ -1166,7 +1168,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
 // Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
 // Grid = walker groups x cluster size (cluster dimension set by the launch attribute; 1 for large ensembles).
 // ---------------------------------------------------------------------------------------
-template <int MODEL, typename R, int WL>
+template <int MODEL, typename R, int WL, bool PLAIN>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
@@ -1185,7 +1187,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     if (Mv.npeers) peers_wait(Mv);
     bool first = true;
     for (long long g = cluster_id_x(); g < ngroups; g += nclusters) {
-        group_pass<MODEL, R, WL>(P, TL, Mv, g, smem, L, first, crank, csize);
+        group_pass<MODEL, R, WL, PLAIN>(P, TL, Mv, g, smem, L, first, crank, csize);
         first = false;
     }
     if (Mv.npeers) peers_publish(Mv);
