@@ -765,22 +765,29 @@ int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *
     if (!e || !coords) return fail(LCF_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(e->p->device));
     const int D = e->D;
-    std::vector<double> hc((size_t)e->W * D), hl(e->W);
-    for (long long j = 0; j < e->W; ++j) {
-        long long r = phys_row(e, j);
-        for (int d = 0; d < D; ++d) {
-            double v = coords[j * D + d];
-            if (std::isinf(v)) return fail(LCF_ERR_ARG, "At least one parameter value was infinite");   // emcee check
-            if (std::isnan(v)) return fail(LCF_ERR_ARG, "At least one parameter value was NaN");
-            hc[r * D + d] = v;
-        }
-        if (log_prob) hl[r] = log_prob[j];
+    const size_t nc = (size_t)e->W * D;
+    // logical order in, colour-major on the device: the permutation and emcee's NaN / infinity checks run in a kernel
+    double *d_in = nullptr, *d_lp = nullptr;
+    int *d_fl = nullptr;
+    CUDA_TRY(cudaMalloc(&d_in, sizeof(double) * nc));
+    cudaError_t ce = cudaMalloc(&d_fl, sizeof(int));
+    if (ce == cudaSuccess && log_prob) ce = cudaMalloc(&d_lp, sizeof(double) * e->W);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_fl, 0, sizeof(int), e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_in, coords, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess && log_prob) ce = cudaMemcpyAsync(d_lp, log_prob, sizeof(double) * e->W, cudaMemcpyHostToDevice, e->stream);
+    int h_fl = 0;
+    if (ce == cudaSuccess) {
+        k_set_state<<<(unsigned)((nc + 255) / 256), 256, 0, e->stream>>>(d_in, d_lp, e->W, D, e->n0, e->d_coords, e->d_logp, d_fl);
+        ce = cudaGetLastError();
     }
-    CUDA_TRY(cudaMemcpyAsync(e->d_coords, hc.data(), sizeof(double) * hc.size(), cudaMemcpyHostToDevice, e->stream));
-    if (log_prob) {
-        CUDA_TRY(cudaMemcpyAsync(e->d_logp, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, e->stream));
-        CUDA_TRY(cudaStreamSynchronize(e->stream));
-    } else {
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&h_fl, d_fl, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_in); cudaFree(d_lp); cudaFree(d_fl);
+    if (ce != cudaSuccess) return fail(LCF_ERR_CUDA, "set_state failed: %s", cudaGetErrorString(ce));
+    if (h_fl) e->has_state = false;                     // the previous state has been overwritten
+    if (h_fl & 1) return fail(LCF_ERR_ARG, "At least one parameter value was infinite");   // emcee's initial-state check
+    if (h_fl & 2) return fail(LCF_ERR_ARG, "At least one parameter value was NaN");
+    if (!log_prob) {
         MoveDev mv;
         memset(&mv, 0, sizeof(mv));
         mv.mode = MODE_LOGPOST;

@@ -175,4 +175,21 @@ __global__ void k_bb_lstsq(long long nepochs, const int *__restrict__ off, const
     status[e] = st;
 }
 
+// Start positions arrive in emcee's logical walker order; the ensemble lives colour-major (even walkers, then odd).  The
+// permutation and emcee's initial-state checks (no NaN, no infinity) run on the device instead of a host loop over W x D.
+__global__ void __launch_bounds__(256) k_set_state(const double *__restrict__ in, const double *__restrict__ lp_in, long long W, int D,
+                                                   long long n0, double *__restrict__ coords, double *__restrict__ logp,
+                                                   int *__restrict__ flags) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * D) return;
+    const long long j = idx / D;
+    const int d = (int)(idx - j * D);
+    const long long r = (j & 1) ? n0 + (j >> 1) : (j >> 1);
+    const double v = in[idx];
+    if (isinf(v)) atomicOr(flags, 1);
+    if (isnan(v)) atomicOr(flags, 2);
+    coords[r * D + d] = v;
+    if (lp_in && d == 0) logp[r] = lp_in[j];
+}
+
 }  // namespace lcf
