@@ -239,9 +239,10 @@ template <typename R> ChainKernel chain_kernel_for(int model) {
 #endif
 
 size_t smem_bytes(const lcf_problem *p, int wpb, int nw) {
+    const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
     if (p->precision == LCF_PRECISION_FP32)
-        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3).total;
-    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3).total;
+        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl).total;
+    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl).total;
 }
 
 constexpr size_t kSmemMax = 227 * 1024;
@@ -475,6 +476,10 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
         P.spl_nint = nint;
         P.spl_x0 = d->sifto_x0;
         P.spl_dx = d->sifto_dx;
+        if (d->model_id >= 5 && d->model_id <= 7) {        // spline origin, spacing, reciprocal spacing as `real` constants
+            P.dk[0] = d->sifto_x0; P.dk[1] = d->sifto_dx; P.dk[2] = 1. / d->sifto_dx;
+            for (int i = 0; i < 4; ++i) P.fk[i] = (float)P.dk[i];
+        }
     }
     return 0;
 }

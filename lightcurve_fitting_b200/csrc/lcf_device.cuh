@@ -371,6 +371,7 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, const 
             s.wc[2] = (0.5 * term[2] + 0.5) * (0.14 * (th * th) - 0.4 * th + 1.);
         }
         s.wc[3] = p[4];                                     // stretch
+        s.wc[9] = 1. / p[4];
         s.wc[8] = (s.wc[0] > 0.) ? 1. / s.wc[0] : 0.;       // 1/T = wc8 t^(74/144)
         if (MODEL == 5) { s.wc[4] = p[5]; s.wc[5] = p[6]; s.wc[6] = p[7]; }   // r_r, r_i, r_U
         else            { s.wc[4] = p[5]; s.wc[5] = p[6]; }                   // dt_U, dt_i
@@ -624,15 +625,17 @@ template <int WHICH> __device__ __forceinline__ float since(const ProblemDev &P,
 }
 
 // SiFTO cubic spline (models.py:717, 817-826): NaN outside the knots -> 0
+// `spl` is the shared-memory copy of the coefficient table (staged by TMA with the filter bank); knot origin, spacing and
+// its reciprocal come as `real` constants (kconst 0..2 for these models).
 template <typename R>
-__device__ __forceinline__ R sifto_eval(const ProblemDev &P, int f, R tau) {
-    const R x0 = (R)P.spl_x0, dx = (R)P.spl_dx;
+__device__ __forceinline__ R sifto_eval(const ProblemDev &P, const typename Vec4<R>::type *__restrict__ spl, int f, R tau) {
+    const R x0 = kconst<R>(P, 0), dx = kconst<R>(P, 1), inv_dx = kconst<R>(P, 2);
     const R xn = x0 + dx * (R)P.spl_nint;
     if (!(tau >= x0 && tau <= xn)) return (R)0;
-    int i = (int)floor((tau - x0) / dx);
+    int i = (int)floor((tau - x0) * inv_dx);
     i = min(max(i, 0), P.spl_nint - 1);
     R h = tau - (x0 + dx * (R)i);
-    typename Vec4<R>::type c = reinterpret_cast<const typename Vec4<R>::type *>(P.spl)[(size_t)f * P.spl_nint + i];
+    const typename Vec4<R>::type c = spl[f * P.spl_nint + i];
     R v = ((c.x * h + c.y) * h + c.z) * h + c.w;
     return (v != v) ? (R)0 : v;
 }
@@ -649,7 +652,8 @@ __device__ __forceinline__ R sifto_eval(const ProblemDev &P, int f, R tau) {
 //   CS*: wc0, wc1 Kasen T/R^2 coefficients, wc2 Kasen factor, wc3 stretch, wc4.. r_r,r_i,r_U | dt_U,dt_i, wc8 = 1/wc0
 //   SED: wc0 = 1/T, wc1 = R^2
 template <int MODEL, typename R>
-__device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<R> &w, int p, R &inv, R &amp, R &add) {
+__device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<R> &w, int p, R &inv, R &amp, R &add,
+                                          const typename Vec4<R>::type *__restrict__ s_spl) {
     typedef Mth<R> M;
     add = (R)0;
     if (MODEL == 8) {
@@ -698,12 +702,12 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
         const int role = P.frole[f];
         const R tw = since<1>(P, w, p);                          // t_wrt_peak, models.py:816
         if (MODEL == 5) {
-            const R ys = sifto_eval<R>(P, f, tw / w.wc[3]);
+            const R ys = sifto_eval<R>(P, s_spl, f, tw * w.wc[9]);       // wc9 = 1 / stretch
             a *= (role & 1) ? w.wc[6] : (R)1;
             add = ys * ((role & 2) ? w.wc[4] : ((role & 4) ? w.wc[5] : (R)1));   // models.py:915
         } else {
             const R dtf = (role & 8) ? w.wc[4] : ((role & 16) ? w.wc[5] : (R)0);
-            add = sifto_eval<R>(P, f, (tw - dtf) / w.wc[3]);
+            add = sifto_eval<R>(P, s_spl, f, (tw - dtf) * w.wc[9]);
             a *= w.wc[2];                                        // models.py:979, 1044
         }
     }
@@ -870,11 +874,12 @@ constexpr int kMaxCluster = 8;      // portable cluster size limit
 constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model terms, prior terms, ln z, ln u
 
 template <typename R> struct SmemLayout {
-    size_t off_e2t, off_bank, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
-    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab) {
+    size_t off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
+    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl) {
         size_t o = 0;
         off_e2t = o;  o += sizeof(R) == 8 ? 16 * sizeof(double) : 0;             // 2^(j/16), FP64 loop
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
+        off_spl = o;  o += (size_t)nspl * 4 * sizeof(R);                          o = (o + 15) & ~(size_t)15;   // SiFTO cubic coefficients
         off_tab = o;  o += tab ? (size_t)nsamples * kTabStride * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][32]
         off_foff = o; o += (size_t)nfilters * sizeof(int4);                       o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
@@ -914,6 +919,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     typedef typename Vec4<R>::type R4;
     R4 *s_bank = reinterpret_cast<R4 *>(smem + L.off_bank);
     R2 *s_tab = reinterpret_cast<R2 *>(smem + L.off_tab);
+    const R4 *s_spl = reinterpret_cast<const R4 *>(smem + L.off_spl);
     const double *s_e2t = reinterpret_cast<const double *>(smem + L.off_e2t);
     int4 *s_finfo = reinterpret_cast<int4 *>(smem + L.off_foff);
     R *s_wc = reinterpret_cast<R *>(smem + L.off_wc);
@@ -931,9 +937,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // ---- phase 0: stage the packed filter bank with one TMA bulk copy -------------------
     if (need_stage) {
         if (tid == 0) {
-            uint32_t bytes = (uint32_t)((size_t)(P.nsamples >> 1) * sizeof(R4));
-            mbar_expect_tx(s_bar, bytes);
+            const uint32_t bytes = (uint32_t)((size_t)(P.nsamples >> 1) * sizeof(R4));
+            const uint32_t sbytes = (MODEL >= 5 && MODEL <= 7) ? (uint32_t)((size_t)P.nfilters * P.spl_nint * sizeof(R4)) : 0u;
+            mbar_expect_tx(s_bar, bytes + sbytes);
             tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
+            if (sbytes) tma_bulk_g2s(smem + L.off_spl, P.spl, sbytes, s_bar);
         }
         for (int i = tid; i < P.nfilters; i += blockDim.x) s_finfo[i] = P.finfo[i];
     }
@@ -1069,8 +1077,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             const int4 fi = s_finfo[tl.z];
             PointFE<R> fa, fb;
             R adda, addb;
-            front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda);      // branch-free: the two MUFU chains interleave
-            front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb);
+            front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda, s_spl);      // branch-free: the two MUFU chains interleave
+            front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb, s_spl);
             fa.state = fa.invT > (R)0 ? 1 : 0;
             fb.state = fb.invT > (R)0 ? 1 : 0;
             R ya, yb;
@@ -1172,7 +1180,7 @@ template <int MODEL, typename R, int WL, bool PLAIN>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
-    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3);
+    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
@@ -1231,7 +1239,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     }
     __syncthreads();
     const int wpb = 1 << B.wpb_log2;
-    SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3);
+    SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? sP.nfilters * sP.spl_nint : 0);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
