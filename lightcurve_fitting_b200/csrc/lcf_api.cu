@@ -335,6 +335,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                 double cost = std::max(t_xu, t_lat);
                 for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
                 if (nw < 8) cost *= 1.15;
+                if (ctas < sms) cost *= 1. + 0.25 * (1. - (double)ctas / sms);  // measured (cfg1 sweep): idle SMs cost more than the chain model says
                 if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; }
             }
         }
