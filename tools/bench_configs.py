@@ -123,8 +123,25 @@ def run_configs(args, only, tune, synthetic, BatchSampler, EnsembleSampler):
              {'acceptance': float(s.acceptance_fraction.mean())})
 
     if not only or 'cfg5' in only:
+        # survey batch: under torchrun every rank takes its round-robin share of the light curves (parallel.shard_items),
+        # no data-path collective; the aggregate is all light curves over the slowest rank's time
+        world, rank = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0'))
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            from lightcurve_fitting_b200 import _capi
+            from lightcurve_fitting_b200.parallel import shard_items
+            local = int(os.environ.get('LOCAL_RANK', '0'))
+            torch.cuda.set_device(local)
+            _capi.check(_capi.lib().lcf_set_device(local))
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            mine = shard_items(args.nlc * world, rank, world)
+        else:
+            mine = list(range(args.nlc))
+        npts = [int(n) for n in np.random.default_rng(0).integers(100, 301, args.nlc * world)]
         t0 = time.time()
-        wls = [synthetic.synthetic_sc4(device_truth, npoints=int(rng.integers(100, 301)), lc_index=i) for i in range(args.nlc)]
+        wls = [synthetic.synthetic_sc4(device_truth, npoints=npts[i], lc_index=i) for i in mine]
         t1 = time.time()                                   # (benchmark's own data generation, not part of the product path)
         probs = [w.device_problem(args.precision) for w in wls]
         prep = time.time() - t1
@@ -134,8 +151,18 @@ def run_configs(args, only, tune, synthetic, BatchSampler, EnsembleSampler):
         ms_short = b.last_ms
         b.run(p0, 200, 200)
         spe = float(np.mean([w.planck_samples_per_eval() for w in wls]))
-        emit('cfg5 %d light curves x ShockCooling4, 256 walkers, 200+200 steps, one launch' % args.nlc, args.nlc * 256, 400,
-             b.last_ms, spe, {'problem_build_s': prep, 'synthetic_data_s': t1 - t0, 'ms_20+20': ms_short, 'acceptance': float(b.acceptance_fraction.mean()),
+        ms_all, nlc_all = b.last_ms, len(wls)
+        if world > 1:
+            t = torch.tensor([b.last_ms, float(len(wls)), spe * len(wls)], device='cuda', dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms_all, nlc_all, spe = float(tmax[0]), int(t[1]), float(t[2] / t[1])
+            dist.destroy_process_group()
+            if rank:
+                return
+        emit('cfg5 %d light curves x ShockCooling4, 256 walkers, 200+200 steps, one launch per GPU, %d GPU(s)' % (nlc_all, world),
+             nlc_all * 256, 400, ms_all, spe, {'problem_build_s': prep, 'synthetic_data_s': t1 - t0, 'ms_20+20': ms_short, 'acceptance': float(b.acceptance_fraction.mean()),
                               'status_ok': bool(np.all(b.status == 0))})
 
 
