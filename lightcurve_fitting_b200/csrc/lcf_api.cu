@@ -238,11 +238,11 @@ template <typename R> ChainKernel chain_kernel_for(int model) {
 }
 #endif
 
-size_t smem_bytes(const lcf_problem *p, int wpb, int nw) {
+size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxCluster) {
     const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
     if (p->precision == LCF_PRECISION_FP32)
-        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl).total;
-    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl).total;
+        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster).total;
+    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster).total;
 }
 
 constexpr size_t kSmemMax = 227 * 1024;
@@ -349,7 +349,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     for (int plain = 0; plain < 2; ++plain) {
         PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
         if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
-        if (bs.smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
+        if (bs.smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
@@ -1347,8 +1347,9 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     int max_tiles = 1;
     for (;;) {
         smem = 0;
-        for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 8));
-        if (smem <= (l > 5 ? kSmemMax / 4 : kSmemMax / 2) || l == 0) break;
+        for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, 8, 1));
+        // four (wide groups) / two CTAs per SM, counting the 1 KB the driver reserves per CTA and the kernel's static 0.8 KB
+        if (smem + 2048 <= (l > 5 ? kSmemMax / 4 : kSmemMax / 2) || l == 0) break;
         --l;
     }
     std::vector<ProblemDev> hp(nproblems);
@@ -1364,11 +1365,14 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     nw = std::max(1, std::min(nw, 8));                    // k_chain is compiled for <= 256 threads
     if (l > 5) nw = 8;                                    // wide groups: 2^(l-5) walker columns of warps must divide nw
     smem = 0;
-    for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw));
+    for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw, 1));
     if (smem > kSmemMax) { delete b; return fail(LCF_ERR_ARG, "filter bank does not fit in shared memory"); }
     b->wpb_log2 = l;
     b->nw = nw;
     b->smem = smem;
+    if (getenv("LCF_DEBUG_SHAPE"))
+        fprintf(stderr, "[lcf] batch shape: %lld problems, %lld walkers, %d walkers/pass, %d warps, %zu B smem\n", (long long)nproblems,
+                (long long)nwalkers, 1 << l, nw, smem);
     void *dp;
     if ((rc = upload(hp, &dp))) { delete b; return rc; }
     b->d_probs = reinterpret_cast<ProblemDev *>(dp);
@@ -1441,7 +1445,7 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.init_logp = b->need_init_logp ? 1 : 0;
     ChainKernel k = (b->precision == LCF_PRECISION_FP32) ? chain_kernel_for<float>(b->model) : chain_kernel_for<double>(b->model);
     if (!k) return fail(LCF_ERR_ARG, "unknown model");
-    if (b->smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    if (b->smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     k<<<(unsigned)b->nprob, b->nw * 32, b->smem, b->stream>>>(B);
     CUDA_TRY(cudaGetLastError());

@@ -875,7 +875,8 @@ constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model term
 
 template <typename R> struct SmemLayout {
     size_t off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
-    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl) {
+    // ncluster: largest cluster that may share a walker group (1 in the chain kernel: no cluster partials to hold)
+    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster) {
         size_t o = 0;
         off_e2t = o;  o += sizeof(R) == 8 ? 16 * sizeof(double) : 0;             // 2^(j/16), FP64 loop
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
@@ -889,7 +890,7 @@ template <typename R> struct SmemLayout {
         off_z = o;    o += (size_t)wpb * sizeof(double);
         off_term = o; o += (size_t)wpb * kTermStride * sizeof(double);
         off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
-        off_cpart = o; o += (size_t)kMaxCluster * wpb * sizeof(double);
+        off_cpart = o; o += ncluster > 1 ? (size_t)ncluster * wpb * sizeof(double) : 0;
         off_flag = o; o += (size_t)wpb * sizeof(int);                             o = (o + 15) & ~(size_t)15;
         off_bar = o;  o += 16;
         total = o;
@@ -1239,7 +1240,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     }
     __syncthreads();
     const int wpb = 1 << B.wpb_log2;
-    SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? sP.nfilters * sP.spl_nint : 0);
+    SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? sP.nfilters * sP.spl_nint : 0, 1);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);

@@ -272,24 +272,26 @@ def test_batched_ensembles_match_single():
     assert 0.05 < b.acceptance_fraction.mean() < 0.95
 
 
-@pytest.mark.parametrize('nw', [70, 150, 300])
+@pytest.mark.parametrize('nw', [70, 150, 256, 300])
 def test_batched_ensembles_wide_walker_groups(nw):
     """Half-ensembles of 35 / 75 / 150 walkers run as ONE wide group (64 / 128 / 256 walkers, several warp columns) per
     half-step in the chain kernel: every stored position carries its own log-posterior, chains move, results match the
     oracle, and the light curves have different lengths (ragged batch)."""
     from lightcurve_fitting_b200.bolometric import BatchSampler
-    wls = [W.synthetic_sc4(npoints=n, lc_index=i) for i, n in enumerate((40, 97, 13))]
-    probs = [w.device_problem('fp64') for w in wls]
+    # (256 walkers x all nine filters is the cfg5 shape: 48.9 KB of dynamic + 0.8 KB of static shared memory, just past
+    # the 48 KB a kernel gets without opting in -- it once failed to launch)
+    wls = [W.synthetic_sc4(npoints=n, lc_index=i) for i, n in enumerate((40, 200 if nw == 256 else 97, 13))]
+    probs = [w.device_problem('fp32' if nw == 256 else 'fp64') for w in wls]
     rng = np.random.default_rng(nw)
     p0 = np.stack([w.start(nw, rng) for w in wls])
     b = BatchSampler(probs, nw, seed=5).run(p0, 6, 5)
     chain, lnp = b.get_chain(), b.get_log_prob()
     assert chain.shape == (3, 5, nw, 5) and np.all(b.status == 0)
     for i, w in enumerate(wls):
-        np.testing.assert_allclose(probs[i].log_posterior(chain[i].reshape(-1, 5)), lnp[i].reshape(-1), rtol=1e-12)
+        np.testing.assert_allclose(probs[i].log_posterior(chain[i].reshape(-1, 5)), lnp[i].reshape(-1), rtol=1e-12 if nw != 256 else 2e-5)
         lp = W.oracle_log_posterior(w)
         sel = np.random.default_rng(i).choice(nw, 6, replace=False)
-        np.testing.assert_allclose(lnp[i, -1, sel], [lp(p) for p in chain[i, -1, sel]], rtol=1e-9)
+        np.testing.assert_allclose(lnp[i, -1, sel], [lp(p) for p in chain[i, -1, sel]], rtol=1e-9 if nw != 256 else 1e-4)
         assert not np.array_equal(chain[i, 0], chain[i, -1])
     assert 0.02 < b.acceptance_fraction.mean() < 0.95
 
