@@ -169,7 +169,8 @@ template <typename R> struct Vec4;
 template <> struct Vec4<float> { typedef float4 type; };
 template <> struct Vec4<double> { typedef double4 type; };
 
-constexpr int kTabStride = 32;      // ShockCooling3 weight table: [pair record][32 walker columns], whatever wpb is
+constexpr int kTabStride = 32;      // ShockCooling3 weight table [pair record][walker column]: 32 columns at compile time in the
+                                    // 32-walker instantiation, min(wpb, 32) at run time otherwise (a big bank still fits at small wpb)
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kLn2 = 0.69314718055994530942;
 
@@ -460,10 +461,10 @@ __device__ __forceinline__ float2 rcp_newton2(float2 x) {
 // (a) two blackbodies (points A, B of one walker) x the two samples of a pair record; two records per iteration.
 //     Pointer-bumped with compile-time strides so that the loop bookkeeping is 2 adds + compare + branch (integer
 //     multiply-adds would land on the FMA pipe, which is the second-busiest one here).
-template <bool TAB, bool WIEN>
+template <bool TAB, bool WIEN, int TS>
 __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, int K2, float iA, float iB,
-                                                const float2 *__restrict__ tab, float &SA, float &SB) {
-    constexpr int ts = kTabStride;
+                                                const float2 *__restrict__ tab, int ts_rt, float &SA, float &SB) {
+    const int ts = TS > 0 ? TS : ts_rt;
     const float sA = WIEN ? -iA : iA, sB = WIEN ? -iB : iB;
     const float2 iA2 = make_float2(sA, sA), iB2 = make_float2(sB, sB);
     float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
@@ -570,8 +571,7 @@ __device__ __forceinline__ double rcp_f64(double x) {
 
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, int K2, double iA, double iB,
-                                                const double2 *__restrict__ tab, const double *__restrict__ e2t, double &SA, double &SB) {
-    constexpr int ts = kTabStride;
+                                                const double2 *__restrict__ tab, int ts, const double *__restrict__ e2t, double &SA, double &SB) {
     double a0 = 0., a1 = 0., b0 = 0., b1 = 0.;
 #pragma unroll 2                                         // eight independent exp2 chains per lane: the FP64 pipe's latency needs them at 16 warps/SM
     for (const double4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
@@ -721,14 +721,14 @@ template <typename R> struct PointFE {
 };
 
 // Blackbody part of up to two points of one filter for one walker.
-template <int MODEL, typename R>
+template <int MODEL, typename R, int TS>
 __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *bank, const int4 fi,
                                                const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, const double *e2t, R &y0, R &y1) {
+                                               const typename Vec2<R>::type *tab, int ts_rt, const double *e2t, R &y0, R &y1) {
     typedef Mth<R> M;
     typedef typename Vec2<R>::type R2;
     typedef typename Vec4<R>::type R4;
-    constexpr int ts = kTabStride;
+    const int ts = TS > 0 ? TS : ts_rt;
     const int k0 = fi.x, K2 = fi.y;                                     // pair records of this filter
     const R4 *b = bank + k0;
     const R2 *tb = tab + (size_t)k0 * ts;
@@ -758,11 +758,11 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
                 if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
             } else {
                 if (MODEL == 3) {
-                    if (clamp) planck_quad_f32<true, true>(bf, K2, i0, i1, tf, S0, S1);
-                    else planck_quad_f32<true, false>(bf, K2, i0, i1, tf, S0, S1);
+                    if (clamp) planck_quad_f32<true, true, TS>(bf, K2, i0, i1, tf, ts, S0, S1);
+                    else planck_quad_f32<true, false, TS>(bf, K2, i0, i1, tf, ts, S0, S1);
                 } else {
-                    if (clamp) planck_quad_f32<false, true>(bf, K2, i0, i1, nullptr, S0, S1);
-                    else planck_quad_f32<false, false>(bf, K2, i0, i1, nullptr, S0, S1);
+                    if (clamp) planck_quad_f32<false, true, TS>(bf, K2, i0, i1, nullptr, ts, S0, S1);
+                    else planck_quad_f32<false, false, TS>(bf, K2, i0, i1, nullptr, ts, S0, S1);
                 }
                 if (n0) y0 = (R)((float)f0.amp * S0);
                 if (n1) y1 = (R)((float)f1.amp * S1);
@@ -782,11 +782,11 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
             const double4 *bd = reinterpret_cast<const double4 *>(b);
             const double2 *td = reinterpret_cast<const double2 *>(tb);
             double S0, S1;
-            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, e2t, S0, S1);
-            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, e2t, S0, S1);
+            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, ts, e2t, S0, S1);
+            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, ts, e2t, S0, S1);
             if (MODEL == 4) {
                 double S0s, S1s;
-                planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, e2t, S0s, S1s);
+                planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, ts, e2t, S0s, S1s);
                 if (n0) y0 = (R)fmin((double)f0.amp * S0, (double)f0.amp * (double)c74_4 * S0s);   // models.py:631
                 if (n1) y1 = (R)fmin((double)f1.amp * S1, (double)f1.amp * (double)c74_4 * S1s);
             } else {
@@ -881,7 +881,7 @@ template <typename R> struct SmemLayout {
         off_e2t = o;  o += sizeof(R) == 8 ? 16 * sizeof(double) : 0;             // 2^(j/16), FP64 loop
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_spl = o;  o += (size_t)nspl * 4 * sizeof(R);                          o = (o + 15) & ~(size_t)15;   // SiFTO cubic coefficients
-        off_tab = o;  o += tab ? (size_t)nsamples * kTabStride * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][32]
+        off_tab = o;  o += tab ? (size_t)nsamples * (wpb < 32 ? wpb : 32) * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][min(wpb, 32)]
         off_foff = o; o += (size_t)nfilters * sizeof(int4);                       o = (o + 15) & ~(size_t)15;
         off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
@@ -1034,6 +1034,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     if (need_stage) mbar_wait(s_bar, 0);
     LCF_TICK(1);
 
+    const int tstride = WL == 5 ? kTabStride : (wpb < 32 ? wpb : 32);     // weight-table columns
     // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33), pair layout
     if (MODEL == 3) {
         const R *kap = reinterpret_cast<const R *>(P.kappa);
@@ -1045,7 +1046,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             R2 v;
             v.x = rec.z * Mth<R>::ex2(-ebv * kap[2 * kp]);
             v.y = rec.w * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
-            s_tab[kp * kTabStride + wl] = v;
+            s_tab[kp * tstride + wl] = v;
         }
         __syncthreads();
     }
@@ -1083,7 +1084,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             fa.state = fa.invT > (R)0 ? 1 : 0;
             fb.state = fb.invT > (R)0 ? 1 : 0;
             R ya, yb;
-            blackbody_pair<MODEL, R>(s_bank, fi, fa, fb, two, s_tabw, s_e2t, ya, yb);
+            blackbody_pair<MODEL, R, (WL == 5 ? kTabStride : 0)>(s_bank, fi, fa, fb, two, s_tabw, tstride, s_e2t, ya, yb);
             if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
             if (!PLAIN && Mv.mode == MODE_MODEL) {
                 Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;

@@ -777,3 +777,32 @@ def test_batched_blackbody_lstsq_matches_curve_fit():
         assert nbound >= 3
     one = B.blackbody_lstsq(epochs[0], 0.003, cutoff_freq=900.)
     np.testing.assert_allclose(one, [temp[0], radius[0], dtemp[0], drad[0], L[0], dL[0], Lopt[0]], rtol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_shockcooling3_with_a_large_filter_bank(precision):
+    """ShockCooling3 through space-telescope filters with > 1000 transmission samples each: the per-walker reddened
+    weight table no longer fits in shared memory at 32 walkers per CTA, the launch-shape model has to pick fewer walkers
+    per CTA (the table is [samples][walkers per CTA]), and the result is still the oracle's."""
+    from lightcurve_fitting_b200.synthetic import Workload
+    rng = np.random.default_rng(9)
+    names = ['NUV', 'F2550W', 'F2100W', 'F444W', 'U', 'B', 'g', 'r']
+    n = 48
+    t0 = 59000.
+    t = np.sort(rng.uniform(t0 + 0.3, t0 + 12., n))
+    fn = [names[i % len(names)] for i in range(n)]
+    p_true = np.array([1., 1., 1., 3., 20., 0.1, t0])
+    ytrue = W.oracle_truth('ShockCooling3', t, fn, p_true, 0.005)
+    dy = 0.05 * ytrue
+    y = ytrue + dy * rng.normal(size=n)
+    pri = [('uniform', 0., 10.), ('uniform', 0., 10.), ('uniform', 0., 100.), ('uniform', 0., 100.), ('uniform', 5., 50.),
+           ('uniform', 0., 1.), ('uniform', t0 - 2., t0 + 0.3)]
+    lo, hi = p_true * 0.9, p_true * 1.1
+    lo[6], hi[6] = t0 - 0.1, t0 + 0.1
+    wl = Workload('sc3-large-bank', 'ShockCooling3', t, fn, y, dy, pri, lo, hi, z=0.005, truth=p_true)
+    assert wl.planck_samples_per_eval() > 30000
+    _check_logpost(wl, precision, n=40, seed=2)
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    s = EnsembleSampler(80, wl.ndim, wl.device_problem(precision), seed=4)
+    s.run_mcmc(wl.start(80, rng), 4)
+    assert np.isfinite(s.get_log_prob()).all()

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(T, 1024 / T) kloop(float *out, const float4 *b
     float accA = 0.f, accB = 0.f;
     for (int r = 0; r < REP; ++r) {
         float SA = 0, SB = 0, SAs = 0, SBs = 0;
-        if (V == 0) planck_quad_f32<false, false>(bank, K2, iA, iB, nullptr, SA, SB);
-        if (V == 1) planck_quad_f32<true, false>(bank, K2, iA, iB, tab + lane, SA, SB);
+        if (V == 0) planck_quad_f32<false, false, 32>(bank, K2, iA, iB, nullptr, 32, SA, SB);
+        if (V == 1) planck_quad_f32<true, false, 32>(bank, K2, iA, iB, tab + lane, 32, SA, SB);
         if (V == 2) quad_nr<1>(bank, K2, iA, iB, SA, SB);
         if (V == 3) quad_nr<2>(bank, K2, iA, iB, SA, SB);
         if (V == 4) oct_em<0>(bank, K2, iA, iB, SA, SB);
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(T, 1024 / T) kloop(float *out, const float4 *b
         if (V == 10) quad_nr_x2<false>(bank, K2, iA, iB, nullptr, 0, SA, SB);
         if (V == 11) quad_nr_x2<true>(bank, K2, iA, iB, tab + lane, 32, SA, SB);
         if (V == 12) { sc4_nr(bank, K2, iA, iB, SA, SAs, SB, SBs); SA += SAs; SB += SBs; }
-        if (V == 13) planck_quad_f32<true, true>(bank, K2, iA, iB, tab + lane, SA, SB);
+        if (V == 13) planck_quad_f32<true, true, 32>(bank, K2, iA, iB, tab + lane, 32, SA, SB);
         if (V == 7) { planck_quad_sc4_f32<false>(bank, K2, iA, iB, SA, SAs, SB, SBs); SA += SAs; SB += SBs; }
         accA += SA; accB += SB;
         iA += 1e-6f; iB += 1e-6f;
