@@ -275,16 +275,22 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         e2.set_state(pin_in.numpy())                                                  # H2D start positions
+        t_set = time.perf_counter()
         first, count = e2.own_walkers()
         if e2.fused:      # this rank's walkers streamed D2H into pinned buffers while the next steps run
             chain = pin_chain.numpy().reshape(-1)[:args.steps * count * D].reshape(args.steps, count, D)
             lnp = pin_lnp.numpy().reshape(-1)[:args.steps * count].reshape(args.steps, count)
             e2.run(args.steps, store=True, chain_out=chain, log_prob_out=lnp)
+            t_run = time.perf_counter()
             e2.finish()
         else:
             e2.run(args.steps, store=True)
+            t_run = time.perf_counter()
             e2.finish()
             chain, lnp = e2.get_own_chain(pin_chain.numpy(), pin_lnp.numpy())            # D2H of this rank's walkers
+        if os.environ.get('LCF_E2E_TIMING') and rank == 0:
+            print('[e2e] set_state %.1f ms, run %.1f ms, finish %.1f ms' % (1e3 * (t_set - t0), 1e3 * (t_run - t_set),
+                                                                             1e3 * (time.perf_counter() - t_run)), file=sys.stderr, flush=True)
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device='cuda', dtype=torch.float64)

@@ -124,9 +124,13 @@ struct lcf_problem {
     bool tiles_built[6] = {false, false, false, false, false, false};
     struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1; size_t smem = 0; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
+    double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
+    int *d_eval_nan = nullptr;
+    size_t eval_q_cap = 0, eval_out_cap = 0;
     int device = 0;
     ~lcf_problem() {
         for (void *p : allocs) cudaFree(p);
+        cudaFree(d_eval_q); cudaFree(d_eval_out); cudaFree(d_eval_nan);
     }
 };
 
@@ -140,7 +144,10 @@ struct lcf_ensemble {
     double *d_coords = nullptr, *d_logp = nullptr;
     unsigned long long *d_acc = nullptr;
     int *d_nan = nullptr;
-    double *d_chain = nullptr, *d_lnp = nullptr;
+    double *d_chain = nullptr, *d_lnp = nullptr;      // [cap][cw][D], [cap][cw]: only the walkers this rank owns
+    long long cfirst = 0, cw = 0;                      // stored logical walkers [cfirst, cfirst + cw)
+    double *d_stage = nullptr;                         // [W][D] + [W]: set_state staging, kept (with peer access on, every
+    int *d_stage_flag = nullptr;                       // cudaMalloc / cudaFree maps into the peers too: slow and erratic)
     long long cap = 0, nstored = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = true;
@@ -159,6 +166,7 @@ struct lcf_ensemble {
     ~lcf_ensemble() {
         for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
         cudaFree(d_flags);
+        cudaFree(d_stage); cudaFree(d_stage_flag);
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -659,14 +667,23 @@ static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, con
     int rc = check_device();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(p->device));
-    double *d_q = nullptr, *d_out = nullptr;
-    int *d_nan = nullptr;
-    CUDA_TRY(cudaMalloc(&d_q, sizeof(double) * nsets * ncols));
-    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * nsets * out_per_set));
-    CUDA_TRY(cudaMalloc(&d_nan, sizeof(int)));
-    CUDA_TRY(cudaMemcpy(d_q, params, sizeof(double) * nsets * ncols, cudaMemcpyHostToDevice));
+    const size_t need_q = sizeof(double) * nsets * ncols, need_out = sizeof(double) * nsets * out_per_set;
+    if (need_q > p->eval_q_cap) {
+        cudaFree(p->d_eval_q); p->d_eval_q = nullptr; p->eval_q_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_eval_q, need_q));
+        p->eval_q_cap = need_q;
+    }
+    if (need_out > p->eval_out_cap) {
+        cudaFree(p->d_eval_out); p->d_eval_out = nullptr; p->eval_out_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_eval_out, need_out));
+        p->eval_out_cap = need_out;
+    }
+    if (!p->d_eval_nan) CUDA_TRY(cudaMalloc(&p->d_eval_nan, sizeof(int)));
+    double *d_q = p->d_eval_q, *d_out = p->d_eval_out;
+    int *d_nan = p->d_eval_nan;
+    CUDA_TRY(cudaMemcpy(d_q, params, need_q, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(d_nan, 0, sizeof(int)));
-    if (mode == MODE_MODEL) CUDA_TRY(cudaMemset(d_out, 0, sizeof(double) * nsets * out_per_set));
+    if (mode == MODE_MODEL) CUDA_TRY(cudaMemset(d_out, 0, need_out));
     MoveDev mv;
     memset(&mv, 0, sizeof(mv));
     mv.mode = mode;
@@ -685,7 +702,6 @@ static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, con
         cudaMemcpy(&h_nan, d_nan, sizeof(int), cudaMemcpyDeviceToHost);
         if (nan_count) *nan_count = h_nan;
     }
-    cudaFree(d_q); cudaFree(d_out); cudaFree(d_nan);
     return rc;
 }
 
@@ -735,6 +751,13 @@ int lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int ran
         e->own_begin[h] = b;
         e->own_count[h] = en - b;
     }
+    // the stored chain holds the walkers this rank updates: all of them on one GPU; with equal colour slices the logical
+    // walkers 2b .. 2(b + c) - 1 of a shared ensemble (1/world of the chain memory and of its allocation time)
+    e->cfirst = 0; e->cw = e->W;
+    if (world > 1 && e->own_begin[0] == e->own_begin[1] && e->own_count[0] == e->own_count[1]) {
+        e->cfirst = 2 * e->own_begin[0];
+        e->cw = 2 * e->own_count[0];
+    }
     cudaError_t ce;
     if ((ce = cudaMalloc(&e->d_coords, sizeof(double) * e->W * e->D)) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_logp, sizeof(double) * e->W)) != cudaSuccess ||
@@ -773,12 +796,13 @@ int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *
     const int D = e->D;
     const size_t nc = (size_t)e->W * D;
     // logical order in, colour-major on the device: the permutation and emcee's NaN / infinity checks run in a kernel
-    double *d_in = nullptr, *d_lp = nullptr;
-    int *d_fl = nullptr;
-    CUDA_TRY(cudaMalloc(&d_in, sizeof(double) * nc));
-    cudaError_t ce = cudaMalloc(&d_fl, sizeof(int));
-    if (ce == cudaSuccess && log_prob) ce = cudaMalloc(&d_lp, sizeof(double) * e->W);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_fl, 0, sizeof(int), e->stream);
+    if (!e->d_stage) {
+        CUDA_TRY(cudaMalloc(&e->d_stage, sizeof(double) * (nc + (size_t)e->W)));
+        CUDA_TRY(cudaMalloc(&e->d_stage_flag, sizeof(int)));
+    }
+    double *d_in = e->d_stage, *d_lp = log_prob ? e->d_stage + nc : nullptr;
+    int *d_fl = e->d_stage_flag;
+    cudaError_t ce = cudaMemsetAsync(d_fl, 0, sizeof(int), e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_in, coords, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess && log_prob) ce = cudaMemcpyAsync(d_lp, log_prob, sizeof(double) * e->W, cudaMemcpyHostToDevice, e->stream);
     int h_fl = 0;
@@ -788,7 +812,6 @@ int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *
     }
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(&h_fl, d_fl, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-    cudaFree(d_in); cudaFree(d_lp); cudaFree(d_fl);
     if (ce != cudaSuccess) return fail(LCF_ERR_CUDA, "set_state failed: %s", cudaGetErrorString(ce));
     if (h_fl) e->has_state = false;                     // the previous state has been overwritten
     if (h_fl & 1) return fail(LCF_ERR_ARG, "At least one parameter value was infinite");   // emcee's initial-state check
@@ -835,19 +858,31 @@ int lcf_ensemble_reset(lcf_ensemble *e) {
     return 0;
 }
 
+// The chain lives in stream-ordered pool memory (cudaMallocAsync): nobody but this rank touches it, and ordinary
+// cudaMalloc / cudaFree of a few hundred MB become slow and erratic (tens of ms) once peer access is on, because every
+// allocation is then mapped into the peers as well.
 static int ensure_capacity(lcf_ensemble *e, long long need) {
     if (need <= e->cap) return 0;
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, e->p->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;                    // keep freed blocks in the pool for the next run
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready = true;
+    }
     long long ncap = std::max(need, e->cap * 2);
     double *nc = nullptr, *nl = nullptr;
-    CUDA_TRY(cudaMalloc(&nc, sizeof(double) * ncap * e->W * e->D));
-    CUDA_TRY(cudaMalloc(&nl, sizeof(double) * ncap * e->W));
+    CUDA_TRY(cudaMallocAsync(&nc, std::max<size_t>(16, sizeof(double) * ncap * e->cw * e->D), e->stream));
+    CUDA_TRY(cudaMallocAsync(&nl, std::max<size_t>(16, sizeof(double) * ncap * e->cw), e->stream));
     if (e->nstored) {
-        CUDA_TRY(cudaMemcpyAsync(nc, e->d_chain, sizeof(double) * e->nstored * e->W * e->D, cudaMemcpyDeviceToDevice, e->stream));
-        CUDA_TRY(cudaMemcpyAsync(nl, e->d_lnp, sizeof(double) * e->nstored * e->W, cudaMemcpyDeviceToDevice, e->stream));
-        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaMemcpyAsync(nc, e->d_chain, sizeof(double) * e->nstored * e->cw * e->D, cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(nl, e->d_lnp, sizeof(double) * e->nstored * e->cw, cudaMemcpyDeviceToDevice, e->stream));
     }
-    cudaFree(e->d_chain);
-    cudaFree(e->d_lnp);
+    if (e->d_chain) CUDA_TRY(cudaFreeAsync(e->d_chain, e->stream));
+    if (e->d_lnp) CUDA_TRY(cudaFreeAsync(e->d_lnp, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));                  // the new blocks are valid on every stream from here on
     e->d_chain = nc;
     e->d_lnp = nl;
     e->cap = ncap;
@@ -870,8 +905,9 @@ static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
     mv.seed = e->seed;
     mv.ctr = (unsigned int)(2 * e->iteration + half);
     if (store) {
-        mv.chain_step = e->d_chain + e->nstored * e->W * e->D;
-        mv.lnp_step = e->d_lnp + e->nstored * e->W;
+        // the kernel indexes by logical walker j: bias the step pointers by the first stored walker
+        mv.chain_step = e->d_chain + (e->nstored * e->cw - e->cfirst) * e->D;
+        mv.lnp_step = e->d_lnp + (e->nstored * e->cw - e->cfirst);
     }
     if (e->npeers) {                                   // fused exchange: one epoch per half-step launch
         mv.npeers = e->npeers;
@@ -1018,7 +1054,8 @@ int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t firs
     NvtxRange r("lcf_ensemble_run_to_host");
     if (!e || !chain_host || !log_prob_host) return fail(LCF_ERR_ARG, "null argument");
     if (!e->has_state) return fail(LCF_ERR_STATE, "run_mcmc before an initial state was set");
-    if (first < 0 || count < 0 || first + count > e->W) return fail(LCF_ERR_ARG, "walker range out of bounds");
+    if (first < e->cfirst || count < 0 || first + count > e->cfirst + e->cw)
+        return fail(LCF_ERR_ARG, "walker range outside the walkers this rank stores");
     CUDA_TRY(cudaSetDevice(e->p->device));
     int rc = ensure_capacity(e, e->nstored + nsteps);
     if (rc) return rc;
@@ -1027,7 +1064,8 @@ int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t firs
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
     }
     e->last_launches = 0;
-    const size_t D = e->D, cw = (size_t)e->W * D, lw = (size_t)e->W;
+    const size_t D = e->D, cw = (size_t)e->cw * D, lw = (size_t)e->cw;
+    const size_t rel = (size_t)(first - e->cfirst);
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     for (long long s = 0; s < nsteps; ++s) {
         for (int half = 0; half < 2; ++half) {
@@ -1038,9 +1076,9 @@ int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t firs
         }
         CUDA_TRY(cudaEventRecord(e->ev_step, e->stream));
         CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_step, 0));
-        CUDA_TRY(cudaMemcpyAsync(chain_host + s * count * D, e->d_chain + e->nstored * cw + first * D, sizeof(double) * count * D,
+        CUDA_TRY(cudaMemcpyAsync(chain_host + s * count * D, e->d_chain + e->nstored * cw + rel * D, sizeof(double) * count * D,
                                  cudaMemcpyDeviceToHost, e->copy_stream));
-        CUDA_TRY(cudaMemcpyAsync(log_prob_host + s * count, e->d_lnp + e->nstored * lw + first, sizeof(double) * count,
+        CUDA_TRY(cudaMemcpyAsync(log_prob_host + s * count, e->d_lnp + e->nstored * lw + rel, sizeof(double) * count,
                                  cudaMemcpyDeviceToHost, e->copy_stream));
         e->iteration += 1;
         e->nstored += 1;
@@ -1056,6 +1094,7 @@ int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t firs
 
 int lcf_ensemble_run_to_host(lcf_ensemble *e, int64_t nsteps, double *chain_host, double *log_prob_host) {
     if (!e) return fail(LCF_ERR_ARG, "null argument");
+    if (e->cw != e->W) return fail(LCF_ERR_ARG, "this rank stores only its own walkers: use lcf_ensemble_run_to_host_slice");
     return lcf_ensemble_run_to_host_slice(e, nsteps, 0, e->W, chain_host, log_prob_host);
 }
 
@@ -1131,28 +1170,34 @@ int lcf_ensemble_get_chain(lcf_ensemble *e, double *chain) {
     if (!e || !chain) return fail(LCF_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(e->p->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    if (e->nstored) CUDA_TRY(cudaMemcpy(chain, e->d_chain, sizeof(double) * e->nstored * e->W * e->D, cudaMemcpyDeviceToHost));
+    // [nstored][W][D] on the host; a rank of a shared ensemble fills the columns of its own walkers only
+    if (e->nstored)
+        CUDA_TRY(cudaMemcpy2D(chain + e->cfirst * e->D, sizeof(double) * e->W * e->D, e->d_chain, sizeof(double) * e->cw * e->D,
+                              sizeof(double) * e->cw * e->D, e->nstored, cudaMemcpyDeviceToHost));
     return 0;
 }
 int lcf_ensemble_get_log_prob(lcf_ensemble *e, double *log_prob) {
     if (!e || !log_prob) return fail(LCF_ERR_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(e->p->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    if (e->nstored) CUDA_TRY(cudaMemcpy(log_prob, e->d_lnp, sizeof(double) * e->nstored * e->W, cudaMemcpyDeviceToHost));
+    if (e->nstored)
+        CUDA_TRY(cudaMemcpy2D(log_prob + e->cfirst, sizeof(double) * e->W, e->d_lnp, sizeof(double) * e->cw, sizeof(double) * e->cw,
+                              e->nstored, cudaMemcpyDeviceToHost));
     return 0;
 }
 int lcf_ensemble_get_chain_slice(lcf_ensemble *e, int64_t first, int64_t count, double *chain, double *log_prob) {
     if (!e) return fail(LCF_ERR_ARG, "null argument");
-    if (first < 0 || count < 0 || first + count > e->W) return fail(LCF_ERR_ARG, "walker range out of bounds");
+    if (first < e->cfirst || count < 0 || first + count > e->cfirst + e->cw)
+        return fail(LCF_ERR_ARG, "walker range outside the walkers this rank stores");
     CUDA_TRY(cudaSetDevice(e->p->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!e->nstored || !count) return 0;
-    const size_t D = e->D;
+    const size_t D = e->D, rel = (size_t)(first - e->cfirst);
     if (chain)
-        CUDA_TRY(cudaMemcpy2D(chain, count * D * sizeof(double), e->d_chain + first * D, e->W * D * sizeof(double),
+        CUDA_TRY(cudaMemcpy2D(chain, count * D * sizeof(double), e->d_chain + rel * D, e->cw * D * sizeof(double),
                               count * D * sizeof(double), e->nstored, cudaMemcpyDeviceToHost));
     if (log_prob)
-        CUDA_TRY(cudaMemcpy2D(log_prob, count * sizeof(double), e->d_lnp + first, e->W * sizeof(double), count * sizeof(double),
+        CUDA_TRY(cudaMemcpy2D(log_prob, count * sizeof(double), e->d_lnp + rel, e->cw * sizeof(double), count * sizeof(double),
                               e->nstored, cudaMemcpyDeviceToHost));
     return 0;
 }
