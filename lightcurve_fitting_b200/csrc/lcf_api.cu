@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -255,6 +257,22 @@ size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxClus
 
 constexpr size_t kSmemMax = 227 * 1024;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and process-wide, and a later, smaller value LOWERS it: two live
+// problems that share an instantiation but need different amounts (a large UV / JWST bank next to a small one) would break each
+// other's cached launches.  Keep a high-water mark per kernel and only ever raise the limit.
+int ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void *, size_t> high;
+    if (bytes <= 40 * 1024) return 0;                     // below the 48 KB every kernel gets (static shared memory included)
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &h = high[kernel];
+    if (bytes > h) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        h = bytes;
+    }
+    return 0;
+}
+
 int build_tiles(lcf_problem *p, int l) {
     if (p->tiles_built[l]) return 0;
     const int ppt = 2 * (32 >> l);              // two points per lane
@@ -357,7 +375,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     for (int plain = 0; plain < 2; ++plain) {
         PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
         if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
-        if (bs.smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs.smem));
+        if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), bs.smem))) return rc;
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
@@ -421,10 +439,18 @@ int check_device() {
 template <typename R>
 int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale, Arena &arena) {
     const int F = d->nfilters, N = d->npoints;
-    // every filter padded to an even number of samples (pad: a = last a, w = 0): the kernels consume sample
-    // pairs and the TMA bulk copy moves multiples of 16 bytes
+    // Samples whose weight is exactly zero (transmission curves start and end with T = 0) contribute exactly nothing to the
+    // trapezoid sum, so they are left out of the device bank; every filter is then padded to an even number of samples
+    // (pad: a = last a, w = 0): the kernels consume sample pairs and the TMA bulk copy moves multiples of 16 bytes.
+    std::vector<std::vector<int>> keep(F);
     std::vector<int> foff(F + 1, 0);
-    for (int f = 0; f < F; ++f) foff[f + 1] = foff[f] + ((d->bank_offsets[f + 1] - d->bank_offsets[f] + 1) & ~1);
+    for (int f = 0; f < F; ++f) {
+        const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
+        for (int k = 0; k < n; ++k)
+            if (d->bank_w[b0 + k] != 0.) keep[f].push_back(b0 + k);
+        if (keep[f].empty()) keep[f].push_back(b0);            // an all-zero curve: one (zero-weight) sample
+        foff[f + 1] = foff[f] + (((int)keep[f].size() + 1) & ~1);
+    }
     const int ns_pad = foff[F];
     typedef typename Vec2<R>::type R2;
     typedef typename Vec4<R>::type R4;
@@ -432,11 +458,12 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
     std::vector<R4> bank(ns_pad / 2);                     // pair records (a0, a1, w0, w1)
     std::vector<int4> finfo(F);
     std::vector<R> kap(ns_pad, (R)0);
+    double kept = 0.;
     for (int f = 0; f < F; ++f) {
-        const int b0 = d->bank_offsets[f], n = d->bank_offsets[f + 1] - b0;
+        const int n = (int)keep[f].size();
         double mn = INFINITY, mx = 0.;
         for (int k = 0; k < foff[f + 1] - foff[f]; ++k) {
-            const int src = b0 + std::min(k, n - 1);
+            const int src = keep[f][std::min(k, n - 1)];
             const R a = (R)(d->bank_alpha[src] * kLog2e);
             const R w = (k < n) ? (R)(d->bank_w[src] * wfac) : (R)0;
             R4 &rec = bank[(foff[f] + k) >> 1];
@@ -451,6 +478,8 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
         memcpy(&bmx, &fmx, 4);
         finfo[f] = make_int4(foff[f] >> 1, (foff[f + 1] - foff[f]) >> 1, bmn, bmx);
     }
+    for (int i = 0; i < N; ++i) kept += (double)(foff[d->point_filter[i] + 1] - foff[d->point_filter[i]]);
+    p->mean_samples = kept / std::max(1, N);                // device samples per photometry point (launch-shape model)
     std::vector<R4> obs(N);
     for (int i = 0; i < N; ++i) {
         obs[i].x = (R)(d->y[i] / scale);
@@ -893,7 +922,7 @@ static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
     memset(&mv, 0, sizeof(mv));
     mv.coords = e->d_coords;
     mv.logp = e->d_logp;
-    mv.accepted = e->d_acc;
+    mv.accepted = store ? e->d_acc : nullptr;          // emcee counts accepted moves of stored steps only (Backend.save_step)
     mv.nanflag = e->d_nan;
     mv.W = e->W;
     mv.n0 = e->n0;
@@ -1490,7 +1519,7 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.init_logp = b->need_init_logp ? 1 : 0;
     ChainKernel k = (b->precision == LCF_PRECISION_FP32) ? chain_kernel_for<float>(b->model) : chain_kernel_for<double>(b->model);
     if (!k) return fail(LCF_ERR_ARG, "unknown model");
-    if (b->smem > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    { int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), b->smem); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     k<<<(unsigned)b->nprob, b->nw * 32, b->smem, b->stream>>>(B);
     CUDA_TRY(cudaGetLastError());

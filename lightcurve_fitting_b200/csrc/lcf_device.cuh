@@ -442,20 +442,94 @@ __device__ __forceinline__ void ex2_terms(float2 a, float2 i2, float2 &d, float2
     e = make_float2(Mth<float>::ex2(x.x), Mth<float>::ex2(x.y));
     d = WIEN ? __fadd2_rn(make_float2(-e.x, -e.y), make_float2(1.f, 1.f)) : __fadd2_rn(e, make_float2(-1.f, -1.f));
 }
+#ifndef LCF_RCP_ORDER
+#define LCF_RCP_ORDER 6
+#endif
+// 1/x for a positive normal float WITHOUT the XU pipe: integer-subtract seed (relative error e0 within +-5.05 %), then
+//   order 6 (default): r (1 + e0)(1 + e0^2 + e0^4) = r (1 + e0 + ... + e0^5): five FMA-pipe operations, dependency depth 4,
+//                      truncation 1.7e-8, max error with rounding 1.4e-7 (1 ulp, the accuracy of MUFU.RCP);
+//   order 8: three Newton steps, six dependent operations, 6e-8.
 __device__ __forceinline__ float rcp_newton(float x) {                   // x positive and normal
     float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
-    float e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
+    float e = fmaf(-x, r, 1.f);
+#if LCF_RCP_ORDER == 6
+    const float r1 = fmaf(r, e, r), e2 = e * e;
+    return fmaf(r1, fmaf(e2, e2, e2), r1);
+#else
+    r = fmaf(r, e, r);
     e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
     e = fmaf(-x, r, 1.f); r = fmaf(r, e, r);
     return r;
+#endif
 }
 __device__ __forceinline__ float2 rcp_newton2(float2 x) {
     float2 r = make_float2(__int_as_float(0x7EF311C7 - __float_as_int(x.x)), __int_as_float(0x7EF311C7 - __float_as_int(x.y)));
     const float2 one = make_float2(1.f, 1.f), nx = make_float2(-x.x, -x.y);
-    float2 e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
+    float2 e = __ffma2_rn(nx, r, one);
+#if LCF_RCP_ORDER == 6
+    const float2 r1 = __ffma2_rn(r, e, r), e2 = __fmul2_rn(e, e);
+    return __ffma2_rn(r1, __ffma2_rn(e2, e2, e2), r1);
+#else
+    r = __ffma2_rn(r, e, r);
     e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
     e = __ffma2_rn(nx, r, one); r = __ffma2_rn(r, e, r);
     return r;
+#endif
+}
+
+// 2^x on the FMA pipe (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2 (magic-number rounding), degree-5 minimax
+// polynomial of 2^f (relative error 1.8e-7 in FP32 Horner form: the accuracy of MUFU.EX2), n added into the exponent field
+// on the ALU pipe.  8 FMA-pipe operations + 2 ALU operations.  Valid for |x| <= 126 (callers clamp where x can leave it).
+#ifndef LCF_LOOP_POLY
+#define LCF_LOOP_POLY 0        // inner loops: 0 = every exponential on MUFU; 8 / 4 = one in eight / four on the FMA pipe
+#endif
+#ifndef LCF_FE_POLY
+#define LCF_FE_POLY 0          // front end: 1 = its exponentials on the FMA pipe (lg2 stays on MUFU)
+#endif
+__device__ __forceinline__ float ex2_fma(float x) {
+    const float magic = 12582912.f;                                      // 1.5 * 2^23
+    const float r = __fadd_rn(x, magic);
+    const float f = __fsub_rn(x, __fsub_rn(r, magic));
+    float p = 0.0013292921939864755f;
+    p = fmaf(p, f, 0.009671508334577084f);
+    p = fmaf(p, f, 0.05550636723637581f);
+    p = fmaf(p, f, 0.24022242426872253f);
+    p = fmaf(p, f, 0.6931470632553101f);
+    p = fmaf(p, f, 1.f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+__device__ __forceinline__ float2 ex2_fma2(float2 x) {
+    const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+    const float2 r = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(r, nmagic);
+    const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+    float2 p = make_float2(0.0013292921939864755f, 0.0013292921939864755f);
+    p = __ffma2_rn(p, f, make_float2(0.009671508334577084f, 0.009671508334577084f));
+    p = __ffma2_rn(p, f, make_float2(0.05550636723637581f, 0.05550636723637581f));
+    p = __ffma2_rn(p, f, make_float2(0.24022242426872253f, 0.24022242426872253f));
+    p = __ffma2_rn(p, f, make_float2(0.6931470632553101f, 0.6931470632553101f));
+    p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
+}
+// the same terms as ex2_terms with part of the exponentials on the FMA pipe: HOW = 1: lane y, HOW = 2: both lanes
+template <bool WIEN, int HOW>
+__device__ __forceinline__ void ex2_terms_mix(float2 a, float2 i2, float2 &d, float2 &e) {
+    float2 x = __fmul2_rn(a, i2);
+    if (WIEN) x = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));   // plain: callers keep every exponent in [1/16, 124]
+    if (HOW == 2) e = ex2_fma2(x);
+    else e = make_float2(Mth<float>::ex2(x.x), ex2_fma(x.y));
+    d = WIEN ? __fadd2_rn(make_float2(-e.x, -e.y), make_float2(1.f, 1.f)) : __fadd2_rn(e, make_float2(-1.f, -1.f));
+}
+template <bool WIEN>
+__device__ __forceinline__ void ex2_terms_last(float2 a, float2 i2, float2 &d, float2 &e) {   // the pair that may leave the XU pipe
+#if LCF_LOOP_POLY == 8
+    ex2_terms_mix<WIEN, 1>(a, i2, d, e);
+#elif LCF_LOOP_POLY == 4
+    ex2_terms_mix<WIEN, 2>(a, i2, d, e);
+#else
+    ex2_terms<WIEN>(a, i2, d, e);
+#endif
 }
 
 // (a) two blackbodies (points A, B of one walker) x the two samples of a pair record; two records per iteration.
@@ -484,7 +558,7 @@ __device__ __forceinline__ void planck_quad_f32(const float4 *__restrict__ b4, i
         }
         float2 dA0, dB0, dA1, dB1, eA0, eB0, eA1, eB1;            // d: denominators of (sample k0, sample k1); e: WIEN only
         ex2_terms<WIEN>(a0, iA2, dA0, eA0); ex2_terms<WIEN>(a0, iB2, dB0, eB0);
-        ex2_terms<WIEN>(a1, iA2, dA1, eA1); ex2_terms<WIEN>(a1, iB2, dB1, eB1);
+        ex2_terms<WIEN>(a1, iA2, dA1, eA1); ex2_terms_last<WIEN>(a1, iB2, dB1, eB1);
         const float2 p0 = __fmul2_rn(dA0, dB0), p1 = __fmul2_rn(dA1, dB1);                          // per sample: dA dB
         const float2 r = rcp_newton2(make_float2(p0.x * p0.y, p1.x * p1.y));                         // one per record
         const float2 t0 = __fmul2_rn(w0, __fmul2_rn(make_float2(r.x, r.x), make_float2(p0.y, p0.x)));  // w/(dA dB)
@@ -524,7 +598,7 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
         const float2 x = make_float2(s.x, s.y), w = make_float2(s.z, s.w);
         float2 dA, dAs, dB, dBs, eA, eAs, eB, eBs;
         ex2_terms<WIEN>(x, iA2, dA, eA); ex2_terms<WIEN>(x, iAs2, dAs, eAs);
-        ex2_terms<WIEN>(x, iB2, dB, eB); ex2_terms<WIEN>(x, iBs2, dBs, eBs);
+        ex2_terms<WIEN>(x, iB2, dB, eB); ex2_terms_last<WIEN>(x, iBs2, dBs, eBs);
         const float2 pA = __fmul2_rn(dA, dAs), pB = __fmul2_rn(dB, dBs);
         const float2 r = rcp_newton2(__fmul2_rn(pA, pB));
         const float2 tA = __fmul2_rn(w, __fmul2_rn(r, pB)), tB = __fmul2_rn(w, __fmul2_rn(r, pA));
@@ -640,6 +714,14 @@ __device__ __forceinline__ R sifto_eval(const ProblemDev &P, const typename Vec4
     return (v != v) ? (R)0 : v;
 }
 
+// exponential of the front end: FP32 builds with LCF_FE_POLY keep it off the XU pipe (arguments clamped to the polynomial's range:
+// 2^-126 stands for an underflow to zero, 2^126 for an overflow whose only use is exp(-huge)); a NaN argument must be
+// handled by the caller (the polynomial does not propagate it)
+template <typename R> __device__ __forceinline__ R fe_ex2(R x) { return Mth<R>::ex2(x); }
+#if LCF_FE_POLY
+template <> __device__ __forceinline__ float fe_ex2<float>(float x) { return ex2_fma(fminf(fmaxf(x, -126.f), 126.f)); }
+#endif
+
 // Front end of one (walker, point): the model value is
 //      y = amp * S(invT) + add                      (ShockCooling4: min(amp S(invT), amp 0.74^-4 S(invT/0.74)))
 // with S the Planck x transmission sum of the point's filter.  invT = 0 encodes "no blackbody": y = amp + add, where amp
@@ -672,9 +754,9 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
     if (MODEL >= 1 && MODEL <= 3) {
         // 4 transcendentals: lg2(t), (a t/t_tr)^alpha, L/T^4, 1/T
         const R epsT = kconst<R>(P, 0), epsA = kconst<R>(P, 1), alpha = kconst<R>(P, 2);
-        const R pw_ = (w.wc[2] > -M::inf()) ? M::ex2(alpha * (lt + w.wc[2])) : (R)0;
-        a = w.wc[5] * M::ex2(epsA * lt - (R)kLog2e * pw_);
-        i = w.wc[4] * M::ex2(-epsT * lt);
+        const R pw_ = (w.wc[2] > -M::inf()) ? fe_ex2<R>(alpha * (lt + w.wc[2])) : (R)0;
+        a = w.wc[5] * fe_ex2<R>(epsA * lt - (R)kLog2e * pw_);
+        i = w.wc[4] * fe_ex2<R>(-epsT * lt);
         if (!(w.wc[4] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : w.wc[1] * (R)0; }   // T <= 0
         if (w.wc[1] < (R)0) { i = (R)0; a = M::nan(); }                       // L < 0: L ** 0.5 is NaN (models.py:268)
         if (!pos) { i = (R)0; a = (w.wc[0] * w.wc[1]) * (R)0; }                // t <= t_exp: zero (NaN constants propagate)
@@ -682,11 +764,12 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
         // 6 transcendentals: lg2(t), suppression (2), two powers of ttilde for L, one for 1/T (branch selected)
         const R A = kconst<R>(P, 0), alpha = kconst<R>(P, 1);
         const R ltt = lt + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
-        const R sup = (w.wc[3] > -M::inf()) ? M::ex2((R)(-kLog2e) * M::ex2(alpha * (lt + w.wc[3]))) : (R)1;
-        const R L = w.wc[1] * (M::ex2((R)(-4. / 3.) * ltt) + A * sup * M::ex2((R)(-0.17) * ltt));
+        const R sup = (w.wc[3] > -M::inf()) ? fe_ex2<R>((R)(-kLog2e) * fe_ex2<R>(alpha * (lt + w.wc[3]))) : (R)1;
+        const R L = w.wc[1] * (fe_ex2<R>((R)(-4. / 3.) * ltt) + A * sup * fe_ex2<R>((R)(-0.17) * ltt));
         // T = T_br min(0.97 u^-1/3, u^-0.45): the first branch is the smaller one for log2(u) < -log2(0.97)/(0.45-1/3)
         const bool early = ltt < (R)0.37665701296944757;
-        i = (early ? w.wc[4] : w.wc[5]) * M::ex2((early ? (R)(1. / 3.) : (R)0.45) * ltt);
+        i = (early ? w.wc[4] : w.wc[5]) * fe_ex2<R>((early ? (R)(1. / 3.) : (R)0.45) * ltt);
+        if (LCF_FE_POLY && sizeof(R) == 4) i = (w.wc[2] != w.wc[2]) ? M::nan() : i;   // invalid t_br: the polynomial does not propagate the NaN
         const R i2 = i * i;
         a = L * (i2 * i2);
         if (!(i > (R)0)) { a = (i != i) ? M::nan() : L * (R)0; i = (R)0; }
@@ -694,8 +777,8 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
         if (!pos) { a = (w.wc[0] * w.wc[1]) * (R)0; i = (R)0; }
     } else {
         // Kasen, models.py:752-754: 3 transcendentals, then the SiFTO template and the per-filter factors
-        i = w.wc[8] * M::ex2((R)(74. / 144.) * lt);
-        a = w.wc[1] * M::ex2((R)(14. / 9.) * lt);               // = R^2 here
+        i = w.wc[8] * fe_ex2<R>((R)(74. / 144.) * lt);
+        a = w.wc[1] * fe_ex2<R>((R)(14. / 9.) * lt);               // = R^2 here
         if (!(w.wc[8] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : (R)0; }
         if (!pos) { i = (R)0; a = (R)0; }
         const int f = P.pfilt[p];
@@ -1192,6 +1275,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
+    if (csize > 1) cluster_sync_all();                     // every CTA of the cluster is running before its shared memory is written remotely
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
     const long long nclusters = cluster_count_x();
     if (Mv.npeers) peers_wait(Mv);

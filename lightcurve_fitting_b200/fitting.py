@@ -1,9 +1,10 @@
 """``lightcurve_mcmc`` -- drop-in for the reference driver (fitting.py:16-168).
 
-Same positional/keyword signature and validation; additive keywords: ``precision`` ('fp64' default =
-reference arithmetic, 'fp32' = throughput mode) and ``seed``.  The ``log_posterior`` closure and the emcee
-sampler of the reference (fitting.py:121-145) are replaced by a :class:`DeviceProblem` and the
-device-resident :class:`EnsembleSampler`.
+Same signature, same error messages, same sequence of global-RNG draws (one ``np.random.rand(nwalkers, ndim)`` for the
+starting positions, fitting.py:132); additive keywords ``precision`` ('fp64' default = reference arithmetic, 'fp32' =
+throughput mode) and ``seed``.  The reference's ``log_posterior`` closure and emcee sampler (fitting.py:121-145) are a
+:class:`DeviceProblem` and the device-resident :class:`EnsembleSampler` here; the optional burn-in / chain figure is
+drawn by :mod:`lightcurve_fitting_b200.plotting` (needs matplotlib; presentation is outside the hot path).
 """
 import warnings
 import numpy as np
@@ -14,6 +15,9 @@ from .sampler import EnsembleSampler
 PRIOR_WARNING = 'The p_max/p_min keywords are deprecated. Use the priors keyword instead.'
 MODEL_KWARGS_WARNING = 'The model_kwargs keyword is deprecated. These are now included in the model intialization.'
 
+# what each output quantity needs from the light curve before it can be fitted (fitting.py:68-72)
+_PREPARE = {'flux': ('calcFlux',), 'lum': ('calcAbsMag', 'calcLum')}
+
 
 def build_problem(lc, model, priors, use_sigma=False, sigma_type='relative', precision=None):
     """The device counterpart of the ``log_posterior`` closure (fitting.py:121-128)."""
@@ -21,6 +25,36 @@ def build_problem(lc, model, priors, use_sigma=False, sigma_type='relative', pre
     return model._device_problem(lc['MJD'].data, lc['filter'].data, lc[q].data, lc['d' + q].data,
                                  model._nmodel + (1 if use_sigma else 0), use_sigma=use_sigma, sigma_type=sigma_type,
                                  priors=priors, precision=precision or model.precision)
+
+
+def _vector(value, ndim, wrong_length):
+    """``value`` as a float vector of length ``ndim``; ``wrong_length`` is the message of the reference's exception."""
+    if len(value) != ndim:             # len(None) raises TypeError, as the reference does for a missing p_up
+        raise Exception(wrong_length)
+    return np.array(value, float)
+
+
+def _start_box(ndim, p_min, p_max, p_lo, p_up):
+    """Prior box (deprecated ``p_min``/``p_max`` keywords) and start box of fitting.py:81-106, as four vectors."""
+    box = {}
+    for key, value, fill in (('p_min', p_min, -np.inf), ('p_max', p_max, np.inf)):
+        if value is None:
+            box[key] = np.full(ndim, fill)
+        else:
+            box[key] = _vector(value, ndim, PRIOR_WARNING)
+            warnings.warn(PRIOR_WARNING)
+    box['p_lo'] = box['p_min'] if p_lo is None else _vector(p_lo, ndim, 'p_lo must have length {:d}'.format(ndim))
+    box['p_up'] = _vector(p_up, ndim, 'p_up must have length {:d}'.format(ndim))
+    return box
+
+
+def _check_start_inside_priors(names, priors, p_lo, p_up):
+    """fitting.py:115-119: the start box must lie inside every prior's support."""
+    for param, prior, lo, up in zip(names, priors, p_lo, p_up):
+        for edge, value, limit, outside in (('p_lo', lo, prior.p_min, lo < prior.p_min), ('p_up', up, prior.p_max, up > prior.p_max)):
+            if outside:
+                raise Exception('starting guess for {} ({} = {}) is outside prior ({} = {})'.format(
+                    param, edge, value, 'p_min' if edge == 'p_lo' else 'p_max', limit))
 
 
 def lightcurve_mcmc(lc, model, priors=None, p_min=None, p_max=None, p_lo=None, p_up=None,
@@ -34,96 +68,37 @@ def lightcurve_mcmc(lc, model, priors=None, p_min=None, p_max=None, p_lo=None, p
     """
     if model_kwargs is not None:
         raise Exception(MODEL_KWARGS_WARNING)
-
-    if model.output_quantity == 'flux':
-        lc.calcFlux()
-    elif model.output_quantity == 'lum':
-        lc.calcAbsMag()
-        lc.calcLum()
-
-    if use_sigma and model.input_names[-1] != '\\sigma':
+    for method in _PREPARE.get(model.output_quantity, ()):
+        getattr(lc, method)()
+    if use_sigma and model.input_names[-1] != '\\sigma':       # fitting.py:74-76 (class-level lists)
         model.input_names.append('\\sigma')
         model.units.append('')
-
     ndim = model.nparams
 
-    # DEPRECATED
-    if p_min is None:
-        p_min = np.tile(-np.inf, ndim)
-    elif len(p_min) == ndim:
-        p_min = np.array(p_min, float)
-        warnings.warn(PRIOR_WARNING)
-    else:
-        raise Exception(PRIOR_WARNING)
-
-    # DEPRECATED
-    if p_max is None:
-        p_max = np.tile(np.inf, ndim)
-    elif len(p_max) == ndim:
-        p_max = np.array(p_max, float)
-        warnings.warn(PRIOR_WARNING)
-    else:
-        raise Exception(PRIOR_WARNING)
-
-    if p_lo is None:
-        p_lo = p_min
-    elif len(p_lo) == ndim:
-        p_lo = np.array(p_lo, float)
-    else:
-        raise Exception('p_lo must have length {:d}'.format(ndim))
-
-    if len(p_up) == ndim:
-        p_up = np.array(p_up, float)
-    else:
-        raise Exception('p_up must have length {:d}'.format(ndim))
-
+    box = _start_box(ndim, p_min, p_max, p_lo, p_up)
     if priors is None:
-        priors = [UniformPrior(p0, p1) for p0, p1 in zip(p_min, p_max)]
+        priors = [UniformPrior(lo, hi) for lo, hi in zip(box['p_min'], box['p_max'])]
     elif len(priors) != ndim:
         raise Exception('priors must have length {:d}'.format(ndim))
-
-    for param, prior, p0, p1 in zip(model.input_names, priors, p_lo, p_up):
-        if p0 < prior.p_min:
-            raise Exception(f'starting guess for {param} (p_lo = {p0}) is outside prior (p_min = {prior.p_min})')
-        if p1 > prior.p_max:
-            raise Exception(f'starting guess for {param} (p_up = {p1}) is outside prior (p_max = {prior.p_max})')
+    _check_start_inside_priors(model.input_names, priors, box['p_lo'], box['p_up'])
 
     problem = build_problem(lc, model, priors, use_sigma=use_sigma, sigma_type=sigma_type, precision=precision)
     sampler = EnsembleSampler(nwalkers, ndim, problem, seed=seed)
-
-    starting_guesses = np.random.rand(nwalkers, ndim) * (p_up - p_lo) + p_lo
+    starting_guesses = np.random.rand(nwalkers, ndim) * (box['p_up'] - box['p_lo']) + box['p_lo']
     pos, _, _ = sampler.run_mcmc(starting_guesses, nsteps_burnin)
 
+    figure = None
     if show or save_plot_as:
-        import matplotlib.pyplot as plt
-        fig, ax = plt.subplots(ndim, 2, figsize=(12., 2. * ndim))
-        ax1 = ax[:, 0]
-        for i in range(ndim):
-            ax1[i].plot(sampler.chain[:, :, i].T, 'k', alpha=0.2)
-            ax1[i].set_ylabel(model.axis_labels[i])
-        ax1[0].set_title('During Burn In')
-        ax1[-1].set_xlabel('Step Number')
+        from . import plotting
+        figure = plotting.ChainFigure(model.axis_labels[:ndim])
+        figure.draw(0, sampler.chain, 'During Burn In')
 
     sampler.reset()
     sampler.run_mcmc(None, nsteps, skip_initial_state_check=True)
     if save_sampler_as:
         np.save(save_sampler_as, sampler.flatchain)
         print('saving sampler.flatchain as ' + save_sampler_as)
-
-    if show or save_plot_as:
-        ax2 = ax[:, 1]
-        for i in range(ndim):
-            ax2[i].plot(sampler.chain[:, :, i].T, 'k', alpha=0.2)
-            ax2[i].set_ylabel(model.axis_labels[i])
-            ax2[i].yaxis.set_label_position('right')
-            ax2[i].yaxis.tick_right()
-        ax2[0].set_title('After Burn In')
-        ax2[-1].set_xlabel('Step Number')
-        fig.tight_layout()
-        if save_plot_as:
-            print('saving chain plot as ' + save_plot_as)
-            fig.savefig(save_plot_as)
-        if show:
-            plt.show()
-
+    if figure is not None:
+        figure.draw(1, sampler.chain, 'After Burn In')
+        figure.finish(save_plot_as, show)
     return sampler

@@ -10,6 +10,7 @@ Reference map: ``Model`` models.py:51-136, ``BaseShockCooling`` :139-298, ``Shoc
 ``blackbody_to_filters`` :1131.
 """
 import os
+import hashlib
 import numpy as np
 
 from . import constants as K
@@ -178,11 +179,18 @@ class Model:
         """The log-likelihood of the model given the data in ``lc`` and parameters ``p`` (models.py:93-136)."""
         if sigma_type not in ('relative', 'absolute'):
             raise Exception('sigma_type must either be "relative" or "absolute"')
-        key = (id(lc), len(lc), bool(use_sigma), sigma_type, self.precision, self.z)
+        # The device problem is cached on the CONTENT of the columns it was packed from (the reference re-reads lc on
+        # every call, so an edited column, a recomputed lum or another table of the same length must all be seen).
+        t, f = lc['MJD'].data, lc['filter'].data
+        y, dy = lc[self.output_quantity].data, lc['d' + self.output_quantity].data
+        h = hashlib.blake2b(digest_size=16)
+        for a in (t, y, dy):
+            h.update(np.ascontiguousarray(a, float).tobytes())
+        h.update('\0'.join(getattr(flt, 'name', str(flt)) for flt in f).encode())
+        key = (h.digest(), bool(use_sigma), sigma_type, self.precision, self.z)
         prob = self._ll_cache.get(key)
         if prob is None:
-            prob = self._device_problem(lc['MJD'].data, lc['filter'].data, lc[self.output_quantity].data,
-                                        lc['d' + self.output_quantity].data, self._nmodel + (1 if use_sigma else 0),
+            prob = self._device_problem(t, f, y, dy, self._nmodel + (1 if use_sigma else 0),
                                         use_sigma=use_sigma, sigma_type=sigma_type)
             self._ll_cache = {key: prob}
         p = np.asarray(p, float)

@@ -36,6 +36,18 @@ class State:
         return (self.coords, self.log_prob, self.random_state)[i]
 
 
+def seed_from_global_rng():
+    """Key for the device RNG derived from numpy's global legacy generator WITHOUT advancing it: emcee copies the global
+    state into a private RandomState, so ``np.random.seed(s)`` makes a fit reproducible and the
+    starting positions drawn afterwards (fitting.py:132) see the same stream as in the reference."""
+    import hashlib
+    kind, keys, pos, has_gauss, cached = np.random.get_state()
+    h = hashlib.blake2b(digest_size=8)
+    h.update(np.ascontiguousarray(keys).tobytes())
+    h.update(repr((kind, int(pos), int(has_gauss), float(cached))).encode())
+    return int.from_bytes(h.digest(), 'little') >> 1
+
+
 def walkers_independent(coords):
     """emcee's initial-state check: finite, non-degenerate, condition number <= 1e8."""
     if not np.all(np.isfinite(coords)):
@@ -58,8 +70,8 @@ class EnsembleSampler:
     problem : DeviceProblem
         Replaces emcee's ``log_prob_fn``: the log-posterior is evaluated inside the kernels.
     seed : int, optional
-        Key of the counter-based device RNG.  Default: drawn from numpy's global legacy RNG, so that
-        ``np.random.seed(s)`` before a fit makes it reproducible, as with the reference.
+        Key of the counter-based device RNG.  Default: a hash of numpy's global legacy RNG state (not advanced), so
+        that ``np.random.seed(s)`` before a fit makes it reproducible, as with the reference.
     rank, world : int
         Shard one ensemble over ``world`` GPUs (see ``parallel.py``).
     """
@@ -69,7 +81,7 @@ class EnsembleSampler:
             raise ValueError('ndim does not match the problem')
         self.nwalkers, self.ndim, self.problem = int(nwalkers), int(ndim), problem
         if seed is None:
-            seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + int(np.random.randint(0, 2 ** 31 - 1))
+            seed = seed_from_global_rng()
         self.seed = int(seed)
         h = C.c_void_p()
         check(lib().lcf_ensemble_create(problem.handle, self.nwalkers, C.c_uint64(self.seed), rank, world, C.byref(h)))

@@ -1,4 +1,4 @@
-"""Generate golden vectors by running the REFERENCE's own code (models.py, filters.py, fitting.py).
+"""Generate golden vectors by running the REFERENCE's own code (models.py, filters.py, fitting.py, bolometric.py).
 
 Run in the authoring container only (needs /root/reference):
 
@@ -27,6 +27,11 @@ warnings.simplefilter('ignore')
 import lightcurve_fitting.models as RM      # noqa: E402  (the reference)
 import lightcurve_fitting.filters as RF     # noqa: E402
 import lightcurve_fitting.fitting as RFit   # noqa: E402
+import lightcurve_fitting.bolometric as RB  # noqa: E402
+
+# spectrum_mcmc always ends by drawing a corner plot (bolometric.py:183-188): presentation, out of scope;
+# everything before it -- the log_posterior closure and the emcee driver -- is the reference's own code
+RB.spectrum_corner = lambda *a, **k: None
 
 
 class Col(np.ndarray):
@@ -51,6 +56,9 @@ class MiniLC:
 
     def __getitem__(self, k):
         return Col(self.cols[k])
+
+    def __len__(self):
+        return len(next(iter(self.cols.values())))
 
     def where(self, filter=None):
         f = RF.filtdict[filter] if isinstance(filter, str) else filter
@@ -208,6 +216,76 @@ def main():
     G['mcmc_sigma/flatchain'] = s2.flatchain
     G['mcmc_sigma/lnprob'] = s2.get_log_prob()
     G['mcmc_sigma/nparams_after'] = np.array(m2.nparams)
+
+    # ---- bolometric.py: pseudo, stefan_boltzmann, median_and_unc, blackbody_lstsq, spectrum_mcmc ----------------------
+    Tp = np.array([4., 6., 9., 11., 14., 18., 25., 33., 47., 60., 85., 2.])
+    Rp = np.array([10., 3., 2.5, 1.5, 1.2, 1., 0.7, 0.5, 0.4, 0.3, 0.2, 30.])
+    G['bolo/pseudo/T'], G['bolo/pseudo/R'] = Tp, Rp
+    G['bolo/pseudo/z0'] = RB.pseudo(Tp, Rp, 0.)
+    G['bolo/pseudo/z'] = RB.pseudo(Tp, Rp, 0.023)
+    G['bolo/pseudo/cut'] = RB.pseudo(Tp, Rp, 0.01, cutoff_freq=800.)
+    G['bolo/pseudo/scalar'] = np.array(RB.pseudo(12., 3., 0.002))
+    G['bolo/pseudo/BtoV'] = RB.pseudo(Tp, Rp, 0.002, filter0=RF.filtdict['V'], filter1=RF.filtdict['B'])
+    G['bolo/sigma_sb'] = np.array(float(RB.sigma_sb))
+    dT, dR, cTR = 0.07 * Tp, 0.05 * Rp, -0.6 * (0.07 * Tp) * (0.05 * Rp)
+    G['bolo/sb/dT'], G['bolo/sb/dR'], G['bolo/sb/cov'] = dT, dR, cTR
+    G['bolo/sb/lum'] = RB.stefan_boltzmann(Tp, Rp)
+    lum, dlum = RB.stefan_boltzmann(Tp, Rp, dT, dR, cTR)
+    G['bolo/sb/lum2'], G['bolo/sb/dlum'] = lum, dlum
+    x1 = rng.lognormal(1., 0.6, 1000)
+    x2 = rng.normal(size=(777, 3)) * np.array([1., 5., 0.1]) + np.array([10., -3., 0.])
+    G['bolo/mu/x1'], G['bolo/mu/x2'] = x1, x2
+    G['bolo/mu/out1'] = np.array(RB.median_and_unc(x1))
+    G['bolo/mu/out2'] = np.array(RB.median_and_unc(x2))
+    G['bolo/mu/out1_100'] = np.array(RB.median_and_unc(x1, 100.))
+
+    pool = ['U', 'B', 'V', 'g', 'r', 'i', 'R', 'I', '0', 'UVW1', 'z']
+    z_b = 0.002
+
+    def sed(nf, T, R, err, cutoff=np.inf):
+        names = list(rng.choice(pool, nf, replace=False))
+        filt = rfilters(names)
+        lum = RM.blackbody_to_filters(filt, np.full(nf, T), np.full(nf, R), z=z_b, cutoff_freq=cutoff)
+        lum = lum * (1. + err * rng.normal(size=nf))
+        freq = np.array([float(f.freq_eff.value) for f in filt])
+        return names, MiniLC(MJD=np.full(nf, 58000.25), filter=filt, lum=lum, dlum=err * np.abs(lum), freq=freq)
+
+    off, names_all, freq_all, lum_all, res = [0], [], [], [], []
+    for k in range(24):
+        nf = int(rng.integers(2, 10))
+        T, R = rng.uniform(4., 40.), np.exp(rng.uniform(np.log(0.3), np.log(30.)))
+        cutoff = 900. if k % 6 == 5 else np.inf
+        names, ep = sed(nf, T, R, 0.05, cutoff)
+        kw = {'cutoff_freq': cutoff}
+        if k % 8 == 7:
+            kw.update(T_range=(1., 12.), R_range=(0.01, 1000.))        # a bound-hitting fit
+        out = RB.blackbody_lstsq(ep, z_b, **kw)
+        names_all += names
+        freq_all += list(ep['freq'].data)
+        lum_all += list(ep['lum'].data)
+        off.append(off[-1] + nf)
+        res.append(list(out) + [cutoff, kw.get('T_range', (1., 100.))[1]])
+    G['bolo/lstsq/offsets'], G['bolo/lstsq/filters'] = np.array(off), np.array(names_all)
+    G['bolo/lstsq/freq'], G['bolo/lstsq/lum'] = np.array(freq_all), np.array(lum_all)
+    G['bolo/lstsq/out'] = np.array(res)          # temp, radius, dtemp, drad, lum, dlum, L_opt, cutoff_freq, T_max
+    G['bolo/lstsq/z'] = np.array(z_b)
+
+    # spectrum_mcmc: the reference's closure (bolometric.py:154-164) and driver (:166-174) on the emcee stand-in
+    for tag, use_sigma, sigma_type, cutoff, nf in (('bolo/mcmc', False, 'relative', np.inf, 6),
+                                                   ('bolo/mcmc_sigma', True, 'absolute', 1000., 4)):
+        names, ep = sed(nf, 12., 2.5, 0.06, cutoff)
+        priors = [RM.UniformPrior(1., 100.), RM.LogUniformPrior(0.01, 1000.)] + ([RM.GaussianPrior(0., 10.)] if use_sigma else [])
+        sg = rng.normal(size=(10, 2)) * 0.5 + np.array([12., 2.5])
+        if use_sigma:
+            sg = np.append(sg, np.abs(rng.normal(size=(10, 1))), axis=1)
+        np.random.seed(4242)
+        smp = RB.spectrum_mcmc(RM.planck_fast, ep, priors, sg, z=z_b, spectrum_kwargs={'cutoff_freq': cutoff}, outpath='/tmp/lcf_golden_out',
+                               nwalkers=10, burnin_steps=12, steps=9, use_sigma=use_sigma, sigma_type=sigma_type)
+        G[tag + '/filters'], G[tag + '/lum'], G[tag + '/dlum'] = np.array(names), ep['lum'].data, ep['dlum'].data
+        G[tag + '/start'], G[tag + '/cutoff'] = sg, np.array(cutoff)
+        G[tag + '/flatchain'] = smp.flatchain
+        G[tag + '/lnprob'] = smp.get_log_prob()
+        G[tag + '/acceptance'] = smp.acceptance_fraction
 
     out = os.path.join(HERE, 'reference_golden.npz')
     np.savez_compressed(out, **G)
