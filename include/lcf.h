@@ -146,6 +146,11 @@ void lcf_ensemble_destroy(lcf_ensemble *e);
 /* sampler.run_mcmc(initial, ...) first evaluates log_prob(initial): coords[nwalkers][ndim];
    log_prob may be NULL (computed on device).  Returns LCF_ERR_NAN like emcee.              */
 int  lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *log_prob);
+/* Shared ensemble (world > 1): this rank's own walkers only, logical [first, first + count) = the range
+   lcf_ensemble_device_view reports (2 * own_begin, 2 * own_count); [count][ndim].  Uploads them, evaluates their
+   log-posteriors and, with the fused exchange attached, stores rows + log-probabilities into every peer's replica over NVLink.
+   Callers put one barrier between this call (on all ranks) and the first step.  Same checks as lcf_ensemble_set_state. */
+int  lcf_ensemble_set_state_slice(lcf_ensemble *e, int64_t first, int64_t count, const double *coords);
 int  lcf_ensemble_get_state(lcf_ensemble *e, double *coords, double *log_prob);
 /* sampler.reset(): forget the stored chain and acceptance counts, keep the position.       */
 int  lcf_ensemble_reset(lcf_ensemble *e);
@@ -223,6 +228,22 @@ int  lcf_batch_get_accepted(lcf_batch *b, int64_t *accepted /* [nproblems][nwalk
 int  lcf_batch_get_status(lcf_batch *b, int32_t *status /* [nproblems]: 0 ok, LCF_ERR_NAN */);
 int  lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches);
 
+/* calculate_bolometric at survey scale (bolometric.py:735-798).
+   lcf_sed_batch_create: every SED epoch of a table as one batch, from flat arrays: epoch e owns points [offsets[e], offsets[e+1]),
+   point_filter indexes the shared packed bank (bank_offsets[nfilters+1], bank_alpha, bank_w as in lcf_problem_desc); model =
+   LCF_MODEL_BLACKBODY_SED (the spectrum_mcmc closure, bolometric.py:154-164), priors / use_sigma / sigma_type common to all
+   epochs.  The batch owns the per-epoch problems; their device arrays share one allocation and one host-to-device copy.
+   lcf_batch_summary: after lcf_batch_run, per epoch the median and the +- perc_contained/2 percentile distances
+   (median_and_unc, bolometric.py:456-480) of T, R, L_bol = stefan_boltzmann(T, R) (:422-447) and L_pseudo = pseudo(T, R)
+   (:32-59; `comb` = a one-point LCF_MODEL_BLACKBODY_SED problem whose single filter is the 1-THz comb) over every stored
+   sample, computed on the HBM-resident chain: out[nproblems][4][3] = (median, median - lower, upper - median).                  */
+int  lcf_sed_batch_create(int64_t nepochs, const int32_t *offsets, const int32_t *point_filter, const double *y, const double *dy,
+                          int32_t nfilters, const int32_t *bank_offsets, const double *bank_alpha, const double *bank_w, int32_t ndim,
+                          int32_t use_sigma, int32_t sigma_type, const int32_t *prior_kind, const double *prior_min,
+                          const double *prior_max, const double *prior_mean, const double *prior_std, int32_t precision,
+                          int64_t nwalkers, uint64_t seed, lcf_batch **out);
+int  lcf_batch_summary(lcf_batch *b, lcf_problem *comb, double sigma_sb, double perc_contained, double *out);
+
 /* Batched box-bounded least-squares fits of planck_fast(nu; T, R) to SEDs, one thread per epoch (replaces the per-epoch
    scipy.optimize.curve_fit of bolometric.py:483-531).  offsets[nepochs+1] delimit each epoch's points in nu [THz, already
    multiplied by (1+z)] and lum; c1, c2 are the constants of models.py:1101-1102; p0/lower/upper are (T, R).
@@ -230,6 +251,13 @@ int  lcf_batch_last_timing(lcf_batch *b, double *ms, int64_t *launches);
 int  lcf_blackbody_lstsq_batch(int64_t nepochs, const int32_t *offsets, const double *nu, const double *lum, double c1, double c2,
                                double cutoff_freq, const double *p0, const double *lower, const double *upper, double *popt,
                                double *pcov, int32_t *status);
+
+/* The launch the library last issued for this problem (tests assert which kernel a workload ran on): walkers per CTA,
+   warps per CTA, cluster size, grid size in CTAs, and the kernel instantiation: 0 = generic k_pass<MODEL, real, -1, false>,
+   1 = k_pass<MODEL, real, 5, false> (32 walkers per CTA at compile time), 2 = k_pass<MODEL, real, 5, true> (32 walkers, no
+   intrinsic-scatter / model-grid branches), 3 = k_ring (persistent cooperative kernel for one small ensemble).          */
+int  lcf_problem_last_launch(lcf_problem *p, int *walkers_per_cta, int *warps_per_cta, int *cluster_size, int64_t *grid,
+                             int *kernel_variant);
 
 /* launch-shape overrides for tuning (0 = heuristic): walkers per CTA (power of two <= 32)
    and warps per CTA.                                                                       */

@@ -59,12 +59,15 @@ SYMBOLS = [
     ('lcf_ensemble_exchange_view', C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int)]),
     ('lcf_problem_create', C.c_int, [C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     ('lcf_problem_destroy', None, [_vp]),
+    ('lcf_problem_last_launch', C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int)]),
     ('lcf_model_eval', C.c_int, [_vp, C.c_int64, _pd, _pd]),
     ('lcf_log_likelihood', C.c_int, [_vp, C.c_int64, _pd, _pd]),
     ('lcf_log_posterior', C.c_int, [_vp, C.c_int64, _pd, _pd, C.POINTER(C.c_int64)]),
     ('lcf_ensemble_create', C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int, C.c_int, C.POINTER(_vp)]),
     ('lcf_ensemble_destroy', None, [_vp]),
     ('lcf_ensemble_set_state', C.c_int, [_vp, _pd, _pd]),
+    ('lcf_ensemble_set_state_slice', C.c_int, [_vp, C.c_int64, C.c_int64, _pd]),
     ('lcf_ensemble_get_state', C.c_int, [_vp, _pd, _pd]),
     ('lcf_ensemble_reset', C.c_int, [_vp]),
     ('lcf_ensemble_run', C.c_int, [_vp, C.c_int64, C.c_int]),
@@ -93,6 +96,9 @@ SYMBOLS = [
     ('lcf_batch_get_accepted', C.c_int, [_vp, C.POINTER(C.c_int64)]),
     ('lcf_batch_get_status', C.c_int, [_vp, _pi]),
     ('lcf_batch_last_timing', C.c_int, [_vp, _pd, C.POINTER(C.c_int64)]),
+    ('lcf_sed_batch_create', C.c_int, [C.c_int64, _pi, _pi, _pd, _pd, C.c_int32, _pi, _pd, _pd, C.c_int32, C.c_int32, C.c_int32,
+                                       _pi, _pd, _pd, _pd, _pd, C.c_int32, C.c_int64, C.c_uint64, C.POINTER(_vp)]),
+    ('lcf_batch_summary', C.c_int, [_vp, _vp, C.c_double, C.c_double, _pd]),
 ]
 
 

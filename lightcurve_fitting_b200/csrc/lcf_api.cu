@@ -93,8 +93,11 @@ struct Arena {
         CUDA_TRY(cudaMalloc(&d, std::max<size_t>(host.size(), 16)));
         allocs.push_back(d);
         CUDA_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
-        for (auto &s : slots) *s.first = reinterpret_cast<const unsigned char *>(d) + s.second;
+        patch(d);
         return 0;
+    }
+    void patch(const void *base) {
+        for (auto &s : slots) *s.first = reinterpret_cast<const unsigned char *>(base) + s.second;
     }
 };
 
@@ -124,13 +127,16 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     TileDev tiles[6];                           // per wpb_log2
     bool tiles_built[6] = {false, false, false, false, false, false};
-    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1; size_t smem = 0; } shape_cache;
+    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1; size_t smem = 0; double cost = 0.; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
+    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1; long long grid = 0; } last_launch;   // lcf_problem_last_launch
     double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
     int *d_eval_nan = nullptr;
     size_t eval_q_cap = 0, eval_out_cap = 0;
     int device = 0;
+    Arena *pending = nullptr;                   // device arrays not uploaded yet (problems of a batch share ONE allocation and copy)
     ~lcf_problem() {
+        delete pending;
         for (void *p : allocs) cudaFree(p);
         cudaFree(d_eval_q); cudaFree(d_eval_out); cudaFree(d_eval_nan);
     }
@@ -165,9 +171,11 @@ struct lcf_ensemble {
     int peer_rank[kMaxPeers] = {0};
     std::vector<void *> ipc_opened;             // mappings to close
     unsigned int epoch = 0;                     // fused half-steps launched so far (identical on every rank)
+    unsigned int *d_ring_bar = nullptr;         // k_ring: arrival counter + generation word
+    int ring_ok = -1, ring_key = -1;            // -1 unknown, 0 the grid does not fit, 1 usable (cached per launch shape)
     ~lcf_ensemble() {
         for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
-        cudaFree(d_flags);
+        cudaFree(d_flags); cudaFree(d_ring_bar);
         cudaFree(d_stage); cudaFree(d_stage_flag);
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
@@ -195,7 +203,13 @@ struct lcf_batch {
     bool has_state = false, need_init_logp = true;
     double last_ms = 0.;
     long long last_launches = 0;
+    std::vector<lcf_problem *> owned;             // problems created by lcf_sed_batch_create (destroyed with the batch)
+    void *d_shared = nullptr;                     // their device arrays and tile tables: one allocation
+    double *d_lpseudo = nullptr, *d_summary = nullptr;
+    size_t lpseudo_cap = 0;
     ~lcf_batch() {
+        for (lcf_problem *p : owned) delete p;
+        cudaFree(d_shared); cudaFree(d_lpseudo); cudaFree(d_summary);
         cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_order); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
         cudaFree(d_acc); cudaFree(d_status);
         if (ev0) cudaEventDestroy(ev0);
@@ -211,6 +225,7 @@ namespace {
 // -----------------------------------------------------------------------------------------
 typedef void (*PassKernel)(const ProblemDev, const TileDev, const MoveDev);
 typedef void (*ChainKernel)(const BatchDev);
+typedef void (*RingKernel)(const ProblemDev, const TileDev, const RingDev);
 
 // LCF_DEV_ONLY_MODEL=<id> (tools/microbench builds): instantiate the FP32 half-step kernel of one model only, so that a
 // kernel experiment compiles in seconds.  Never defined for the shipped library.
@@ -221,6 +236,7 @@ template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool pla
     return k_pass<LCF_DEV_ONLY_MODEL, R, -1, false>;
 }
 template <typename R> ChainKernel chain_kernel_for(int) { return nullptr; }
+template <typename R> RingKernel ring_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_ring<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 #else
 // l = walkers-per-CTA exponent of the launch: 5 (32 walkers, every large ensemble) has its own instantiation
 // and, for it, one more without the per-tile mode / use_sigma branches (plain = no intrinsic scatter, not a model evaluation)
@@ -243,6 +259,19 @@ template <typename R> ChainKernel chain_kernel_for(int model) {
         case 6: return k_chain<6, R>;
         case 7: return k_chain<7, R>;
         case 8: return k_chain<8, R>;
+    }
+    return nullptr;
+}
+template <typename R> RingKernel ring_kernel_for(int model) {
+    switch (model) {
+        case 1: return k_ring<1, R>;
+        case 2: return k_ring<2, R>;
+        case 3: return k_ring<3, R>;
+        case 4: return k_ring<4, R>;
+        case 5: return k_ring<5, R>;
+        case 6: return k_ring<6, R>;
+        case 7: return k_ring<7, R>;
+        case 8: return k_ring<8, R>;
     }
     return nullptr;
 }
@@ -317,12 +346,13 @@ int count_tiles(const lcf_problem *p, int l) {
     return tiles;
 }
 
-struct Shape { int l, nw, cluster; size_t smem; };
+struct Shape { int l, nw, cluster; size_t smem; double cost; };
 
 int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const int tune = (g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster;
     if (p->shape_cache.Ns == Ns && p->shape_cache.tune == tune) {
         out->l = p->shape_cache.l; out->nw = p->shape_cache.nw; out->cluster = p->shape_cache.cluster; out->smem = p->shape_cache.smem;
+        out->cost = p->shape_cache.cost;
         return 0;
     }
     int sms = 148;
@@ -333,7 +363,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
     const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
     double best = 1e300;
-    Shape bs = {5, 16, 1, 0};
+    Shape bs = {5, 16, 1, 0, 0.};
     for (int l = 5; l >= 0; --l) {
         if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
         const int ntiles = count_tiles(p, l);
@@ -378,7 +408,8 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
         if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), bs.smem))) return rc;
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
-    p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune;
+    p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune; p->shape_cache.cost = best;
+    bs.cost = best;
     if (getenv("LCF_DEBUG_SHAPE"))
         fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, %zu B smem (model %d, modelled %.0f clk)\n",
                 Ns, 1 << bs.l, bs.nw, bs.cluster, bs.smem, p->dev.model, best);
@@ -421,6 +452,8 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], mv));
+    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster;
+    p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
     if (launches) ++*launches;
     return 0;
 }
@@ -577,7 +610,7 @@ int lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size) 
     return 0;
 }
 
-int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
+static int problem_create_impl(const lcf_problem_desc *d, lcf_problem **out, bool defer) {
     if (!d || !out) return fail(LCF_ERR_ARG, "null argument");
     *out = nullptr;
     const int nm = model_nparams(d->model_id);
@@ -658,7 +691,9 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
     P.const_term = ct;
     p->h_point_filter.assign(d->point_filter, d->point_filter + d->npoints);
 
-    Arena arena;
+    Arena *arena_p = new Arena();
+    p->pending = arena_p;
+    Arena &arena = *arena_p;
     std::vector<int> role(d->nfilters, 0);
     if (d->filter_role) role.assign(d->filter_role, d->filter_role + d->nfilters);
     std::vector<double> t(d->t, d->t + d->npoints);
@@ -680,13 +715,30 @@ int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) {
         p->mean_samples = sk / d->npoints;
     }
     rc = (d->precision == LCF_PRECISION_FP32) ? build_problem_arrays<float>(d, p, scale, arena) : build_problem_arrays<double>(d, p, scale, arena);
-    if (!rc) rc = arena.commit(p->allocs);
+    if (!rc && !defer) {
+        rc = arena.commit(p->allocs);
+        delete p->pending;
+        p->pending = nullptr;
+    }
     if (rc) { delete p; return rc; }
     *out = p;
     return 0;
 }
 
+int lcf_problem_create(const lcf_problem_desc *d, lcf_problem **out) { return problem_create_impl(d, out, false); }
+
 void lcf_problem_destroy(lcf_problem *p) { delete p; }
+
+int lcf_problem_last_launch(lcf_problem *p, int *walkers_per_cta, int *warps_per_cta, int *cluster_size, int64_t *grid, int *kernel_variant) {
+    if (!p) return fail(LCF_ERR_ARG, "null problem");
+    if (p->last_launch.variant < 0) return fail(LCF_ERR_STATE, "no kernel has been launched for this problem yet");
+    if (walkers_per_cta) *walkers_per_cta = p->last_launch.wpb;
+    if (warps_per_cta) *warps_per_cta = p->last_launch.nw;
+    if (cluster_size) *cluster_size = p->last_launch.cluster;
+    if (grid) *grid = p->last_launch.grid;
+    if (kernel_variant) *kernel_variant = p->last_launch.variant;
+    return 0;
+}
 
 static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, const double *params, double *out, size_t out_per_set,
                        long long *nan_count) {
@@ -858,6 +910,59 @@ int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *
         rc = check_nan(e);
         if (rc) return rc;
     }
+    e->has_state = true;
+    return 0;
+}
+
+// Start state of a SHARED ensemble: every rank passes only the walkers it owns (logical [first, first + count), both colours
+// of its slice).  They are uploaded, permuted into this rank's replica, their log-posteriors evaluated here, and -- with the fused
+// exchange attached -- rows and log-probabilities are stored into every peer's replica over NVLink.  The caller must make sure
+// no peer is still sampling (its kernels read the replicas), and put ONE barrier between this call on all ranks and the first
+// step.  Replaces "every rank uploads the full [W][D] array, evaluates its slice, all-gathers the log-probabilities".
+int lcf_ensemble_set_state_slice(lcf_ensemble *e, int64_t first, int64_t count, const double *coords) {
+    if (!e || !coords) return fail(LCF_ERR_ARG, "null argument");
+    if (first != e->cfirst || count != e->cw) return fail(LCF_ERR_ARG, "the slice must be exactly the walkers this rank owns");
+    CUDA_TRY(cudaSetDevice(e->p->device));
+    const int D = e->D;
+    const size_t nc = (size_t)count * D;
+    if (!e->d_stage) {
+        CUDA_TRY(cudaMalloc(&e->d_stage, sizeof(double) * ((size_t)e->W * D + (size_t)e->W)));
+        CUDA_TRY(cudaMalloc(&e->d_stage_flag, sizeof(int)));
+    }
+    int h_fl = 0;
+    CUDA_TRY(cudaMemsetAsync(e->d_stage_flag, 0, sizeof(int), e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->d_stage, coords, sizeof(double) * nc, cudaMemcpyHostToDevice, e->stream));
+    k_set_state_slice<<<(unsigned)((nc + 255) / 256), 256, 0, e->stream>>>(e->d_stage, first, count, D, e->n0, e->d_coords, e->d_stage_flag);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(&h_fl, e->d_stage_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    PublishDev pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.npeers = e->npeers;
+    for (int p = 0; p < e->npeers; ++p) { pd.peer_coords[p] = e->peer_coords[p]; pd.peer_logp[p] = e->peer_logp[p]; }
+    for (int h = 0; h < 2; ++h) {                          // own rows of each colour block: evaluate, then publish
+        const long long row0 = (h ? e->n0 : 0) + e->own_begin[h], nrows = e->own_count[h];
+        if (nrows <= 0) continue;
+        MoveDev mv;
+        memset(&mv, 0, sizeof(mv));
+        mv.mode = MODE_LOGPOST;
+        mv.Ns = nrows;
+        mv.qin = e->d_coords + row0 * D;
+        mv.out = e->d_logp + row0;
+        mv.nanflag = e->d_nan;
+        int rc = launch_pass(e->p, mv, e->stream, nullptr);
+        if (rc) return rc;
+        if (e->npeers) {
+            const long long n = nrows * (D + 1);
+            k_publish_rows<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_coords, e->d_logp, row0, nrows, D, pd);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (h_fl) e->has_state = false;
+    if (h_fl & 1) return fail(LCF_ERR_ARG, "At least one parameter value was infinite");
+    if (h_fl & 2) return fail(LCF_ERR_ARG, "At least one parameter value was NaN");
+    int rc = check_nan(e);
+    if (rc) return rc;
     e->has_state = true;
     return 0;
 }
@@ -1046,6 +1151,88 @@ int lcf_ensemble_end_step(lcf_ensemble *e, int store) {
     return 0;
 }
 
+// Small ensembles: the whole run as ONE cooperative launch of the persistent kernel k_ring (device-side barrier between half-steps)
+// instead of two k_pass launches per step.  Used when the grid of the chosen launch shape is co-resident and a half-step is short
+// enough to be launch-bound (cost model of choose_shape); LCF_RING=0 / 1 forces it off / on (when it fits).
+static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
+    *used = false;
+    lcf_problem *p = e->p;
+    if (e->world != 1 || e->npeers || nsteps <= 0) return 0;
+    const char *env = getenv("LCF_RING");
+    if (env && env[0] == '0') return 0;
+    Shape sh;
+    int rc = choose_shape(p, std::max(e->n0, e->n1), &sh);
+    if (rc) return rc;
+    if (!(env && env[0] == '1') && sh.cost > 120000.) return 0;             // > ~60 us per half-step: launch latency is already hidden
+    const bool f32 = p->precision == LCF_PRECISION_FP32;
+    RingKernel k = f32 ? ring_kernel_for<float>(p->dev.model) : ring_kernel_for<double>(p->dev.model);
+    if (!k) return 0;
+    if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), sh.smem))) return rc;
+    const long long ngroups = (std::max(e->n0, e->n1) + (1 << sh.l) - 1) >> sh.l;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(ngroups * sh.cluster), 1, 1);
+    cfg.blockDim = dim3((unsigned)(sh.nw * 32), 1, 1);
+    cfg.dynamicSmemBytes = sh.smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+    if (sh.cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)sh.cluster;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const int ring_key = (sh.l * 64 + sh.nw) * 16 + sh.cluster;
+    if (e->ring_ok < 0 || e->ring_key != ring_key) {            // does the whole grid fit on the device at once?
+        e->ring_key = ring_key;
+        long long capacity = 0;
+        if (sh.cluster > 1) {
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+            capacity = (long long)ncl * sh.cluster;
+        } else {
+            int nb = 0, sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, sh.nw * 32, sh.smem) != cudaSuccess) { cudaGetLastError(); nb = 0; }
+            capacity = (long long)nb * sms;
+        }
+        e->ring_ok = (ngroups * sh.cluster <= capacity) ? 1 : 0;
+        if (getenv("LCF_DEBUG_SHAPE"))
+            fprintf(stderr, "[lcf] persistent chain kernel: grid %lld CTAs, co-resident capacity %lld -> %s\n", ngroups * sh.cluster, capacity,
+                    e->ring_ok ? "used" : "not used");
+    }
+    if (!e->ring_ok) return 0;
+    if (!e->d_ring_bar) CUDA_TRY(cudaMalloc(&e->d_ring_bar, 2 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(e->d_ring_bar, 0, 2 * sizeof(unsigned int), e->stream));
+    rc = build_tiles(p, sh.l);
+    if (rc) return rc;
+    RingDev G;
+    memset(&G, 0, sizeof(G));
+    G.coords = e->d_coords; G.logp = e->d_logp; G.accepted = e->d_acc; G.nanflag = e->d_nan;
+    G.chain = store ? e->d_chain + e->nstored * e->W * e->D : nullptr;
+    G.lnp = store ? e->d_lnp + e->nstored * e->W : nullptr;
+    G.W = e->W; G.n0 = e->n0;
+    G.nsteps = nsteps; G.iter0 = e->iteration;
+    G.seed = e->seed;
+    G.bar = e->d_ring_bar;
+    G.wpb_log2 = sh.l;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], G));
+    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster;
+    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3;
+    e->last_launches += 1;
+    e->iteration += nsteps;
+    if (store) e->nstored += nsteps;
+    *used = true;
+    return 0;
+}
+
 int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
     NvtxRange r("lcf_ensemble_run");
     if (!e) return fail(LCF_ERR_ARG, "null argument");
@@ -1057,7 +1244,10 @@ int lcf_ensemble_run(lcf_ensemble *e, int64_t nsteps, int store) {
     }
     e->last_launches = 0;
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-    for (long long s = 0; s < nsteps; ++s) {
+    bool ring = false;
+    int rrc = try_ring(e, nsteps, store, &ring);
+    if (rrc) return rrc;
+    for (long long s = 0; s < nsteps && !ring; ++s) {
         for (int half = 0; half < 2; ++half) {
             MoveDev mv;
             fill_move(e, half, store, mv);
@@ -1096,6 +1286,22 @@ int lcf_ensemble_run_to_host_slice(lcf_ensemble *e, int64_t nsteps, int64_t firs
     const size_t D = e->D, cw = (size_t)e->cw * D, lw = (size_t)e->cw;
     const size_t rel = (size_t)(first - e->cfirst);
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    bool ring = false;
+    const long long stored0 = e->nstored;
+    rc = try_ring(e, nsteps, 1, &ring);
+    if (rc) return rc;
+    if (ring) {            // a small ensemble: the whole chain in one launch, then one copy of the (small) chain
+        CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(chain_host, count * D * sizeof(double), e->d_chain + stored0 * cw + rel * D, cw * sizeof(double),
+                                   count * D * sizeof(double), nsteps, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(log_prob_host, count * sizeof(double), e->d_lnp + stored0 * lw + rel, lw * sizeof(double),
+                                   count * sizeof(double), nsteps, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        float rms = 0.f;
+        cudaEventElapsedTime(&rms, e->ev0, e->ev1);
+        e->last_ms = rms;
+        return check_nan(e);
+    }
     for (long long s = 0; s < nsteps; ++s) {
         for (int half = 0; half < 2; ++half) {
             MoveDev mv;
@@ -1532,6 +1738,129 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     b->iteration += nburn + nsteps;
     b->nsteps_stored = nsteps;
     b->need_init_logp = false;
+    return 0;
+}
+
+// ---- a whole table of SED epochs as ONE batch (calculate_bolometric at survey scale) ---------------------
+// Flat arrays in, one handle out: per-epoch problems are built in C (points grouped by filter, sub-bank gathered from the shared
+// filter bank, sigma units = median dy as bolometric.py:147-150), their device arrays share ONE allocation filled by ONE copy.
+int lcf_sed_batch_create(int64_t nepochs, const int32_t *offsets, const int32_t *point_filter, const double *y, const double *dy,
+                         int32_t nfilters, const int32_t *bank_offsets, const double *bank_alpha, const double *bank_w, int32_t ndim,
+                         int32_t use_sigma, int32_t sigma_type, const int32_t *prior_kind, const double *prior_min,
+                         const double *prior_max, const double *prior_mean, const double *prior_std, int32_t precision,
+                         int64_t nwalkers, uint64_t seed, lcf_batch **out) {
+    if (!offsets || !point_filter || !y || !dy || !bank_offsets || !bank_alpha || !bank_w || !prior_kind || !prior_min || !prior_max || !out)
+        return fail(LCF_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (nepochs <= 0) return fail(LCF_ERR_ARG, "no epochs");
+    std::vector<lcf_problem *> probs;
+    auto cleanup = [&]() { for (lcf_problem *p : probs) delete p; };
+    std::vector<int> order, local, sub_off, pf;
+    std::vector<double> sub_alpha, sub_w, sub_kappa, t0, yy, dd, med;
+    for (int64_t e = 0; e < nepochs; ++e) {
+        const int b0 = offsets[e], n = offsets[e + 1] - b0;
+        if (n <= 0) { cleanup(); return fail(LCF_ERR_ARG, "epoch %lld has no photometry point", (long long)e); }
+        order.resize(n);
+        for (int i = 0; i < n; ++i) {
+            order[i] = i;
+            if (point_filter[b0 + i] < 0 || point_filter[b0 + i] >= nfilters) { cleanup(); return fail(LCF_ERR_ARG, "point_filter out of range"); }
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return point_filter[b0 + a] < point_filter[b0 + b]; });
+        sub_off.assign(1, 0); sub_alpha.clear(); sub_w.clear(); pf.resize(n); yy.resize(n); dd.resize(n);
+        int last = -1, nf = 0;
+        for (int i = 0; i < n; ++i) {
+            const int g = point_filter[b0 + order[i]];
+            if (g != last) {
+                sub_alpha.insert(sub_alpha.end(), bank_alpha + bank_offsets[g], bank_alpha + bank_offsets[g + 1]);
+                sub_w.insert(sub_w.end(), bank_w + bank_offsets[g], bank_w + bank_offsets[g + 1]);
+                sub_off.push_back((int)sub_alpha.size());
+                last = g; ++nf;
+            }
+            pf[i] = nf - 1;
+            yy[i] = y[b0 + order[i]];
+            dd[i] = dy[b0 + order[i]];
+        }
+        med.assign(dd.begin(), dd.end());
+        std::sort(med.begin(), med.end());
+        t0.assign(n, 0.);
+        sub_kappa.assign(sub_alpha.size(), 0.);
+        lcf_problem_desc d;
+        memset(&d, 0, sizeof(d));
+        d.model_id = LCF_MODEL_BLACKBODY_SED;
+        d.precision = precision; d.ndim = ndim; d.use_sigma = use_sigma; d.sigma_type = sigma_type;
+        d.npoints = n; d.nfilters = nf;
+        d.sigma_unit_abs = (n & 1) ? med[n / 2] : 0.5 * (med[n / 2 - 1] + med[n / 2]);      // np.median(dy)
+        d.bank_offsets = sub_off.data(); d.bank_alpha = sub_alpha.data(); d.bank_w = sub_w.data(); d.bank_kappa = sub_kappa.data();
+        d.t = t0.data(); d.point_filter = pf.data(); d.y = yy.data(); d.dy = dd.data();
+        d.prior_kind = prior_kind; d.prior_min = prior_min; d.prior_max = prior_max; d.prior_mean = prior_mean; d.prior_std = prior_std;
+        lcf_problem *p = nullptr;
+        int rc = problem_create_impl(&d, &p, true);
+        if (rc) { cleanup(); return rc; }
+        probs.push_back(p);
+    }
+    // one allocation, one copy for the device arrays of every epoch
+    size_t total = 0;
+    std::vector<size_t> base(probs.size());
+    for (size_t i = 0; i < probs.size(); ++i) { base[i] = total; total += (probs[i]->pending->host.size() + 255) & ~(size_t)255; }
+    std::vector<unsigned char> host(std::max<size_t>(total, 16));
+    for (size_t i = 0; i < probs.size(); ++i) memcpy(host.data() + base[i], probs[i]->pending->host.data(), probs[i]->pending->host.size());
+    void *dblock = nullptr;
+    cudaError_t ce = cudaMalloc(&dblock, host.size());
+    if (ce == cudaSuccess) ce = cudaMemcpy(dblock, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(dblock); cleanup(); return fail(LCF_ERR_CUDA, "batch upload failed: %s", cudaGetErrorString(ce)); }
+    for (size_t i = 0; i < probs.size(); ++i) {
+        probs[i]->pending->patch(reinterpret_cast<unsigned char *>(dblock) + base[i]);
+        delete probs[i]->pending;
+        probs[i]->pending = nullptr;
+    }
+    lcf_batch *b = nullptr;
+    int rc = lcf_batch_create(nepochs, probs.data(), nwalkers, seed, &b);
+    if (rc) { cudaFree(dblock); cleanup(); return rc; }
+    b->owned = probs;
+    b->d_shared = dblock;
+    *out = b;
+    return 0;
+}
+
+// Posterior summaries of every epoch of a SED batch on the device (bolometric.py:792-798): T, R, Stefan-Boltzmann L_bol and the
+// pseudo-bolometric luminosity of every stored sample (`comb`: the 1-THz comb problem of pseudo(), evaluated IN PLACE on the
+// HBM-resident chain), then median_and_unc of each: out[nproblems][4][3] = (median, median - lower, upper - median).
+int lcf_batch_summary(lcf_batch *b, lcf_problem *comb, double sigma_sb, double perc_contained, double *out) {
+    if (!b || !comb || !out) return fail(LCF_ERR_ARG, "null argument");
+    if (comb->dev.model != LCF_MODEL_BLACKBODY_SED || comb->dev.npoints != 1) return fail(LCF_ERR_ARG, "comb must be a one-point blackbody problem");
+    if (b->model != LCF_MODEL_BLACKBODY_SED) return fail(LCF_ERR_ARG, "summary is defined for blackbody SED batches");
+    const long long n = b->nsteps_stored * b->W, total = n * b->nprob;
+    if (n < 1) return fail(LCF_ERR_STATE, "no stored samples");
+    CUDA_TRY(cudaSetDevice(b->probs[0]->device));
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    const size_t smem = sizeof(double) * (size_t)npad;
+    if (smem > kSmemMax) return fail(LCF_ERR_ARG, "more than %zu samples per epoch: take the percentiles of get_chain() on the host", kSmemMax / 8);
+    if ((size_t)total > b->lpseudo_cap) {
+        cudaFree(b->d_lpseudo); b->d_lpseudo = nullptr; b->lpseudo_cap = 0;
+        CUDA_TRY(cudaMalloc(&b->d_lpseudo, sizeof(double) * total));
+        b->lpseudo_cap = (size_t)total;
+    }
+    if (!b->d_summary) CUDA_TRY(cudaMalloc(&b->d_summary, sizeof(double) * 12 * b->nprob));
+    if (!comb->d_eval_nan) CUDA_TRY(cudaMalloc(&comb->d_eval_nan, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(comb->d_eval_nan, 0, sizeof(int), b->stream));
+    CUDA_TRY(cudaMemsetAsync(b->d_lpseudo, 0, sizeof(double) * total, b->stream));
+    MoveDev mv;
+    memset(&mv, 0, sizeof(mv));
+    mv.mode = MODE_MODEL;
+    mv.Ns = total;
+    mv.qin = b->d_chain;
+    mv.qstride = b->D;
+    mv.out = b->d_lpseudo;
+    mv.nanflag = comb->d_eval_nan;
+    int rc = launch_pass(comb, mv, b->stream, nullptr);
+    if (rc) return rc;
+    rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k_batch_summary), smem);
+    if (rc) return rc;
+    k_batch_summary<<<(unsigned)b->nprob, 256, smem, b->stream>>>(b->d_chain, b->d_lpseudo, n, b->D, npad, sigma_sb, perc_contained, b->d_summary);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, b->d_summary, sizeof(double) * 12 * b->nprob, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
     return 0;
 }
 

@@ -93,6 +93,7 @@ struct MoveDev {
     unsigned int ctr;                // 2*iteration + half
     // evaluation modes
     const double *qin;               // [Ns][D]  (nmodel columns in MODE_MODEL)
+    int qstride;                     // row stride of qin in doubles (0: the column count) -- lets a pass read a stored chain in place
     double *out;                     // [Ns] or [Ns][npoints]
     // fused multi-GPU exchange (npeers = 0: single GPU, or the host exchanges with NCCL): every rank holds a full replica;
     // the accept epilogue stores accepted walkers into the peers' replicas over NVLink (peer memory mapped with cudaIpc),
@@ -1063,7 +1064,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                 s_z[tid] = z;
             } else {
                 const int nq = (Mv.mode == MODE_MODEL) ? P.nmodel : D;
-                for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * nq + d];
+                const long long qs = Mv.qstride ? Mv.qstride : nq;
+                for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * qs + d];
                 for (int d = nq; d < D; ++d) q[d] = 0.;
             }
             for (int d = 0; d < D; ++d) s_q[tid * D + d] = q[d];
@@ -1343,7 +1345,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
     Mv.npeers = 0;
     Mv.seed = B.seed ^ ((unsigned long long)(prob + 1) * 0x9E3779B97F4A7C15ull);
-    Mv.qin = nullptr; Mv.out = nullptr;
+    Mv.qin = nullptr; Mv.out = nullptr; Mv.qstride = 0;
     bool first = true;
     if (B.init_logp) {                                   // log-prob of the initial positions
         Mv.mode = MODE_LOGPOST;
@@ -1369,6 +1371,95 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
             Mv.comp_base = half ? 0 : B.n0;
             const long long ng = (Mv.Ns + wpb - 1) / wpb;
             for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel C: ONE small ensemble, whole chain in one launch on a persistent co-resident grid (cooperative launch).
+// A half-step of a 100-walker ensemble is ~1 us of arithmetic; launched as one k_pass per half-step it costs ~20 us of
+// launch latency even with programmatic dependent launch.  Here the grid stays resident for the whole run: cluster c
+// owns walker group c of every half-step (its CTAs split the light curve as in k_pass), and half-steps are separated by
+// a device-side generation barrier (one atomic per CTA, release/acquire on a generation word) instead of a kernel
+// boundary.  Same group_pass, same RNG keys, same order of partial sums as the k_pass launches of the same shape:
+// chains are bit-identical to the per-half-step path.
+// ---------------------------------------------------------------------------------------
+struct RingDev {
+    double *coords, *logp;
+    unsigned long long *accepted;
+    int *nanflag;
+    double *chain, *lnp;               // [nsteps][W][D], [nsteps][W] for this run (NULL: not stored)
+    long long W, n0;
+    long long nsteps, iter0;
+    unsigned long long seed;
+    unsigned int *bar;                 // [2]: arrival counter, generation (zeroed before the launch)
+    int wpb_log2;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// every CTA of the (co-resident) grid has finished its part of the half-step and its global writes are visible
+__device__ __forceinline__ void ring_barrier(unsigned int *bar, unsigned int &gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += 1u;
+        __threadfence();
+        const unsigned int prev = atomicAdd(bar, 1u);
+        if (prev == gridDim.x - 1u) {
+            bar[0] = 0u;                                   // nobody arrives again before seeing the new generation
+            st_release_gpu(bar + 1, gen);
+        } else {
+            while (ld_acquire_gpu(bar + 1) != gen) { }
+        }
+    }
+    __syncthreads();
+}
+
+template <int MODEL, typename R>
+__global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const ProblemDev P, const TileDev TL, const RingDev G) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wpb = 1 << G.wpb_log2;
+    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
+    __syncthreads();
+    const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
+    if (csize > 1) cluster_sync_all();
+    const long long cid = cluster_id_x(), nclusters = cluster_count_x();
+    const int D = P.ndim;
+    MoveDev Mv;
+    Mv.coords = G.coords; Mv.logp = G.logp;
+    Mv.nanflag = G.nanflag;
+    Mv.W = G.W; Mv.n0 = G.n0;
+    Mv.mode = MODE_MOVE; Mv.wpb_log2 = G.wpb_log2;
+    Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
+    Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
+    Mv.npeers = 0;
+    Mv.seed = G.seed;
+    Mv.qin = nullptr; Mv.out = nullptr; Mv.qstride = 0;
+    const long long n1 = G.W - G.n0;
+    unsigned int gen = 0u;
+    bool first = true;
+    for (long long it = 0; it < G.nsteps; ++it) {
+        Mv.accepted = G.chain ? G.accepted : nullptr;      // acceptance counts cover stored steps only (emcee's Backend)
+        Mv.chain_step = G.chain ? G.chain + it * G.W * D : nullptr;
+        Mv.lnp_step = G.chain ? G.lnp + it * G.W : nullptr;
+        for (int half = 0; half < 2; ++half) {
+            Mv.ctr = (unsigned int)(2 * (G.iter0 + it) + half);
+            Mv.Ns = half ? n1 : G.n0;
+            Mv.act_base = half ? G.n0 : 0;
+            Mv.Nc = half ? G.n0 : n1;
+            Mv.comp_base = half ? 0 : G.n0;
+            const long long ng = (Mv.Ns + wpb - 1) / wpb;
+            for (long long g = cid; g < ng; g += nclusters) { group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize); first = false; }
+            ring_barrier(G.bar, gen);
         }
     }
 }

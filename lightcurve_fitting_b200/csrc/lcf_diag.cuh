@@ -83,6 +83,96 @@ __global__ void __launch_bounds__(256) k_mean_acf(const double *__restrict__ x, 
     }
 }
 
+// ---- bolometric post-processing of a batch of SED chains (bolometric.py:792-798, 422-480) --------------------------------------
+// One CTA per epoch.  For the four per-sample quantities T, R, L_bol = 4 pi R^2 sigma_SB T^4 (stefan_boltzmann) and the
+// pseudo-bolometric luminosity (computed beforehand by the Planck-sum pass on the 1-THz comb, `lpseudo`), the samples of the epoch's
+// flat chain are sorted in shared memory (bitonic network, padded with +inf) and the percentiles 50 -+ perc/2 are read off with
+// numpy's linear interpolation; out[epoch][quantity] = (median, median - lower, upper - median) = median_and_unc.
+__device__ __forceinline__ double percentile_sorted(const double *a, long long n, double q) {
+    const double pos = q * 0.01 * (double)(n - 1);                     // numpy 'linear': virtual index q/100 (n-1)
+    long long lo = (long long)floor(pos);
+    if (lo < 0) lo = 0;
+    if (lo > n - 1) lo = n - 1;
+    const long long hi = lo + 1 < n ? lo + 1 : n - 1;
+    const double t = pos - (double)lo, x = a[lo], y = a[hi];
+    return t < 0.5 ? x + (y - x) * t : y - (y - x) * (1. - t);            // numpy's _lerp
+}
+__global__ void __launch_bounds__(256) k_batch_summary(const double *__restrict__ chain, const double *__restrict__ lpseudo, long long n, int D,
+                                                        int npad, double sigma_sb, double perc, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *a = reinterpret_cast<double *>(smem_raw);
+    const long long e = blockIdx.x;
+    const double *c = chain + e * n * D;
+    const double *lp = lpseudo + e * n;
+    for (int q = 0; q < 4; ++q) {
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            double v = __longlong_as_double(0x7ff0000000000000LL);
+            if (i < n) {
+                const double T = c[(long long)i * D], R = c[(long long)i * D + 1];
+                if (q == 0) v = T;
+                else if (q == 1) v = R;
+                else if (q == 2) { const double T2 = T * T; v = 4. * 3.14159265358979323846 * (R * R) * sigma_sb * (T2 * T2); }   // bolometric.py:447
+                else v = lp[i];
+                if (v != v) v = __longlong_as_double(0x7ff0000000000000LL);     // NaN sorts last (numpy would return NaN: flagged by the status)
+            }
+            a[i] = v;
+        }
+        __syncthreads();
+        for (int k = 2; k <= npad; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const double x = a[i], y = a[l];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { a[i] = y; a[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) {
+            const double lo = percentile_sorted(a, n, 50. - 0.5 * perc), md = percentile_sorted(a, n, 50.), hi = percentile_sorted(a, n, 50. + 0.5 * perc);
+            double *o = out + (e * 4 + q) * 3;
+            o[0] = md; o[1] = md - lo; o[2] = hi - md;
+        }
+        __syncthreads();
+    }
+}
+
+// Shared ensembles: a rank receives only ITS walkers (logical [first, first + count)) from the host ...
+__global__ void __launch_bounds__(256) k_set_state_slice(const double *__restrict__ in, long long first, long long count, int D, long long n0,
+                                                         double *__restrict__ coords, int *__restrict__ flags) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * D) return;
+    const long long j = first + idx / D;
+    const int d = (int)(idx % D);
+    const long long r = (j & 1) ? n0 + (j >> 1) : (j >> 1);
+    const double v = in[idx];
+    if (isinf(v)) atomicOr(flags, 1);
+    if (isnan(v)) atomicOr(flags, 2);
+    coords[r * D + d] = v;
+}
+// ... and, once their log-probabilities are known, stores both straight into every peer's replica (NVLink peer memory): the same
+// posted stores the accept epilogue of k_pass uses, so no rank ever uploads or gathers the full start array.
+struct PublishDev {
+    int npeers;
+    double *peer_coords[kMaxPeers];
+    double *peer_logp[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) k_publish_rows(const double *__restrict__ coords, const double *__restrict__ logp, long long row0,
+                                                      long long nrows, int D, PublishDev P) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * (D + 1)) return;
+    if (idx < nrows * D) {
+        const double v = coords[row0 * D + idx];
+        for (int p = 0; p < P.npeers; ++p) P.peer_coords[p][row0 * D + idx] = v;
+    } else {
+        const long long r = row0 + (idx - nrows * D);
+        const double v = logp[r];
+        for (int p = 0; p < P.npeers; ++p) P.peer_logp[p][r] = v;
+    }
+}
+
 }  // namespace lcf
 
 // ---------------------------------------------------------------------------------------

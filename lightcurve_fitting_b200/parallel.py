@@ -94,6 +94,7 @@ class ShardedEnsemble:
         self.logp = torch.as_tensor(_DevArray(dl.value, (self.nwalkers,)), device='cuda')
         self.own = [(ob[0], oc[0]), (ob[1], oc[1])]
         self.fused = False
+        self._dirty = False                  # sampling kernels may still be in flight on some rank
         if world > 1 and exchange == 'p2p':
             self._attach_peers()
 
@@ -117,6 +118,7 @@ class ShardedEnsemble:
             self.torch.cuda.current_stream().synchronize()
             check(lib().lcf_ensemble_sync(self.sampler.handle))
             dist.barrier(group=self.group)
+            self._dirty = False
 
     def close(self):
         """Unmap the peers' replicas on every rank before any rank frees its own (collective when fused)."""
@@ -128,22 +130,34 @@ class ShardedEnsemble:
             dist.barrier(group=self.group)
 
     def set_state(self, coords):
-        if self.fused:
-            self._quiesce()
+        """Start positions ``[nwalkers, ndim]`` in emcee's walker order (the same array on every rank, as in the reference's
+        ``run_mcmc(initial)``).  Each rank uploads and evaluates ONLY the walkers it owns; their rows and log-probabilities
+        reach the other replicas by posted NVLink stores from a device kernel (fused exchange) or one all-gather per colour
+        block (NCCL exchange).  One barrier before (only when a run is still in flight) and one after."""
         if self.world > 1 and self.coords.is_cuda and self._even():
-            # initial log-probabilities: every rank evaluates its own walkers only, one all-gather completes them
             import torch.distributed as dist
-            from .sampler import State
-            coords = np.ascontiguousarray(coords, float)
+            from ._capi import dptr
+            if self._dirty:
+                self._quiesce()              # the peers' kernels read the replicas about to be overwritten
+            coords = np.asarray(coords, float)
+            if coords.shape != (self.nwalkers, self.ndim):
+                raise ValueError('incompatible input dimensions')
             first, count = self.own_walkers()
-            mine = self.torch.from_numpy(self.sampler.problem.log_posterior(coords[first:first + count], raise_nan=True)).cuda()
-            full = self.torch.empty(self.nwalkers, dtype=self.torch.float64, device='cuda')
-            dist.all_gather_into_tensor(full, mine, group=self.group)
-            self.sampler._set_initial(State(coords, full.cpu().numpy(), None), True)
+            mine = np.ascontiguousarray(coords[first:first + count])
+            check(lib().lcf_ensemble_set_state_slice(self.sampler.handle, first, count, dptr(mine)))
+            if not self.fused:
+                for block in (self.coords[:self.n0], self.coords[self.n0:], self.logp[:self.n0].unsqueeze(1),
+                              self.logp[self.n0:].unsqueeze(1)):
+                    exchange_half(block, self.rank, self.world, self.group)
+                self.torch.cuda.current_stream().synchronize()
+            dist.barrier(group=self.group)   # every replica is complete before anyone steps
+            self._dirty = False
         else:
+            if self.fused:
+                self._quiesce()
             self.sampler._set_initial(coords, True)
-        if self.fused:
-            self._quiesce()
+            if self.fused:
+                self._quiesce()
 
     def _even(self):
         (b0, c0), (b1, c1) = self.own
@@ -157,6 +171,7 @@ class ShardedEnsemble:
         [nsteps, own count, ndim] / ``log_prob_out`` [nsteps, own count] (page-locked) then receive this rank's walkers
         step by step while the next steps are sampled.  NCCL exchange: one kernel + one all-gather per half-step."""
         L, h = lib(), self.sampler.handle
+        self._dirty = True
         if store:
             self.reserve(nsteps)
         if self.fused and chain_out is not None:

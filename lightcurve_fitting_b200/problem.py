@@ -157,6 +157,14 @@ class DeviceProblem:
             _capi._lib.lcf_problem_destroy(h)
             self.handle = None
 
+    def last_launch(self):
+        """Shape and kernel instantiation of the last launch for this problem (``lcf_problem_last_launch``)."""
+        a, b, c, v = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        g = C.c_int64()
+        check(lib().lcf_problem_last_launch(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(g), C.byref(v)))
+        return {'walkers_per_cta': a.value, 'warps_per_cta': b.value, 'cluster': c.value, 'grid': g.value,
+                'kernel': {0: 'k_pass<generic>', 1: 'k_pass<32 walkers>', 2: 'k_pass<32 walkers, plain>', 3: 'k_ring'}[v.value]}
+
     # -- evaluation entry points ----------------------------------------------------------
     def model_eval(self, params):
         """params [nsets, n_model_params] -> model values [nsets, npoints] in the caller's point order."""

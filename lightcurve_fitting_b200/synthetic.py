@@ -190,3 +190,26 @@ def sed_epoch(truth, rng, z=0.002, use_sigma=False):
         lo, hi = lo + [0.], hi + [1.]
     return Workload('cfg3-sed', 'BlackbodySED', np.zeros(nf), fn, y, dy, pri, lo, hi, z=z, use_sigma=use_sigma,
                     truth=np.array([T, R]))
+
+
+def sed_table(truth, nepochs=500, seed=2, z=0.002, dm=32.5):
+    """cfg3 as the table ``calculate_bolometric`` receives: ``nepochs`` nightly epochs, each observed in 3-9 distinct filters of
+    {U,B,V,g,r,i,R,I,unfiltered}, blackbody truth T ~ U(5, 30) kK, R ~ logU(1, 30) kR_sun, 5 % photometry, magnitudes."""
+    rng = np.random.default_rng(seed)
+    pool = ['U', 'B', 'V', 'g', 'r', 'i', 'R', 'I', '0']
+    mjd, names, mag, dmag = [], [], [], []
+    for e in range(nepochs):
+        nf = int(rng.integers(3, 10))
+        fn = list(rng.choice(pool, nf, replace=False))
+        T, R = rng.uniform(5., 30.), np.exp(rng.uniform(np.log(1.), np.log(30.)))
+        lum = np.asarray(truth('BlackbodySED', np.zeros(nf), fn, np.array([T, R]), z), float)
+        lum = lum * (1. + 0.05 * rng.normal(size=nf))
+        zp = np.array([filtdict[n].m0 for n in fn]) + 90.19            # lightcurve.py:358
+        mag += list(zp - 2.5 * np.log10(lum) + dm)
+        dmag += [2.5 / np.log(10.) * 0.05] * nf
+        mjd += list(58000. + e + rng.uniform(-0.2, 0.2, nf))
+        names += fn
+    lc = LC({'MJD': np.array(mjd), 'mag': np.array(mag), 'dmag': np.array(dmag), 'filter': np.array(names),
+             'nondet': np.zeros(len(mjd), bool)})
+    lc.meta.update(dm=dm, redshift=z, extinction={}, hostext={})
+    return lc

@@ -64,26 +64,38 @@ def _f99_uv(x, c1_, c2_):
     return k + 0.41 * (0.5392 * y5 ** 2 + 0.05644 * y5 ** 3)
 
 
+_F99_SPLINE = {}
+
+
+def _f99_spline(r_v):
+    """Knots of the optical/IR cubic spline for one R_V; built once (the compiled `extinction` package does not refit a
+    spline per call either: without the cache half of a `synthesize` call was `splrep`)."""
+    if r_v not in _F99_SPLINE:
+        from scipy.interpolate import splrep
+        c2_ = -0.824 + 4.717 / r_v
+        c1_ = 2.030 - 3.007 * c2_
+        rv2 = r_v * r_v
+        with np.errstate(divide='ignore'):
+            xk = 1e4 / np.array([np.inf, 26500., 12200., 6000., 5470., 4670., 4110., 2700., 2600.])
+        kk = np.array([
+            -r_v,
+            0.26469 * r_v / 3.1 - r_v,
+            0.82925 * r_v / 3.1 - r_v,
+            -0.422809 + 1.00270 * r_v + 2.13572e-04 * rv2 - r_v,
+            -5.13540e-02 + 1.00216 * r_v - 7.35778e-05 * rv2 - r_v,
+            0.700127 + 1.00184 * r_v - 3.32598e-05 * rv2 - r_v,
+            1.19456 + 1.01707 * r_v - 5.46959e-03 * rv2 + 7.97809e-04 * rv2 * r_v - 4.45636e-05 * rv2 * rv2 - r_v,
+            0., 0.])
+        kk[7:] = _f99_uv(xk[7:], c1_, c2_)
+        _F99_SPLINE[r_v] = (splrep(xk, kk), c1_, c2_)
+    return _F99_SPLINE[r_v]
+
+
 def fitzpatrick99(wave, a_v, r_v=3.1):
     """A(lambda) in magnitudes for wavelengths in angstrom (extinction package, F99)."""
-    from scipy.interpolate import splrep, splev
+    from scipy.interpolate import splev
     wave = np.atleast_1d(np.asarray(wave, float))
-    c2_ = -0.824 + 4.717 / r_v
-    c1_ = 2.030 - 3.007 * c2_
-    rv2 = r_v * r_v
-    with np.errstate(divide='ignore'):
-        xk = 1e4 / np.array([np.inf, 26500., 12200., 6000., 5470., 4670., 4110., 2700., 2600.])
-    kk = np.array([
-        -r_v,
-        0.26469 * r_v / 3.1 - r_v,
-        0.82925 * r_v / 3.1 - r_v,
-        -0.422809 + 1.00270 * r_v + 2.13572e-04 * rv2 - r_v,
-        -5.13540e-02 + 1.00216 * r_v - 7.35778e-05 * rv2 - r_v,
-        0.700127 + 1.00184 * r_v - 3.32598e-05 * rv2 - r_v,
-        1.19456 + 1.01707 * r_v - 5.46959e-03 * rv2 + 7.97809e-04 * rv2 * r_v - 4.45636e-05 * rv2 * rv2 - r_v,
-        0., 0.])
-    kk[7:] = _f99_uv(xk[7:], c1_, c2_)
-    tck = splrep(xk, kk)
+    tck, c1_, c2_ = _f99_spline(r_v)
     x = 1e4 / wave
     uv = x >= 1e4 / 2700.
     k = np.empty_like(x)
@@ -557,16 +569,19 @@ class StretchReplay:
                 nlp = self._lnprob(q)
                 logu = np.empty(Ns)
                 acc = np.zeros(Ns, bool)
+                margin = np.empty(Ns)                               # lnpdiff - ln u of every decision (how close a call it was)
                 for i, j in enumerate(np.flatnonzero(S1)):
                     lnpdiff = factors[i] + nlp[i] - lnp[j]
                     logu[i] = np.log(self.random.rand())
+                    margin[i] = lnpdiff - logu[i]
                     if lnpdiff > logu[i]:
                         acc[i] = True
                 idx = np.flatnonzero(S1)[acc]
                 coords[idx] = q[acc]
                 lnp[idx] = nlp[acc]
                 self.accepted[idx] += 1
-                step_draws['halves'].append({'z': zz, 'rint': rint, 'logu': logu})
+                step_draws['halves'].append({'z': zz, 'rint': rint, 'logu': logu, 'margin': margin, 'nlp': nlp.copy(),
+                                             'walkers': np.flatnonzero(S1)})
             if record:
                 self.draws.append(step_draws)
             self._chain.append(coords.copy())

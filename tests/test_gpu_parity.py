@@ -200,10 +200,26 @@ def test_chain_replay_matches_oracle(name, precision):
         np.testing.assert_allclose(s.get_log_prob(), ref.get_log_prob(), rtol=1e-9)
         np.testing.assert_array_equal(s.acceptance_fraction, ref.acceptance_fraction)
     else:
-        # FP32 log-posteriors differ at the 1e-4 level, so a borderline accept decision may flip; require that
-        # the bulk of the walkers agree and that agreeing walkers match to tolerance
-        same = np.all(np.isclose(got, want, rtol=1e-4, atol=0), axis=(0, 2))
-        assert same.mean() >= 0.7
+        # FP32 log-posteriors differ from the oracle's at the 1e-4 level, so an accept decision that was a close call may
+        # flip, after which the two chains legitimately part.  Criterion: every step before the first divergence matches at
+        # 1e-4, and every walker that diverges AT that step was such a close call in the oracle's run:
+        # |lnpdiff - ln u| < 1e-3 |lnp'| (the oracle records the margin of every decision).
+        close = np.all(np.isclose(got, want, rtol=1e-4, atol=0), axis=2)              # [step, walker]
+        bad_steps = np.flatnonzero(~close.all(axis=1))
+        if len(bad_steps):
+            s0 = bad_steps[0]
+            np.testing.assert_allclose(got[:s0], want[:s0], rtol=1e-4)
+            np.testing.assert_allclose(s.get_log_prob()[:s0], ref.get_log_prob()[:s0], rtol=1e-4)
+            margin, nlp = np.full(nw, np.inf), np.ones(nw)
+            for h in ref.draws[s0]['halves']:
+                margin[h['walkers']], nlp[h['walkers']] = h['margin'], h['nlp']
+            # a walker can also differ at step s0 because its partner (of the other colour) flipped earlier in the same step
+            flipped = np.abs(margin) < 1e-3 * np.abs(nlp)
+            assert flipped[~close[s0]].any(), 'chains diverge at step %d without a close accept decision' % s0
+            first_half = ref.draws[s0]['halves'][0]['walkers']
+            assert np.all(flipped[np.intersect1d(np.flatnonzero(~close[s0]), first_half)])
+        else:
+            np.testing.assert_allclose(s.get_log_prob(), ref.get_log_prob(), rtol=1e-4)
     np.testing.assert_allclose(state.coords, got[-1])
     assert s.chain.shape == (nw, nsteps, wl.ndim) and s.flatchain.shape == (nsteps * nw, wl.ndim)
 
@@ -806,3 +822,275 @@ def test_shockcooling3_with_a_large_filter_bank(precision):
     s = EnsembleSampler(80, wl.ndim, wl.device_problem(precision), seed=4)
     s.run_mcmc(wl.start(80, rng), 4)
     assert np.isfinite(s.get_log_prob()).all()
+
+
+# ---- the BASELINE.json shapes themselves, on the kernels the benchmark times -------------------------------------------
+def _check_chain_rows_against_oracle(wl, chain, lnp, precision, nrows, seed):
+    """Recompute the log-posterior of `nrows` sampled (step, walker) rows of a stored chain with the oracle."""
+    lp = W.oracle_log_posterior(wl)
+    rng = np.random.default_rng(seed)
+    S, Wn = lnp.shape
+    pick = rng.choice(S * Wn, nrows, replace=False)
+    got = lnp.reshape(-1)[pick]
+    want = np.array([lp(p) for p in chain.reshape(S * Wn, -1)[pick]])
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, want, rtol=RTOL[precision])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+def test_cfg2_shape_native_moves_on_the_benchmark_kernel(precision):
+    """BASELINE cfg2 at its real light-curve shape (ShockCooling3, N = 2000, 8 filters, 10^5 walkers: the benchmark's own ensemble, 1563 CTAs
+    of 32 walkers x 16 warps per half-step): five native stretch-move steps must run on
+    k_pass<3, real, 5, true> in MODE_MOVE, and the stored log-probabilities must be the oracle's log-posterior of the
+    stored positions."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_sc3(npoints=2000)
+    prob = wl.device_problem(precision)
+    nw = 100_000
+    s = EnsembleSampler(nw, wl.ndim, prob, seed=11)
+    p0 = wl.start(nw, np.random.default_rng(2))
+    s.run_mcmc(p0, 5, skip_initial_state_check=True)
+    launch = prob.last_launch()
+    assert launch['kernel'] == 'k_pass<32 walkers, plain>' and launch['walkers_per_cta'] == 32 and launch['warps_per_cta'] == 16
+    assert launch['grid'] == (nw // 2 + 31) // 32 and launch['cluster'] == 1
+    chain, lnp = s.get_chain(), s.get_log_prob()
+    assert chain.shape == (5, nw, wl.ndim)
+    acc = s.acceptance_fraction
+    assert 0.05 < acc.mean() < 0.95
+    moved = np.any(chain[-1] != p0, axis=1)
+    assert moved.mean() > 0.5                                   # the ensemble really moved
+    _check_chain_rows_against_oracle(wl, chain, lnp, precision, 24, 5)
+    # a walker that never accepted still carries its initial log-posterior: initial evaluation (MODE_LOGPOST) and moves agree
+    still = np.flatnonzero(~moved)[:4]
+    if len(still):
+        lp = W.oracle_log_posterior(wl)
+        np.testing.assert_allclose(lnp[-1, still], [lp(p) for p in p0[still]], rtol=RTOL[precision])
+
+
+def test_cfg4_shape_native_moves(precision='fp32'):
+    """BASELINE cfg4: CompanionShocking3, N = 1000 over U,B,V,g,r,i, 10^4 walkers (the launch shape the cost model picks for
+    it), native moves checked against the oracle."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_cs3(npoints=1000)
+    prob = wl.device_problem(precision)
+    nw = 10_000
+    s = EnsembleSampler(nw, wl.ndim, prob, seed=12)
+    s.run_mcmc(wl.start(nw, np.random.default_rng(3)), 4, skip_initial_state_check=True)
+    launch = prob.last_launch()
+    assert launch['grid'] * launch['walkers_per_cta'] >= nw // 2
+    chain, lnp = s.get_chain(), s.get_log_prob()
+    assert 0.05 < s.acceptance_fraction.mean() < 0.95
+    _check_chain_rows_against_oracle(wl, chain, lnp, precision, 16, 6)
+
+
+def test_cfg5_shape_batched_chains_256_walkers():
+    """BASELINE cfg5 member shape: ShockCooling4 on N = 300 points, 256 walkers, whole chain in one k_chain launch
+    (wide 128-walker groups); stored log-probabilities against the oracle."""
+    from lightcurve_fitting_b200.bolometric import BatchSampler
+    rng = np.random.default_rng(4)
+    wls = [W.synthetic_sc4(npoints=n, lc_index=i) for i, n in enumerate((300, 117))]
+    probs = [w.device_problem('fp32') for w in wls]
+    b = BatchSampler(probs, 256, seed=9)
+    b.run(np.stack([w.start(256, rng) for w in wls]), 6, 4)
+    assert np.all(b.status == 0)
+    chain, lnp = b.get_chain(), b.get_log_prob()
+    assert chain.shape == (2, 4, 256, 5)
+    for k, w in enumerate(wls):
+        _check_chain_rows_against_oracle(w, chain[k], lnp[k], 'fp32', 12, 7 + k)
+
+
+def test_two_live_problems_with_different_shared_memory_on_one_kernel():
+    """Two problems of the same model and precision share a k_pass instantiation but need different dynamic shared memory (a
+    large UV bank next to a small optical one).  Launches of the large one must keep working after the small one was set up
+    (the opt-in shared-memory limit of a kernel is process-wide and must only ever be raised)."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    big = _ragged_workload(['UVW2', 'UVW1', 'NUV', 'w', 'Kepler', 'TESS', 'Itagaki', 'g'], [40] * 8, model='ShockCooling4')   # 5200 samples: 83 KB in FP64
+    small = _ragged_workload(['B', 'V'], [40, 40], model='ShockCooling4')
+    from lightcurve_fitting_b200._capi import lib, check
+    pb, ps = big.device_problem('fp64'), small.device_problem('fp64')
+    rng = np.random.default_rng(0)
+    nw = 2048
+    check(lib().lcf_set_tuning_ex(8, 8, 1))                        # one shape for both: the generic k_pass<4, double> instantiation
+    try:
+        sb = EnsembleSampler(nw, big.ndim, pb, seed=1)
+        sb.run_mcmc(big.start(nw, rng), 1, skip_initial_state_check=True)
+        ss = EnsembleSampler(nw, small.ndim, ps, seed=2)
+        ss.run_mcmc(small.start(nw, rng), 1, skip_initial_state_check=True)
+        assert pb.last_launch()['kernel'] == ps.last_launch()['kernel']     # one instantiation (k_pass<generic> or the persistent k_ring)
+        sb.run_mcmc(None, 2)                                       # cached shape of the large problem, after the small one ran
+        ss.run_mcmc(None, 2)
+        P = big.start(8, rng)
+        lp = W.oracle_log_posterior(big)
+        np.testing.assert_allclose(pb.log_posterior(P), [lp(p) for p in P], rtol=1e-9)
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
+# ---- bolometric.py against vectors produced by the REFERENCE's bolometric.py (tests/golden/make_golden.py) ---------------
+def test_bolometric_functions_match_reference_golden():
+    from lightcurve_fitting_b200 import bolometric as B, LC
+    from lightcurve_fitting_b200.filters import filtdict
+    T, R = GOLD['bolo/pseudo/T'], GOLD['bolo/pseudo/R']
+    np.testing.assert_allclose(B.pseudo(T, R, 0.), GOLD['bolo/pseudo/z0'], rtol=1e-9)
+    np.testing.assert_allclose(B.pseudo(T, R, 0.023), GOLD['bolo/pseudo/z'], rtol=1e-9)
+    np.testing.assert_allclose(B.pseudo(T, R, 0.01, cutoff_freq=800.), GOLD['bolo/pseudo/cut'], rtol=1e-9)
+    np.testing.assert_allclose(B.pseudo(12., 3., 0.002), GOLD['bolo/pseudo/scalar'], rtol=1e-9)
+    np.testing.assert_allclose(B.pseudo(T, R, 0.002, filter0=filtdict['V'], filter1=filtdict['B']), GOLD['bolo/pseudo/BtoV'], rtol=1e-9)
+    np.testing.assert_allclose(B.sigma_sb, GOLD['bolo/sigma_sb'], rtol=1e-14)
+    np.testing.assert_allclose(B.stefan_boltzmann(T, R), GOLD['bolo/sb/lum'], rtol=1e-13)
+    lum, dlum = B.stefan_boltzmann(T, R, GOLD['bolo/sb/dT'], GOLD['bolo/sb/dR'], GOLD['bolo/sb/cov'])
+    np.testing.assert_allclose(lum, GOLD['bolo/sb/lum2'], rtol=1e-13)
+    np.testing.assert_allclose(dlum, GOLD['bolo/sb/dlum'], rtol=1e-13)
+    for x, out, pc in ((GOLD['bolo/mu/x1'], GOLD['bolo/mu/out1'], 68.), (GOLD['bolo/mu/x2'], GOLD['bolo/mu/out2'], 68.),
+                       (GOLD['bolo/mu/x1'], GOLD['bolo/mu/out1_100'], 100.)):
+        np.testing.assert_allclose(np.array(B.median_and_unc(x, pc)), out, rtol=1e-12)
+    # least-squares blackbody of every golden SED in one launch (the reference: scipy curve_fit per epoch, stops at 1e-8)
+    off, out = GOLD['bolo/lstsq/offsets'], GOLD['bolo/lstsq/out']
+    z = float(GOLD['bolo/lstsq/z'])
+    for cutoff, tmax in sorted({(float(c), float(t)) for c, t in out[:, 7:9]}):
+        ks = [k for k in range(len(out)) if out[k, 7] == cutoff and out[k, 8] == tmax]
+        eps = []
+        for k in ks:
+            names = [str(n) for n in GOLD['bolo/lstsq/filters'][off[k]:off[k + 1]]]
+            np.testing.assert_allclose([filtdict[n].freq_eff for n in names], GOLD['bolo/lstsq/freq'][off[k]:off[k + 1]], rtol=1e-12)
+            eps.append(LC({'freq': GOLD['bolo/lstsq/freq'][off[k]:off[k + 1]], 'lum': GOLD['bolo/lstsq/lum'][off[k]:off[k + 1]]}))
+        res = np.array(B.blackbody_lstsq_batch(eps, z, T_range=(1., tmax), cutoff_freq=cutoff)[:7]).T       # [epoch, 7]
+        want = out[ks, :7]
+        np.testing.assert_allclose(res[:, [0, 1, 4, 6]], want[:, [0, 1, 4, 6]], rtol=2e-6)                    # temp, radius, lum, L_opt
+        fin = np.isfinite(want[:, [2, 3, 5]]) & (want[:, [0]] < 0.999 * tmax)    # covariance: undefined for nfilt <= 2 / at a bound
+        np.testing.assert_allclose(res[:, [2, 3, 5]][fin], want[:, [2, 3, 5]][fin], rtol=2e-4)
+
+
+@pytest.mark.parametrize('tag,use_sigma,sigma_type', [('bolo/mcmc', False, 'relative'), ('bolo/mcmc_sigma', True, 'absolute')])
+def test_reference_spectrum_mcmc_chain_reproduced_on_device(tag, use_sigma, sigma_type):
+    """The chain the reference's spectrum_mcmc produced (golden: its own closure, bolometric.py:154-164, and driver) is
+    reproduced by the device SED problem driven with the same stretch-move draws."""
+    from tests.test_oracle_golden import _sed_driver
+    from lightcurve_fitting_b200 import bolometric as B, models as M, LC
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    ref, burn = _sed_driver(tag, use_sigma, sigma_type, record=True)
+    names = [str(n) for n in GOLD[tag + '/filters']]
+    ep = LC({'MJD': np.full(len(names), 58000.25), 'filter': np.array(_pf(names), dtype=object), 'lum': GOLD[tag + '/lum'],
+             'dlum': GOLD[tag + '/dlum']})
+    priors = [M.UniformPrior(1., 100.), M.LogUniformPrior(0.01, 1000.)] + ([M.GaussianPrior(0., 10.)] if use_sigma else [])
+    prob = B._sed_problem(ep, priors, 0.002, 0., float(GOLD[tag + '/cutoff']), use_sigma, sigma_type, 'fp64')
+    s = EnsembleSampler(10, len(priors), prob, seed=0)
+    s.run_replay(GOLD[tag + '/start'], burn)
+    s.reset()
+    s.run_replay(None, ref.draws)
+    np.testing.assert_allclose(s.flatchain, GOLD[tag + '/flatchain'], rtol=1e-9)
+    np.testing.assert_allclose(s.get_log_prob(), GOLD[tag + '/lnprob'], rtol=1e-9)
+    np.testing.assert_array_equal(s.acceptance_fraction, GOLD[tag + '/acceptance'])
+
+
+def test_shared_ensemble_start_state_from_own_slices():
+    """lcf_ensemble_set_state_slice on two rank-ensembles of one process: each uploads and evaluates only its own walkers and
+    stores them into the other replica; both replicas must equal the state a single ensemble gets from the full array,
+    and the chains that follow must stay bit-identical."""
+    import ctypes as C
+    from lightcurve_fitting_b200._capi import lib, check, dptr
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.synthetic_sc3(npoints=96)
+    prob = wl.device_problem('fp64')
+    nw, nsteps = 48, 3
+    check(lib().lcf_set_tuning_ex(8, 4, 1))
+    try:
+        p0 = wl.start(nw, np.random.default_rng(8))
+        single = EnsembleSampler(nw, wl.ndim, prob, seed=5)
+        single._set_initial(p0, True)
+        want = single._state()
+        ranks = [EnsembleSampler(nw, wl.ndim, prob, seed=5, rank=r, world=2) for r in range(2)]
+        coords, logps, flags = (C.c_void_p * 2)(), (C.c_void_p * 2)(), (C.c_void_p * 2)()
+        for r, s in enumerate(ranks):
+            dc, dl, st, fl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            check(lib().lcf_ensemble_device_view(s.handle, C.byref(dc), C.byref(dl), C.byref(st), None, None, None))
+            check(lib().lcf_ensemble_exchange_view(s.handle, C.byref(fl), None))
+            coords[r], logps[r], flags[r] = dc.value, dl.value, fl.value
+        for s in ranks:
+            check(lib().lcf_ensemble_peers_attach_ptrs(s.handle, coords, logps, flags))
+        per = nw // 2
+        with pytest.raises(ValueError, match='owns'):
+            lib_rc = lib().lcf_ensemble_set_state_slice(ranks[0].handle, 2, per, dptr(np.ascontiguousarray(p0[2:2 + per])))
+            check(lib_rc)
+        for r, s in enumerate(ranks):
+            check(lib().lcf_ensemble_set_state_slice(s.handle, r * per, per, dptr(np.ascontiguousarray(p0[r * per:(r + 1) * per]))))
+        for s in ranks:
+            st = s._state()
+            np.testing.assert_array_equal(st.coords, want.coords)
+            np.testing.assert_array_equal(st.log_prob, want.log_prob)
+        bad = p0.copy()
+        bad[3, 1] = np.nan
+        with pytest.raises(ValueError, match='NaN'):
+            check(lib().lcf_ensemble_set_state_slice(ranks[0].handle, 0, per, dptr(np.ascontiguousarray(bad[:per]))))
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
+def test_calculate_bolometric_device_summaries_match_host_post_processing():
+    """calculate_bolometric end to end on a synthetic table: the posterior summaries taken on the device (Stefan-Boltzmann and
+    pseudo-bolometric luminosity of every sample, percentiles by an in-kernel sort) equal the reference's post-processing
+    (bolometric.py:792-798) applied on the host to the same chains; the least-squares columns equal the per-epoch fits."""
+    import warnings
+    from lightcurve_fitting_b200 import bolometric as B, synthetic
+    import bench
+    lc = synthetic.sed_table(bench.device_truth, nepochs=40, seed=11)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        t0, batch, tm = B.calculate_bolometric(lc, nwalkers=12, burnin_steps=60, steps=50, use_sigma=True, sigma_type='absolute',
+                                               colors=['B-V'], cutoff_freq=1500., seed=4, return_sampler=True, return_timing=True)
+    assert len(t0) == 40 and np.all(batch.status == 0) and tm['sampling_ms'] > 0
+    chain = batch.get_chain()                                       # [E, S, W, 3]
+    flat = chain.reshape(len(t0), -1, 3)
+    for i in range(len(t0)):
+        (T, R), (dT0, dR0), (dT1, dR1) = B.median_and_unc(flat[i][:, :2])
+        Lb, dLb0, dLb1 = B.median_and_unc(B.stefan_boltzmann(flat[i][:, 0], flat[i][:, 1]))
+        Lp, dLp0, dLp1 = B.median_and_unc(B.pseudo(flat[i][:, 0], flat[i][:, 1], 0.002, cutoff_freq=1500.))
+        for names, vals in ((('temp_mcmc', 'dtemp_mcmc0', 'dtemp_mcmc1'), (T, dT0, dT1)), (('radius_mcmc', 'dradius_mcmc0', 'dradius_mcmc1'), (R, dR0, dR1)),
+                            (('L_bol_mcmc', 'dL_bol_mcmc0', 'dL_bol_mcmc1'), (Lb, dLb0, dLb1)), (('L_mcmc', 'dL_mcmc0', 'dL_mcmc1'), (Lp, dLp0, dLp1))):
+            for k, v in zip(names, vals):                              # interval half-widths are differences: tolerance relative to the median
+                np.testing.assert_allclose(t0[k][i], v, rtol=1e-9, atol=1e-11 * abs(vals[0]), err_msg=k)
+    # the truths are recovered (5 % photometry): medians within a few sigma-widths
+    assert np.all(t0['temp_mcmc'].data > 1.) and np.all(np.isfinite(t0['L_mcmc'].data))
+    assert np.all(t0['npoints'].data >= 3) and np.all(np.diff(t0['MJD'].data) > 0)
+    with pytest.raises(NotImplementedError, match='single detected filter'):
+        one = lc[np.asarray(lc['MJD'].data) < 58000.5][:1]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            B.calculate_bolometric(one, min_nfilt=1)
+
+
+@pytest.mark.parametrize('shape', [(0, 0, 0), (1, 8, 4), (4, 4, 2), (8, 8, 1)])
+def test_persistent_chain_kernel_matches_half_step_launches(shape, monkeypatch):
+    """cfg1-sized ensembles (100 walkers) run as ONE cooperative launch of the persistent kernel k_ring, with a device-side
+    barrier between half-steps.  The chain must be bit-identical to the one produced by one k_pass launch per half-step
+    (LCF_RING=0) with the same launch shape, in both precisions, with and without the intrinsic-scatter parameter."""
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    check(lib().lcf_set_tuning_ex(*shape))
+    try:
+        for precision, use_sigma in (('fp32', False), ('fp64', True)):
+            wl = W.example_sc4(use_sigma=use_sigma)
+            prob = wl.device_problem(precision)
+            p0 = wl.start(100, np.random.default_rng(5))
+            out = {}
+            for ring in ('0', '1'):
+                monkeypatch.setenv('LCF_RING', ring)
+                s = EnsembleSampler(100, wl.ndim, prob, seed=31)
+                s.run_mcmc(p0, 7, store=False)
+                s.run_mcmc(None, 9)
+                s.run_mcmc(None, 4)                                   # a second stored run appends to the chain
+                out[ring] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction, prob.last_launch())
+            assert out['1'][3]['kernel'] == 'k_ring' and out['0'][3]['kernel'].startswith('k_pass')
+            assert out['1'][0].shape == (13, 100, wl.ndim)
+            np.testing.assert_array_equal(out['1'][0], out['0'][0])
+            np.testing.assert_array_equal(out['1'][1], out['0'][1])
+            np.testing.assert_array_equal(out['1'][2], out['0'][2])
+        # a large ensemble does not use the persistent kernel (its grid is not co-resident / not launch-bound)
+        monkeypatch.delenv('LCF_RING')
+        wl = W.synthetic_sc3(npoints=400)
+        prob = wl.device_problem('fp32')
+        s = EnsembleSampler(20000, wl.ndim, prob, seed=1)
+        s.run_mcmc(wl.start(20000, np.random.default_rng(1)), 2, skip_initial_state_check=True)
+        assert prob.last_launch()['kernel'].startswith('k_pass')
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))

@@ -291,3 +291,46 @@ def test_oracle_autocorrelation_fft_equals_direct_lag_products():
     y = x.copy()
     y[:, :12, 0] += 5.                                  # half of the walkers sit elsewhere: not converged
     assert rp.split_rhat(y)[0] > 1.3
+
+
+def test_epoch_table_matches_the_per_epoch_loop():
+    """The whole-table preparation of calculate_bolometric (EpochTable) equals the reference-shaped loop over epochs:
+    group_by_epoch -> calcFlux -> bin(delta=inf) -> calcMag -> calcAbsMag -> calcLum (bolometric.py:735-746), epoch by epoch,
+    including integrate_sed, calc_colors, the detected-filter counts and the epoch times."""
+    from lightcurve_fitting_b200 import bolometric as B, LC
+    lc = LC.example()
+    dmag = np.asarray(lc['dmag'].data, float)
+    lc = lc[np.isfinite(dmag) & (dmag > 0.)]
+    tab = B.EpochTable(lc.copy(), 1.)
+    groups = B.group_by_epoch(lc.copy(), 1.)
+    assert tab.n_epochs == len(groups) == 91
+    colors = ['B-V', 'g-r', 'r-i']
+    cols = tab.colors(colors)
+    L_int = tab.integrate_sed()
+    for e, g in enumerate(groups):
+        g.calcFlux()
+        g = g.bin(delta=np.inf)
+        g.meta = dict(lc.meta)
+        g.calcMag(); g.calcAbsMag(); g.calcLum()
+        g['freq'] = np.array([f.freq_eff for f in g['filter'].data])
+        g['dfreq'] = np.array([f.dfreq for f in g['filter'].data])
+        got = tab.epoch_lc(e)
+        assert len(got) == len(g)
+        # rows of an epoch may be ordered differently (set iteration order in LC.bin): align on (filter, source)
+        key = lambda t: sorted(range(len(t)), key=lambda i: (str(t['filter'][i]), str(t['source'][i]) if 'source' in t.colnames else ''))
+        a, b = key(got), key(g)
+        for c in ('MJD', 'flux', 'dflux', 'mag', 'dmag', 'absmag', 'lum', 'dlum', 'freq', 'dfreq'):
+            np.testing.assert_allclose(np.asarray(got[c].data, float)[a], np.asarray(g[c].data, float)[b], rtol=1e-12, atol=0, equal_nan=True, err_msg=c)
+        np.testing.assert_array_equal(np.asarray(got['nondet'].data)[a], np.asarray(g['nondet'].data)[b])
+        det = ~np.asarray(g['nondet'].data, bool)
+        filts = set(np.asarray(g['filter'].data, object)[det])
+        assert tab.nfilt[e] == len(filts)
+        assert tab.filtstr[e] == ''.join(f.char for f in sorted(filts))
+        m, d0, d1 = B.median_and_unc(g['MJD'].data, 100.)
+        np.testing.assert_allclose([tab.mjd_med[e], tab.mjd_med[e] - tab.mjd_min[e], tab.mjd_max[e] - tab.mjd_med[e]], [m, d0, d1], rtol=1e-13, atol=1e-9)
+        np.testing.assert_allclose(L_int[e], B.integrate_sed(g), rtol=1e-12)
+        want = B.calc_colors(g, colors)
+        for j, c in enumerate(colors):
+            np.testing.assert_allclose(cols[c][0][e], want[0][j], rtol=1e-12, atol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(cols[c][1][e], want[1][j], rtol=1e-12, equal_nan=True)
+            assert bool(cols[c][2][e]) == bool(want[2][j]) and bool(cols[c][3][e]) == bool(want[3][j])

@@ -189,3 +189,58 @@ def test_stretch_replay_properties():
         rp.StretchReplay(4, 3, lp).run_mcmc(np.zeros((4, 3)), 1)
     with pytest.raises(ValueError, match='NaN'):
         rp.StretchReplay(8, 3, lambda p: np.nan, random_state=rs).run_mcmc(rs.randn(8, 3), 1)
+
+
+# ---- bolometric.py (reference run through the shim: tests/golden/make_golden.py, section "bolometric.py") ----------------
+def test_bolometric_post_processing_matches_reference():
+    T, R = G['bolo/pseudo/T'], G['bolo/pseudo/R']
+    np.testing.assert_allclose(rp.pseudo(T, R, 0.), G['bolo/pseudo/z0'], rtol=RT)
+    np.testing.assert_allclose(rp.pseudo(T, R, 0.023), G['bolo/pseudo/z'], rtol=RT)
+    np.testing.assert_allclose(rp.pseudo(T, R, 0.01, cutoff_freq=800.), G['bolo/pseudo/cut'], rtol=RT)
+    np.testing.assert_allclose(rp.pseudo(12., 3., 0.002), G['bolo/pseudo/scalar'], rtol=RT)
+    np.testing.assert_allclose(rp.pseudo(T, R, 0.002, filter0=rp.filtdict['V'], filter1=rp.filtdict['B']), G['bolo/pseudo/BtoV'], rtol=RT)
+    np.testing.assert_allclose(rp.sigma_sb, G['bolo/sigma_sb'], rtol=1e-14)
+    np.testing.assert_allclose(rp.stefan_boltzmann(T, R), G['bolo/sb/lum'], rtol=1e-14)
+    lum, dlum = rp.stefan_boltzmann(T, R, G['bolo/sb/dT'], G['bolo/sb/dR'], G['bolo/sb/cov'])
+    np.testing.assert_allclose(lum, G['bolo/sb/lum2'], rtol=1e-14)
+    np.testing.assert_allclose(dlum, G['bolo/sb/dlum'], rtol=1e-14)
+    np.testing.assert_allclose(np.array(rp.median_and_unc(G['bolo/mu/x1'])), G['bolo/mu/out1'], rtol=1e-14)
+    np.testing.assert_allclose(np.array(rp.median_and_unc(G['bolo/mu/x2'])), G['bolo/mu/out2'], rtol=1e-14)
+    np.testing.assert_allclose(np.array(rp.median_and_unc(G['bolo/mu/x1'], 100.)), G['bolo/mu/out1_100'], rtol=1e-14)
+
+
+def test_blackbody_lstsq_matches_reference():
+    off, out = G['bolo/lstsq/offsets'], G['bolo/lstsq/out']
+    for k in range(len(off) - 1):
+        sl = slice(off[k], off[k + 1])
+        # the effective frequencies the reference's Filter objects carried are the oracle's (filters/*/scalars pins the rest)
+        np.testing.assert_allclose([float(rp.filtdict[str(n)].freq_eff) for n in G['bolo/lstsq/filters'][sl]], G['bolo/lstsq/freq'][sl], rtol=1e-12)
+        got = rp.blackbody_lstsq(G['bolo/lstsq/freq'][sl], G['bolo/lstsq/lum'][sl], float(G['bolo/lstsq/z']), cutoff_freq=out[k, 7],
+                                 T_range=(1., out[k, 8]))
+        # curve_fit stops at ftol = xtol = 1e-8 with a finite-difference Jacobian: two runs agree to the optimiser's tolerance
+        np.testing.assert_allclose(got, out[k, :7], rtol=2e-6)
+
+
+def _sed_driver(tag, use_sigma, sigma_type, record=False):
+    names = [str(n) for n in G[tag + '/filters']]
+    model = rp.BlackbodySED(redshift=0.002, cutoff_freq=float(G[tag + '/cutoff']))
+    priors = [rp.UniformPrior(1., 100.), rp.LogUniformPrior(0.01, 1000.)] + ([rp.GaussianPrior(0., 10.)] if use_sigma else [])
+    lp = rp.make_log_posterior(model, priors, np.zeros(len(names)), of(names), G[tag + '/lum'], G[tag + '/dlum'], use_sigma=use_sigma,
+                               sigma_type=sigma_type)
+    np.random.seed(4242)                       # bolometric.py:166-174 under the emcee stand-in: private copy of the global RNG
+    rs = np.random.RandomState()
+    rs.set_state(np.random.get_state())
+    s = rp.StretchReplay(10, len(priors), lp, random_state=rs)
+    pos, _, _ = s.run_mcmc(G[tag + '/start'], 12, record=record)
+    burn = list(s.draws)
+    s.reset()
+    s.run_mcmc(pos, 9, record=record)
+    return s, burn
+
+
+@pytest.mark.parametrize('tag,use_sigma,sigma_type', [('bolo/mcmc', False, 'relative'), ('bolo/mcmc_sigma', True, 'absolute')])
+def test_spectrum_mcmc_chain_matches_reference(tag, use_sigma, sigma_type):
+    s, _ = _sed_driver(tag, use_sigma, sigma_type)
+    np.testing.assert_allclose(s.flatchain, G[tag + '/flatchain'], rtol=1e-12)
+    np.testing.assert_allclose(s.get_log_prob(), G[tag + '/lnprob'], rtol=1e-12)
+    np.testing.assert_array_equal(s.acceptance_fraction, G[tag + '/acceptance'])
