@@ -204,12 +204,13 @@ struct lcf_batch {
     double last_ms = 0.;
     long long last_launches = 0;
     std::vector<lcf_problem *> owned;             // problems created by lcf_sed_batch_create (destroyed with the batch)
-    void *d_shared = nullptr;                     // their device arrays and tile tables: one allocation
+    void *d_shared = nullptr, *d_shared_tiles = nullptr;   // their device arrays / tile tables: one allocation each
+    size_t chain_cap = 0, lnp_cap = 0;            // grow-only chain buffers
     double *d_lpseudo = nullptr, *d_summary = nullptr;
     size_t lpseudo_cap = 0;
     ~lcf_batch() {
         for (lcf_problem *p : owned) delete p;
-        cudaFree(d_shared); cudaFree(d_lpseudo); cudaFree(d_summary);
+        cudaFree(d_shared); cudaFree(d_shared_tiles); cudaFree(d_lpseudo); cudaFree(d_summary);
         cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_order); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
         cudaFree(d_acc); cudaFree(d_status);
         if (ev0) cudaEventDestroy(ev0);
@@ -321,6 +322,40 @@ int build_tiles(lcf_problem *p, int l) {
     p->tiles[l].tiles = reinterpret_cast<const int4 *>(d);
     p->tiles[l].ntiles = (int)t.size();
     p->tiles_built[l] = true;
+    return 0;
+}
+
+// Tile tables of MANY problems (all six walkers-per-CTA exponents) in one allocation and one copy: the problems of a batch
+// created from flat arrays are tiny (an SED epoch has 3-9 points), and a cudaMalloc + cudaMemcpy pair per problem and
+// shape was most of the time spent creating them.  The caller owns `*block`.
+int build_tiles_shared(const std::vector<lcf_problem *> &probs, void **block) {
+    std::vector<int4> all;
+    std::vector<size_t> first;
+    std::vector<int> count;
+    for (lcf_problem *p : probs) {
+        const int N = p->dev.npoints;
+        for (int l = 0; l < 6; ++l) {
+            const int ppt = 2 * (32 >> l);
+            first.push_back(all.size());
+            int i = 0;
+            while (i < N) {
+                int f = p->h_point_filter[i], j = i;
+                while (j < N && p->h_point_filter[j] == f) ++j;
+                for (int s = i; s < j; s += ppt) all.push_back(make_int4(s, std::min(ppt, j - s), f, 0));
+                i = j;
+            }
+            count.push_back((int)(all.size() - first.back()));
+        }
+    }
+    int rc = upload(all, block);
+    if (rc) return rc;
+    size_t k = 0;
+    for (lcf_problem *p : probs)
+        for (int l = 0; l < 6; ++l, ++k) {
+            p->tiles[l].tiles = reinterpret_cast<const int4 *>(*block) + first[k];
+            p->tiles[l].ntiles = count[k];
+            p->tiles_built[l] = true;
+        }
     return 0;
 }
 
@@ -593,7 +628,7 @@ int lcf_set_tuning(int walkers_per_cta, int warps_per_cta) {
 
 #ifdef LCF_X_TIMING
 int lcf_debug_phase_clocks(unsigned long long *out) {   // experiment builds only: read and reset the per-phase clock sums
-    unsigned long long z[8] = {0};
+    unsigned long long z[10] = {0};
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(z));
     cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
@@ -1710,10 +1745,18 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     if (!b->has_state) return fail(LCF_ERR_STATE, "batch has no initial state");
     if (nburn < 0 || nsteps < 0) return fail(LCF_ERR_ARG, "negative step count");
     CUDA_TRY(cudaSetDevice(b->probs[0]->device));
-    cudaFree(b->d_chain); cudaFree(b->d_lnp);
-    b->d_chain = nullptr; b->d_lnp = nullptr;
-    CUDA_TRY(cudaMalloc(&b->d_chain, std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W * b->D)));
-    CUDA_TRY(cudaMalloc(&b->d_lnp, std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W)));
+    const size_t need_chain = std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W * b->D);
+    const size_t need_lnp = std::max<size_t>(16, sizeof(double) * b->nprob * nsteps * b->W);
+    if (need_chain > b->chain_cap) {
+        cudaFree(b->d_chain); b->d_chain = nullptr; b->chain_cap = 0;
+        CUDA_TRY(cudaMalloc(&b->d_chain, need_chain));
+        b->chain_cap = need_chain;
+    }
+    if (need_lnp > b->lnp_cap) {
+        cudaFree(b->d_lnp); b->d_lnp = nullptr; b->lnp_cap = 0;
+        CUDA_TRY(cudaMalloc(&b->d_lnp, need_lnp));
+        b->lnp_cap = need_lnp;
+    }
     CUDA_TRY(cudaMemsetAsync(b->d_acc, 0, sizeof(unsigned long long) * b->nprob * b->W, b->stream));
     BatchDev B;
     memset(&B, 0, sizeof(B));
@@ -1813,11 +1856,15 @@ int lcf_sed_batch_create(int64_t nepochs, const int32_t *offsets, const int32_t 
         delete probs[i]->pending;
         probs[i]->pending = nullptr;
     }
-    lcf_batch *b = nullptr;
-    int rc = lcf_batch_create(nepochs, probs.data(), nwalkers, seed, &b);
+    void *tblock = nullptr;
+    int rc = build_tiles_shared(probs, &tblock);
     if (rc) { cudaFree(dblock); cleanup(); return rc; }
+    lcf_batch *b = nullptr;
+    rc = lcf_batch_create(nepochs, probs.data(), nwalkers, seed, &b);
+    if (rc) { cudaFree(dblock); cudaFree(tblock); cleanup(); return rc; }
     b->owned = probs;
     b->d_shared = dblock;
+    b->d_shared_tiles = tblock;
     *out = b;
     return 0;
 }

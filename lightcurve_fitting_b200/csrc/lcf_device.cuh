@@ -25,7 +25,7 @@
 namespace lcf {
 
 #ifdef LCF_X_TIMING   // experiment builds: per-phase SM clocks summed over CTAs (thread 0), see tools/microbench
-__device__ unsigned long long g_phase_clk[8];
+__device__ unsigned long long g_phase_clk[10];
 #define LCF_TICK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 #define LCF_TICK_INIT long long _t0 = clock64()
 #else
@@ -1459,7 +1459,13 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
             Mv.comp_base = half ? 0 : G.n0;
             const long long ng = (Mv.Ns + wpb - 1) / wpb;
             for (long long g = cid; g < ng; g += nclusters) { group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize); first = false; }
+#ifdef LCF_X_TIMING
+            const long long tb0 = clock64();
+#endif
             ring_barrier(G.bar, gen);
+#ifdef LCF_X_TIMING
+            if (threadIdx.x == 0) atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - tb0));
+#endif
         }
     }
 }

@@ -287,6 +287,43 @@ def main():
         G[tag + '/lnprob'] = smp.get_log_prob()
         G[tag + '/acceptance'] = smp.acceptance_fraction
 
+    # ---- posterior statistics of a long reference run (statistical parity of the native device sampler) ---------------------
+    # ShockCooling2 (T_1, L_1, t_tr, t_0): a well-constrained, unimodal posterior, truth inside the priors
+    m3 = RM.ShockCooling2(redshift=0.002)
+    p_true = np.array([20., 2., 6., 57467.8])
+    srng = np.random.default_rng(99)
+    ts = np.sort(srng.uniform(57468.3, 57482., N))
+    fs = rfilters([names9[i % 8] for i in srng.permutation(N)])
+    ys = m3(ts, fs, *p_true)
+    dys = 0.05 * np.abs(ys)
+    ys = ys + dys * srng.normal(size=N)
+    lcs = MiniLC(MJD=ts, filter=fs, lum=ys, dlum=dys)
+    pri3 = [RM.UniformPrior(5., 60.), RM.UniformPrior(0.1, 20.), RM.UniformPrior(1., 30.), RM.UniformPrior(57465., 57468.2)]
+    np.random.seed(2024)
+    s3 = RFit.lightcurve_mcmc(lcs, m3, priors=pri3, p_lo=p_true * [0.9, 0.9, 0.9, 1.] - [0, 0, 0, 0.1], p_up=p_true * [1.1, 1.1, 1.1, 1.] + [0, 0, 0, 0.1],
+                              nwalkers=32, nsteps=1200, nsteps_burnin=600)
+    G['stats/t'], G['stats/filters'], G['stats/y'], G['stats/dy'], G['stats/p_true'] = ts, np.array([f.name for f in fs]), ys, dys, p_true
+    G['stats/percentiles'] = np.percentile(s3.flatchain, [16., 50., 84.], axis=0)
+    G['stats/mean'], G['stats/cov'] = s3.flatchain.mean(axis=0), np.cov(s3.flatchain.T)
+    G['stats/acceptance'] = np.array(s3.acceptance_fraction.mean())
+    G['stats/setup'] = np.array([32, 600, 1200])
+
+    # ---- every filter with a transmission curve: moments of the normalised curve as read by the reference (filters.py:170-230) --
+    names_all, rows_all = [], []
+    for f in RF.all_filters:
+        if not f.filename:
+            continue
+        try:
+            nu = np.asarray(f.trans['freq'].value, float)
+            tn = np.asarray(f.trans['T_norm_per_freq'].data, float)
+        except Exception:
+            continue
+        names_all.append(f.name)
+        rows_all.append([len(nu), nu[0], nu[-1], nu.sum(), tn.sum(), (nu * tn).sum(), (nu * nu * tn).sum(), np.abs(np.diff(tn)).sum(),
+                         float(f.freq_eff.value), float(np.asarray(f.dfreq)), float(f.wl_eff.value), f.m0, f.M0])
+    G['filters_all/names'] = np.array(names_all)
+    G['filters_all/moments'] = np.array(rows_all)
+
     out = os.path.join(HERE, 'reference_golden.npz')
     np.savez_compressed(out, **G)
     print('wrote', out, '%d arrays, %.0f kB' % (len(G), os.path.getsize(out) / 1e3))

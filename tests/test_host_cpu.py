@@ -334,3 +334,17 @@ def test_epoch_table_matches_the_per_epoch_loop():
             np.testing.assert_allclose(cols[c][0][e], want[0][j], rtol=1e-12, atol=1e-12, equal_nan=True)
             np.testing.assert_allclose(cols[c][1][e], want[1][j], rtol=1e-12, equal_nan=True)
             assert bool(cols[c][2][e]) == bool(want[2][j]) and bool(cols[c][3][e]) == bool(want[3][j])
+
+
+def test_every_product_filter_curve_matches_reference_moments():
+    """The product's Filter.read_curve for every filter with a curve, against the moments the reference produced (golden)."""
+    import os
+    from lightcurve_fitting_b200.filters import filtdict
+    G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.npz'))
+    for n, row in zip(G['filters_all/names'], G['filters_all/moments']):
+        f = filtdict[str(n)]
+        tr = f.trans
+        nu, tn = tr['freq'], tr['T_norm_per_freq']
+        got = [len(nu), nu[0], nu[-1], nu.sum(), tn.sum(), (nu * tn).sum(), (nu * nu * tn).sum(), np.abs(np.diff(tn)).sum(),
+               f.freq_eff, f.dfreq, f.wl_eff, f.m0, f.M0]
+        np.testing.assert_allclose(got, row, rtol=1e-11, err_msg=str(n))

@@ -244,3 +244,18 @@ def test_spectrum_mcmc_chain_matches_reference(tag, use_sigma, sigma_type):
     np.testing.assert_allclose(s.flatchain, G[tag + '/flatchain'], rtol=1e-12)
     np.testing.assert_allclose(s.get_log_prob(), G[tag + '/lnprob'], rtol=1e-12)
     np.testing.assert_array_equal(s.acceptance_fraction, G[tag + '/acceptance'])
+
+
+def test_every_filter_curve_matches_reference_moments():
+    """All filters with a transmission curve (not only the 16 whose full curves are frozen): sample count, end frequencies and
+    five moments of (freq, T_norm_per_freq) as the reference's read_curve produced them, plus freq_eff / dfreq / wl_eff / zero
+    points.  A packing error in data/filter_curves.npz or filter_registry.py, which the oracle and the product share, cannot
+    hide behind a common mode."""
+    names, mom = G['filters_all/names'], G['filters_all/moments']
+    assert len(names) >= 60
+    for n, row in zip(names, mom):
+        f = rp.filtdict[str(n)]
+        nu, tn = np.asarray(f.trans['freq'], float), np.asarray(f.trans['T_norm_per_freq'], float)
+        got = [len(nu), nu[0], nu[-1], nu.sum(), tn.sum(), (nu * tn).sum(), (nu * nu * tn).sum(), np.abs(np.diff(tn)).sum(),
+               float(f.freq_eff), float(f.dfreq), row[10], f.m0, f.M0]      # (the oracle's filter does not carry wl_eff)
+        np.testing.assert_allclose(got, row, rtol=1e-11, err_msg=str(n))

@@ -43,7 +43,7 @@ def child(args):
         L = _capi.lib()
         if hasattr(L, 'lcf_debug_phase_clocks'):
             import ctypes as C
-            buf = (C.c_uint64 * 8)()
+            buf = (C.c_uint64 * 10)()
             L.lcf_debug_phase_clocks(buf)                      # reset
             s.run_mcmc(None, 1, skip_initial_state_check=True, store=False)
             L.lcf_debug_phase_clocks(buf)
