@@ -265,6 +265,9 @@ int  lcf_set_tuning(int walkers_per_cta, int warps_per_cta);
 /* same, plus the thread-block-cluster size (power of two <= 8): the CTAs of a cluster share one
    walker group and split its light curve between them (small ensembles on many SMs).          */
 int  lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size);
+/* split-K override: the transmission samples of a (walker, point pair) are swept by `sample_chunks` lanes (power of two, walkers per
+   CTA x chunks <= 32) whose partial sums are combined with warp shuffles -- small ensembles / SED epochs; 0 = heuristic.        */
+int  lcf_set_tuning_split(int sample_chunks);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ struct NvtxRange {
 };
 
 thread_local std::string g_err;
-int g_tune_wpb = 0, g_tune_nw = 0, g_tune_cluster = 0;
+int g_tune_wpb = 0, g_tune_nw = 0, g_tune_cluster = 0, g_tune_ks = -1;   // launch-shape overrides (0 / -1: heuristic)
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -127,9 +127,9 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     TileDev tiles[6];                           // per wpb_log2
     bool tiles_built[6] = {false, false, false, false, false, false};
-    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1; size_t smem = 0; double cost = 0.; } shape_cache;
+    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0; size_t smem = 0; double cost = 0.; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
-    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1; long long grid = 0; } last_launch;   // lcf_problem_last_launch
+    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0; long long grid = 0; } last_launch;   // lcf_problem_last_launch
     double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
     int *d_eval_nan = nullptr;
     size_t eval_q_cap = 0, eval_out_cap = 0;
@@ -189,7 +189,7 @@ struct lcf_ensemble {
 struct lcf_batch {
     std::vector<lcf_problem *> probs;
     long long W = 0, n0 = 0, nprob = 0, nsteps_stored = 0, iteration = 0;
-    int D = 0, model = 0, precision = 0, wpb_log2 = 0, nw = 0;
+    int D = 0, model = 0, precision = 0, wpb_log2 = 0, nw = 0, ks = 0;
     size_t smem = 0;
     unsigned long long seed = 0;
     ProblemDev *d_probs = nullptr;
@@ -381,13 +381,13 @@ int count_tiles(const lcf_problem *p, int l) {
     return tiles;
 }
 
-struct Shape { int l, nw, cluster; size_t smem; double cost; };
+struct Shape { int l, nw, cluster; size_t smem; double cost; int ks; };
 
 int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
-    const int tune = (g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster;
+    const int tune = ((g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster) * 8 + (g_tune_ks + 1);
     if (p->shape_cache.Ns == Ns && p->shape_cache.tune == tune) {
         out->l = p->shape_cache.l; out->nw = p->shape_cache.nw; out->cluster = p->shape_cache.cluster; out->smem = p->shape_cache.smem;
-        out->cost = p->shape_cache.cost;
+        out->cost = p->shape_cache.cost; out->ks = p->shape_cache.ks;
         return 0;
     }
     int sms = 148;
@@ -398,36 +398,43 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
     const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
     double best = 1e300;
-    Shape bs = {5, 16, 1, 0, 0.};
+    Shape bs = {5, 16, 1, 0, 0., 0};
     for (int l = 5; l >= 0; --l) {
         if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
-        const int ntiles = count_tiles(p, l);
         const long long groups = (Ns + (1 << l) - 1) >> l;
-        const int nw_cand[5] = {16, 8, 4, 2, g_tune_nw};   // candidates; the last entry is the override
-        for (int ci = (g_tune_nw > 0 ? 4 : 0); ci < (g_tune_nw > 0 ? 5 : 4); ++ci) {
-            const int nw = nw_cand[ci];
-            const size_t sm = smem_bytes(p, 1 << l, nw);
-            if (sm > kSmemMax) continue;
-            int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
-            occ = std::max(1, std::min(occ, 32));
-            for (int S = 1; S <= kMaxCluster; S <<= 1) {
-                if (g_tune_cluster > 0 && S != g_tune_cluster) continue;
-                if (S > 1 && (long long)nw * S > 2LL * ntiles && g_tune_cluster == 0) break;    // nothing left to split
-                const double tiles_warp = (double)((ntiles + nw * S - 1) / (nw * S));
-                const double tiles_cta = std::min<double>(ntiles, tiles_warp * nw);
-                const long long ctas = groups * S;
-                const double n = (double)((ctas + sms - 1) / sms);               // CTAs on the busiest SM
-                const double resident = std::min<double>(n, occ);
-                const double w = std::min(32., resident * nw);
-                const double xu_eff = w >= 8. ? 1. - 0.29 * (32. - w) * (32. - w) / 576. : 0.71 * w / 8.;
-                const double fixed = 12000. + (S > 1 ? 3000. : 0.);            // proposal + priors + FP64 model constants (+ DSMEM reduce)
-                const double t_xu = n * tiles_cta * pipe_tile / xu_eff + 0.3 * fixed;
-                const double t_lat = std::ceil(n / occ) * (fixed + tiles_warp * lat_tile);
-                double cost = std::max(t_xu, t_lat);
-                for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
-                if (nw < 8) cost *= 1.15;
-                if (ctas < sms) cost *= 1. + 0.25 * (1. - (double)ctas / sms);  // measured (cfg1 sweep): idle SMs cost more than the chain model says
-                if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; }
+        // split-K: 2^ks lanes share a (walker, point pair) and each sweeps 1/2^ks of the filter's samples (front end repeated)
+        for (int ks = 0; l + ks <= 5; ++ks) {
+            if (g_tune_ks >= 0 && ks != g_tune_ks) continue;
+            const int ntiles = count_tiles(p, l + ks);
+            const double Kc = K / (double)(1 << ks);
+            const double pipe_tile = 64. * (f32 ? (Kc + 5.) / 14.5 : 0.9 * Kc + 4.);   // SM clocks per tile at full pipe rate
+            const double lat_tile = (f32 ? 70. : 600.) * Kc + 500. + (ks ? 60. * ks : 0.);   // clocks one warp needs for a tile on its own
+            const int nw_cand[5] = {16, 8, 4, 2, g_tune_nw};   // candidates; the last entry is the override
+            for (int ci = (g_tune_nw > 0 ? 4 : 0); ci < (g_tune_nw > 0 ? 5 : 4); ++ci) {
+                const int nw = nw_cand[ci];
+                const size_t sm = smem_bytes(p, 1 << l, nw);
+                if (sm > kSmemMax) continue;
+                int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
+                occ = std::max(1, std::min(occ, 32));
+                for (int S = 1; S <= kMaxCluster; S <<= 1) {
+                    if (g_tune_cluster > 0 && S != g_tune_cluster) continue;
+                    if (S > 1 && (long long)nw * S > 2LL * ntiles && g_tune_cluster == 0) break;    // nothing left to split
+                    const double tiles_warp = (double)((ntiles + nw * S - 1) / (nw * S));
+                    const double tiles_cta = std::min<double>(ntiles, tiles_warp * nw);
+                    const long long ctas = groups * S;
+                    const double n = (double)((ctas + sms - 1) / sms);               // CTAs on the busiest SM
+                    const double resident = std::min<double>(n, occ);
+                    const double w = std::min(32., resident * nw);
+                    const double xu_eff = w >= 8. ? 1. - 0.29 * (32. - w) * (32. - w) / 576. : 0.71 * w / 8.;
+                    const double fixed = 12000. + (S > 1 ? 3000. : 0.);            // proposal + priors + FP64 model constants (+ DSMEM reduce)
+                    const double t_xu = n * tiles_cta * pipe_tile / xu_eff + 0.3 * fixed;
+                    const double t_lat = std::ceil(n / occ) * (fixed + tiles_warp * lat_tile);
+                    double cost = std::max(t_xu, t_lat);
+                    for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
+                    if (nw < 8) cost *= 1.15;
+                    if (ctas < sms) cost *= 1. + 0.25 * (1. - (double)ctas / sms);  // measured (cfg1 sweep): idle SMs cost more than the chain model says
+                    if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; bs.ks = ks; }
+                }
             }
         }
     }
@@ -435,7 +442,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
         if (g_tune_nw > 16 || g_tune_wpb > 32) return fail(LCF_ERR_ARG, "bad tuning override");
         return fail(LCF_ERR_ARG, "filter bank needs more than %zu bytes of shared memory: too many transmission samples", kSmemMax);
     }
-    int rc = build_tiles(p, bs.l);
+    int rc = build_tiles(p, bs.l + bs.ks);
     if (rc) return rc;
     for (int plain = 0; plain < 2; ++plain) {
         PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
@@ -443,11 +450,11 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
         if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), bs.smem))) return rc;
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
-    p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune; p->shape_cache.cost = best;
+    p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune; p->shape_cache.cost = best; p->shape_cache.ks = bs.ks;
     bs.cost = best;
     if (getenv("LCF_DEBUG_SHAPE"))
-        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, %zu B smem (model %d, modelled %.0f clk)\n",
-                Ns, 1 << bs.l, bs.nw, bs.cluster, bs.smem, p->dev.model, best);
+        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, split-K %d, %zu B smem (model %d, modelled %.0f clk)\n",
+                Ns, 1 << bs.l, bs.nw, bs.cluster, 1 << bs.ks, bs.smem, p->dev.model, best);
     *out = bs;
     return 0;
 }
@@ -459,6 +466,7 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     int rc = choose_shape(p, mv.Ns, &sh);
     if (rc) return rc;
     mv.wpb_log2 = sh.l;
+    mv.ks = sh.ks;
     const bool plain = mv.mode != MODE_MODEL && !p->dev.use_sigma;
     PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain)
                                                         : pass_kernel_for<double>(p->dev.model, sh.l, plain);
@@ -486,8 +494,8 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], mv));
-    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l + sh.ks], mv));
+    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
     if (launches) ++*launches;
     return 0;
@@ -635,6 +643,13 @@ int lcf_debug_phase_clocks(unsigned long long *out) {   // experiment builds onl
     return 0;
 }
 #endif
+
+int lcf_set_tuning_split(int sample_chunks) {
+    if (sample_chunks < 0 || sample_chunks > 32 || (sample_chunks & (sample_chunks - 1))) return fail(LCF_ERR_ARG, "sample_chunks must be 0 or a power of two <= 32");
+    g_tune_ks = -1;
+    for (int k = 0; sample_chunks && k <= 5; ++k) if ((1 << k) == sample_chunks) g_tune_ks = k;
+    return 0;
+}
 
 int lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size) {
     if (cluster_size < 0 || cluster_size > kMaxCluster || (cluster_size & (cluster_size - 1)))
@@ -1224,7 +1239,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const int ring_key = (sh.l * 64 + sh.nw) * 16 + sh.cluster;
+    const int ring_key = ((sh.l * 64 + sh.nw) * 16 + sh.cluster) * 8 + sh.ks;
     if (e->ring_ok < 0 || e->ring_key != ring_key) {            // does the whole grid fit on the device at once?
         e->ring_key = ring_key;
         long long capacity = 0;
@@ -1246,7 +1261,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     if (!e->ring_ok) return 0;
     if (!e->d_ring_bar) CUDA_TRY(cudaMalloc(&e->d_ring_bar, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(e->d_ring_bar, 0, 2 * sizeof(unsigned int), e->stream));
-    rc = build_tiles(p, sh.l);
+    rc = build_tiles(p, sh.l + sh.ks);
     if (rc) return rc;
     RingDev G;
     memset(&G, 0, sizeof(G));
@@ -1258,8 +1273,9 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     G.seed = e->seed;
     G.bar = e->d_ring_bar;
     G.wpb_log2 = sh.l;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l], G));
-    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster;
+    G.ks = sh.ks;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l + sh.ks], G));
+    p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3;
     e->last_launches += 1;
     e->iteration += nsteps;
@@ -1667,10 +1683,26 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
         if (smem + 2048 <= (l > 5 ? kSmemMax / 4 : kSmemMax / 2) || l == 0) break;
         --l;
     }
+    // split-K for narrow groups of small problems (an SED epoch has 3-9 points, one per filter): with 2^ks lanes per (walker, point
+    // pair) a warp is full of short loops instead of a quarter full of long ones.  Chosen from the mean number of points that
+    // share a filter: a tile of 2 * 32 / (wpb 2^ks) points should still be about full.
+    int ks = 0;
+    if (l < 5) {
+        double runs = 0., pts = 0.;
+        for (lcf_problem *p : b->probs) {
+            const int N = p->dev.npoints;
+            for (int i = 0; i < N; ++i) runs += (i == 0 || p->h_point_filter[i] != p->h_point_filter[i - 1]);
+            pts += N;
+        }
+        const double per_filter = pts / std::max(1., runs);
+        while (l + ks < 5 && (double)(32 >> (l + ks)) >= per_filter) ++ks;     // 2 * (32 >> (l + ks + 1)) >= points per filter
+        if (g_tune_ks >= 0) ks = std::min(g_tune_ks, 5 - l);
+    }
+    b->ks = ks;
     std::vector<ProblemDev> hp(nproblems);
     std::vector<TileDev> ht(nproblems);
     for (long long i = 0; i < nproblems; ++i) {
-        const int lt = std::min(l, 5);                   // wide groups use the 32-walker tiles (two points per lane)
+        const int lt = std::min(l, 5) + ks;              // wide groups use the 32-walker tiles (two points per lane)
         if ((rc = build_tiles(b->probs[i], lt))) { delete b; return rc; }
         hp[i] = b->probs[i]->dev;
         ht[i] = b->probs[i]->tiles[lt];
@@ -1686,8 +1718,8 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     b->nw = nw;
     b->smem = smem;
     if (getenv("LCF_DEBUG_SHAPE"))
-        fprintf(stderr, "[lcf] batch shape: %lld problems, %lld walkers, %d walkers/pass, %d warps, %zu B smem\n", (long long)nproblems,
-                (long long)nwalkers, 1 << l, nw, smem);
+        fprintf(stderr, "[lcf] batch shape: %lld problems, %lld walkers, %d walkers/pass, %d warps, split-K %d, %zu B smem\n", (long long)nproblems,
+                (long long)nwalkers, 1 << l, nw, 1 << b->ks, smem);
     void *dp;
     if ((rc = upload(hp, &dp))) { delete b; return rc; }
     b->d_probs = reinterpret_cast<ProblemDev *>(dp);
@@ -1765,7 +1797,7 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     B.chain = b->d_chain; B.lnp = b->d_lnp;
     B.W = b->W; B.n0 = b->n0; B.nproblems = b->nprob;
     B.nburn = nburn; B.nsteps = nsteps; B.iter0 = b->iteration;
-    B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.init_logp = b->need_init_logp ? 1 : 0;
+    B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.ks = b->ks; B.init_logp = b->need_init_logp ? 1 : 0;
     ChainKernel k = (b->precision == LCF_PRECISION_FP32) ? chain_kernel_for<float>(b->model) : chain_kernel_for<double>(b->model);
     if (!k) return fail(LCF_ERR_ARG, "unknown model");
     { int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), b->smem); if (rc) return rc; }

@@ -80,6 +80,7 @@ struct MoveDev {
     int *nanflag;
     long long W, n0;                 // n0 = rows of colour 0
     int mode, wpb_log2;
+    int ks;                          // log2 of the sample chunks a (walker, point pair) is split into (split-K tiles, small problems)
     // active set: physical row = act_rows ? act_rows[i] : act_base + i,  i in [0, Ns)
     long long Ns, act_base;
     const int *act_rows;
@@ -804,23 +805,23 @@ template <typename R> struct PointFE {
     int state;
 };
 
-// Blackbody part of up to two points of one filter for one walker.
+// Planck x transmission sums of up to two points of one filter for one walker, over the pair records [k_lo, k_lo + k_cnt) of
+// the filter (the whole filter, or one chunk of it when a tile is split over several lanes).  S0 / S1: sums at the points'
+// temperatures; S0s / S1s (ShockCooling4 only): at 0.74 T.  Lanes that share a (walker, point pair) take the same path, because
+// the guards only look at the filter's exponent range and the two temperatures.
 template <int MODEL, typename R, int TS>
-__device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *bank, const int4 fi,
-                                               const PointFE<R> &f0, const PointFE<R> &f1, bool two,
-                                               const typename Vec2<R>::type *tab, int ts_rt, const double *e2t, R &y0, R &y1) {
-    typedef Mth<R> M;
+__device__ __forceinline__ void blackbody_sums(const typename Vec4<R>::type *bank, const int4 fi, int k_lo, int k_cnt,
+                                               const PointFE<R> &f0, const PointFE<R> &f1, bool n0, bool n1,
+                                               const typename Vec2<R>::type *tab, int ts_rt, const double *e2t, R &S0, R &S0s, R &S1, R &S1s) {
     typedef typename Vec2<R>::type R2;
     typedef typename Vec4<R>::type R4;
     const int ts = TS > 0 ? TS : ts_rt;
-    const int k0 = fi.x, K2 = fi.y;                                     // pair records of this filter
+    const int k0 = fi.x + k_lo, K2 = k_cnt;
     const R4 *b = bank + k0;
     const R2 *tb = tab + (size_t)k0 * ts;
-    const R c74 = (R)(1. / 0.74), c74_4 = (R)(1. / (0.74 * 0.74 * 0.74 * 0.74));
-    y0 = f0.amp;
-    y1 = f1.amp;
-    const bool n0 = f0.state == 1, n1 = two && f1.state == 1;
-    if (!n0 && !n1) return;
+    const R c74 = (R)(1. / 0.74);
+    S0 = S0s = S1 = S1s = (R)0;
+    if ((!n0 && !n1) || K2 <= 0) return;
     if (sizeof(R) == 4) {
         const float2 rng = make_float2(__int_as_float(fi.z), __int_as_float(fi.w));   // (a_min, a_max) of the filter
         const float i0 = n0 ? (float)f0.invT : (float)f1.invT, i1 = n1 ? (float)f1.invT : i0;
@@ -833,24 +834,18 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
 #endif
             const float4 *bf = reinterpret_cast<const float4 *>(b);
             const float2 *tf = reinterpret_cast<const float2 *>(tb);
-            float S0, S1;
+            float s0, s1, s0s = 0.f, s1s = 0.f;
             if (MODEL == 4) {
-                float S0s, S1s;
-                if (clamp) planck_quad_sc4_f32<true>(bf, K2, i0, i1, S0, S0s, S1, S1s);
-                else planck_quad_sc4_f32<false>(bf, K2, i0, i1, S0, S0s, S1, S1s);
-                if (n0) y0 = (R)fminf((float)f0.amp * S0, (float)f0.amp * (float)c74_4 * S0s);   // models.py:631
-                if (n1) y1 = (R)fminf((float)f1.amp * S1, (float)f1.amp * (float)c74_4 * S1s);
+                if (clamp) planck_quad_sc4_f32<true>(bf, K2, i0, i1, s0, s0s, s1, s1s);
+                else planck_quad_sc4_f32<false>(bf, K2, i0, i1, s0, s0s, s1, s1s);
+            } else if (MODEL == 3) {
+                if (clamp) planck_quad_f32<true, true, TS>(bf, K2, i0, i1, tf, ts, s0, s1);
+                else planck_quad_f32<true, false, TS>(bf, K2, i0, i1, tf, ts, s0, s1);
             } else {
-                if (MODEL == 3) {
-                    if (clamp) planck_quad_f32<true, true, TS>(bf, K2, i0, i1, tf, ts, S0, S1);
-                    else planck_quad_f32<true, false, TS>(bf, K2, i0, i1, tf, ts, S0, S1);
-                } else {
-                    if (clamp) planck_quad_f32<false, true, TS>(bf, K2, i0, i1, nullptr, ts, S0, S1);
-                    else planck_quad_f32<false, false, TS>(bf, K2, i0, i1, nullptr, ts, S0, S1);
-                }
-                if (n0) y0 = (R)((float)f0.amp * S0);
-                if (n1) y1 = (R)((float)f1.amp * S1);
+                if (clamp) planck_quad_f32<false, true, TS>(bf, K2, i0, i1, nullptr, ts, s0, s1);
+                else planck_quad_f32<false, false, TS>(bf, K2, i0, i1, nullptr, ts, s0, s1);
             }
+            S0 = (R)s0; S1 = (R)s1; S0s = (R)s0s; S1s = (R)s1s;
             return;
         }
     }
@@ -865,18 +860,11 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
             i1 = fmin(i1, icap);
             const double4 *bd = reinterpret_cast<const double4 *>(b);
             const double2 *td = reinterpret_cast<const double2 *>(tb);
-            double S0, S1;
-            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, ts, e2t, S0, S1);
-            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, ts, e2t, S0, S1);
-            if (MODEL == 4) {
-                double S0s, S1s;
-                planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, ts, e2t, S0s, S1s);
-                if (n0) y0 = (R)fmin((double)f0.amp * S0, (double)f0.amp * (double)c74_4 * S0s);   // models.py:631
-                if (n1) y1 = (R)fmin((double)f1.amp * S1, (double)f1.amp * (double)c74_4 * S1s);
-            } else {
-                if (n0) y0 = (R)((double)f0.amp * S0);
-                if (n1) y1 = (R)((double)f1.amp * S1);
-            }
+            double s0, s1, s0s = 0., s1s = 0.;
+            if (MODEL == 3) planck_quad_f64<true>(bd, K2, i0, i1, td, ts, e2t, s0, s1);
+            else planck_quad_f64<false>(bd, K2, i0, i1, nullptr, ts, e2t, s0, s1);
+            if (MODEL == 4) planck_quad_f64<false>(bd, K2, i0 * (double)c74, i1 * (double)c74, nullptr, ts, e2t, s0s, s1s);
+            S0 = (R)s0; S1 = (R)s1; S0s = (R)s0s; S1s = (R)s1s;
             return;
         }
     }
@@ -885,15 +873,21 @@ __device__ __forceinline__ void blackbody_pair(const typename Vec4<R>::type *ban
     atomicAdd(&g_phase_clk[5], 1ull << 40);                   // lane-tiles on the careful path (upper bits of slot 5)
 #endif
     if (n0) {
-        const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f0.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f0.invT, nullptr, 0);
-        y0 = f0.amp * S;
-        if (MODEL == 4) y0 = M::mn(y0, f0.amp * c74_4 * planck_sum_safe<R, false>(b, K2, f0.invT * c74, nullptr, 0));
+        S0 = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f0.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f0.invT, nullptr, 0);
+        if (MODEL == 4) S0s = planck_sum_safe<R, false>(b, K2, f0.invT * c74, nullptr, 0);
     }
     if (n1) {
-        const R S = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f1.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f1.invT, nullptr, 0);
-        y1 = f1.amp * S;
-        if (MODEL == 4) y1 = M::mn(y1, f1.amp * c74_4 * planck_sum_safe<R, false>(b, K2, f1.invT * c74, nullptr, 0));
+        S1 = (MODEL == 3) ? planck_sum_safe<R, true>(b, K2, f1.invT, tb, ts) : planck_sum_safe<R, false>(b, K2, f1.invT, nullptr, 0);
+        if (MODEL == 4) S1s = planck_sum_safe<R, false>(b, K2, f1.invT * c74, nullptr, 0);
     }
+}
+// model value of a point from its sums (ShockCooling4: min over the two blackbodies, models.py:629-631)
+template <int MODEL, typename R>
+__device__ __forceinline__ R blackbody_value(const PointFE<R> &f, bool n, R S, R Ss) {
+    if (!n) return f.amp;
+    const R c74_4 = (R)(1. / (0.74 * 0.74 * 0.74 * 0.74));
+    if (MODEL == 4) return Mth<R>::mn(f.amp * S, f.amp * c74_4 * Ss);
+    return f.amp * S;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -958,7 +952,7 @@ constexpr int kMaxCluster = 8;      // portable cluster size limit
 constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model terms, prior terms, ln z, ln u
 
 template <typename R> struct SmemLayout {
-    size_t off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_term, off_part, off_cpart, off_flag, off_bar, total;
+    size_t off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_old, off_term, off_part, off_cpart, off_flag, off_bar, total;
     // ncluster: largest cluster that may share a walker group (1 in the chain kernel: no cluster partials to hold)
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster) {
         size_t o = 0;
@@ -972,6 +966,7 @@ template <typename R> struct SmemLayout {
         off_q = o;    o += (size_t)wpb * ndim * sizeof(double);
         off_lp = o;   o += (size_t)wpb * sizeof(double);
         off_z = o;    o += (size_t)wpb * sizeof(double);
+        off_old = o;  o += (size_t)wpb * sizeof(double);                         // log-probability of the walker being moved (prefetched)
         off_term = o; o += (size_t)wpb * kTermStride * sizeof(double);
         off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
         off_cpart = o; o += ncluster > 1 ? (size_t)ncluster * wpb * sizeof(double) : 0;
@@ -1012,6 +1007,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     double *s_q = reinterpret_cast<double *>(smem + L.off_q);
     double *s_lp = reinterpret_cast<double *>(smem + L.off_lp);
     double *s_z = reinterpret_cast<double *>(smem + L.off_z);
+    double *s_old = reinterpret_cast<double *>(smem + L.off_old);
     double *s_term = reinterpret_cast<double *>(smem + L.off_term);
     double *s_part = reinterpret_cast<double *>(smem + L.off_part);
     double *s_cpart = reinterpret_cast<double *>(smem + L.off_cpart);
@@ -1059,6 +1055,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                 }
                 const long long crow = Mv.comp_rows ? (long long)Mv.comp_rows[pr] : Mv.comp_base + pr;
                 const double *s = Mv.coords + row * D, *c = Mv.coords + crow * D;
+                s_old[tid] = Mv.logp[row];          // needed only by the accept test: fetched now, off the critical path
                 for (int d = 0; d < D; ++d)              // q = c - (c - s) z, numpy op order, no FMA
                     q[d] = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), z));
                 s_z[tid] = z;
@@ -1140,9 +1137,14 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // ---- phase 2: tiles (each lane: up to two points of the tile's filter) ----------------
     // narrow groups (wpb <= 32): lane = (walker, point slot).  Wide groups (wpb = 64..256, chain kernel): the warps form
     // wpb/32 walker columns x nw/(wpb/32) tile stripes, so ONE proposal phase serves up to 256 walkers.
+    // Split-K (ks > 0, small problems): the samples of a (walker, point pair) are split over 2^ks lanes -- lane = (walker, chunk,
+    // point slot) -- and the partial sums are combined with warp shuffles, so that a 100-walker ensemble or a 5-point SED epoch
+    // spends its half-step in many short loops instead of a few long ones.
     const int ncol = wpb > 32 ? wpb >> 5 : 1, col = warp % ncol, stripe = warp / ncol, nstripes = nw / ncol;
+    const int ks = (WL == 5 || wpb > 32) ? 0 : Mv.ks;
     const int wl = wpb > 32 ? col * 32 + lane : lane & (wpb - 1);
-    const int slot = wpb > 32 ? 0 : lane >> wl2, ppt = wpb > 32 ? 1 : 32 >> wl2;
+    const int chunk = (lane >> wl2) & ((1 << ks) - 1);
+    const int slot = wpb > 32 ? 0 : lane >> (wl2 + ks), ppt = wpb > 32 ? 1 : 32 >> (wl2 + ks);
     const long long iw = g * wpb + wl;
     const bool skip = s_flag[wl] != 0;
     LaneWalker<R> lw;
@@ -1155,7 +1157,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     R chi = 0;
     for (int tile = crank * nstripes + stripe; tile < TL.ntiles; tile += nstripes * csize) {
         const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
-        if (!skip && slot < tl.y) {
+        const bool active = !skip && slot < tl.y;
+        const unsigned amask = ks ? __ballot_sync(0xffffffffu, active) : 0u;    // the chunk lanes of a point pair are active together
+        if (active) {
             const int pa = tl.x + slot;
             const bool two = slot + ppt < tl.y;
             const int pb = two ? pa + ppt : pa;
@@ -1168,27 +1172,40 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb, s_spl);
             fa.state = fa.invT > (R)0 ? 1 : 0;
             fb.state = fb.invT > (R)0 ? 1 : 0;
-            R ya, yb;
-            blackbody_pair<MODEL, R, (WL == 5 ? kTabStride : 0)>(s_bank, fi, fa, fb, two, s_tabw, tstride, s_e2t, ya, yb);
-            if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
-            if (!PLAIN && Mv.mode == MODE_MODEL) {
-                Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
-                if (two) Mv.out[iw * P.npoints + pb] = (double)yb * P.scale;
-            } else if (!PLAIN && P.use_sigma) {
-                const R s2a = oa.y + lw.wc[7] * oa.z;                // models.py:130
-                const R ra = oa.x - ya;
-                chi += Mth<R>::lg2(s2a) * (R)kLn2 + ra * ra * Mth<R>::rcp(s2a);
-                if (two) {
-                    const R s2b = ob.y + lw.wc[7] * ob.z;
-                    const R rb = ob.x - yb;
-                    chi += Mth<R>::lg2(s2b) * (R)kLn2 + rb * rb * Mth<R>::rcp(s2b);
+            const bool na = fa.state == 1, nb = two && fb.state == 1;
+            const int k_lo = ks ? (int)(((long long)fi.y * chunk) >> ks) : 0;
+            const int k_cnt = ks ? (int)(((long long)fi.y * (chunk + 1)) >> ks) - k_lo : fi.y;
+            R Sa, Sas, Sb, Sbs;
+            blackbody_sums<MODEL, R, (WL == 5 ? kTabStride : 0)>(s_bank, fi, k_lo, k_cnt, fa, fb, na, nb, s_tabw, tstride, s_e2t, Sa, Sas, Sb, Sbs);
+            if (ks) {
+                for (int off = wpb; off < (wpb << ks); off <<= 1) {
+                    Sa += __shfl_xor_sync(amask, Sa, off);
+                    Sb += __shfl_xor_sync(amask, Sb, off);
+                    if (MODEL == 4) { Sas += __shfl_xor_sync(amask, Sas, off); Sbs += __shfl_xor_sync(amask, Sbs, off); }
                 }
-            } else {
-                const R ra = (oa.x - ya) * oa.y;                     // models.py:135
-                chi = fma(ra, ra, chi);
-                if (two) {
-                    const R rb = (ob.x - yb) * ob.y;
-                    chi = fma(rb, rb, chi);
+            }
+            R ya = blackbody_value<MODEL, R>(fa, na, Sa, Sas), yb = blackbody_value<MODEL, R>(fb, nb, Sb, Sbs);
+            if (MODEL >= 5 && MODEL <= 7) { ya += adda; yb += addb; }
+            if (chunk == 0) {
+                if (!PLAIN && Mv.mode == MODE_MODEL) {
+                    Mv.out[iw * P.npoints + pa] = (double)ya * P.scale;
+                    if (two) Mv.out[iw * P.npoints + pb] = (double)yb * P.scale;
+                } else if (!PLAIN && P.use_sigma) {
+                    const R s2a = oa.y + lw.wc[7] * oa.z;                // models.py:130
+                    const R ra = oa.x - ya;
+                    chi += Mth<R>::lg2(s2a) * (R)kLn2 + ra * ra * Mth<R>::rcp(s2a);
+                    if (two) {
+                        const R s2b = ob.y + lw.wc[7] * ob.z;
+                        const R rb = ob.x - yb;
+                        chi += Mth<R>::lg2(s2b) * (R)kLn2 + rb * rb * Mth<R>::rcp(s2b);
+                    }
+                } else {
+                    const R ra = (oa.x - ya) * oa.y;                     // models.py:135
+                    chi = fma(ra, ra, chi);
+                    if (two) {
+                        const R rb = (ob.x - yb) * ob.y;
+                        chi = fma(rb, rb, chi);
+                    }
                 }
             }
         }
@@ -1233,7 +1250,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                 const long long j = (row < Mv.n0) ? 2 * row : 2 * (row - Mv.n0) + 1;
                 const double logu = Mv.luin ? Mv.luin[i] : s_term[tid * kTermStride + NT + kMaxDim + 1];
                 if (nlp != nlp) atomicAdd(Mv.nanflag, 1);           // emcee: "Probability function returned NaN"
-                const double old = Mv.logp[row];
+                const double old = s_old[tid];
                 const double lnpdiff = (double)(D - 1) * s_term[tid * kTermStride + NT + kMaxDim] + nlp - old;
                 const bool acc = lnpdiff > logu;
                 double *crd = Mv.coords + row * D;
@@ -1306,7 +1323,7 @@ struct BatchDev {
     long long W, n0, nproblems;
     long long nburn, nsteps, iter0;
     unsigned long long seed;
-    int wpb_log2, init_logp;
+    int wpb_log2, init_logp, ks;
 };
 
 // at most 8 warps per CTA; FP32: 64 registers so that four CTAs (32 warps) share an SM, as in k_pass
@@ -1340,7 +1357,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     Mv.accepted = nullptr;
     Mv.nanflag = B.status + prob;
     Mv.W = B.W; Mv.n0 = B.n0;
-    Mv.wpb_log2 = B.wpb_log2;
+    Mv.wpb_log2 = B.wpb_log2; Mv.ks = B.ks;
     Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
     Mv.npeers = 0;
@@ -1393,7 +1410,7 @@ struct RingDev {
     long long nsteps, iter0;
     unsigned long long seed;
     unsigned int *bar;                 // [2]: arrival counter, generation (zeroed before the launch)
-    int wpb_log2;
+    int wpb_log2, ks;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -1438,7 +1455,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     Mv.coords = G.coords; Mv.logp = G.logp;
     Mv.nanflag = G.nanflag;
     Mv.W = G.W; Mv.n0 = G.n0;
-    Mv.mode = MODE_MOVE; Mv.wpb_log2 = G.wpb_log2;
+    Mv.mode = MODE_MOVE; Mv.wpb_log2 = G.wpb_log2; Mv.ks = G.ks;
     Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
     Mv.npeers = 0;

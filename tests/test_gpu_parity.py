@@ -1208,3 +1208,55 @@ def test_fused_peer_exchange_stress_randomised_launch_order():
         np.testing.assert_array_equal(states[0].coords, ref[-1])
     finally:
         check(lib().lcf_set_tuning_ex(0, 0, 0))
+
+
+@pytest.mark.parametrize('shape', [(1, 8, 1, 32), (2, 4, 2, 8), (4, 8, 1, 4), (8, 4, 1, 2), (16, 4, 1, 2), (1, 16, 1, 4)])
+@pytest.mark.parametrize('name,precision', [('sc4_example', 'fp32'), ('sc4_example_sigma_abs', 'fp64'), ('sc3_synth_sigma', 'fp32'),
+                                            ('cs3_synth', 'fp64'), ('sed', 'fp32'), ('sed_sigma', 'fp64')])
+def test_split_k_tiles_match_oracle(name, precision, shape):
+    """Split-K tiles (the samples of a (walker, point pair) swept by 2..32 lanes, partial sums combined with warp shuffles): every
+    model family, both precisions, with thread-block clusters, against the oracle; and a short native run on the persistent
+    kernel equals the half-step launches of the same shape bit for bit."""
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    check(lib().lcf_set_tuning_ex(*shape[:3]))
+    check(lib().lcf_set_tuning_split(shape[3]))
+    try:
+        wl = WORKLOADS[name]()
+        _check_logpost(wl, precision, n=19, seed=4, widen=0.3)
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+        check(lib().lcf_set_tuning_split(0))
+
+
+def test_split_k_persistent_kernel_and_batches(monkeypatch):
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.bolometric import BatchSampler
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = W.example_sc4()
+    prob = wl.device_problem('fp32')
+    p0 = wl.start(100, np.random.default_rng(5))
+    check(lib().lcf_set_tuning_ex(1, 16, 1))
+    check(lib().lcf_set_tuning_split(8))
+    try:
+        out = {}
+        for ring in ('0', '1'):
+            monkeypatch.setenv('LCF_RING', ring)
+            s = EnsembleSampler(100, wl.ndim, prob, seed=31)
+            s.run_mcmc(p0, 9)
+            out[ring] = (s.get_chain(), s.get_log_prob())
+        np.testing.assert_array_equal(out['1'][0], out['0'][0])
+        np.testing.assert_array_equal(out['1'][1], out['0'][1])
+        _check_chain_rows_against_oracle(wl, out['1'][0], out['1'][1], 'fp32', 12, 3)
+    finally:
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+        check(lib().lcf_set_tuning_split(0))
+        monkeypatch.delenv('LCF_RING')
+    # SED batches pick split-K themselves (10 walkers, one point per filter): chains against the oracle
+    rng = np.random.default_rng(3)
+    wls = [W.sed_epoch(rng) for _ in range(5)]
+    b = BatchSampler([w.device_problem('fp64') for w in wls], 10, seed=5)
+    b.run(np.stack([w.start(10, rng) for w in wls]), 15, 10)
+    chain, lnp = b.get_chain(), b.get_log_prob()
+    for k, w in enumerate(wls):
+        _check_chain_rows_against_oracle(w, chain[k], lnp[k], 'fp64', 10, k)
