@@ -125,8 +125,8 @@ struct lcf_problem {
     int precision = 0;
     std::vector<void *> allocs;                 // every device allocation, freed on destroy
     std::vector<int> h_point_filter;            // grouped by filter
-    TileDev tiles[6];                           // per wpb_log2
-    bool tiles_built[6] = {false, false, false, false, false, false};
+    std::map<int, TileDev> tile_tabs;           // key = lanes-per-point exponent * 1024 + dealing period (0: natural order), see get_tiles
+    std::vector<int> h_filter_records;          // pair records of every filter (tile cost)
     struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0; size_t smem = 0; double cost = 0.; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
     struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0; long long grid = 0; } last_launch;   // lcf_problem_last_launch
@@ -303,9 +303,16 @@ int ensure_dynamic_smem(const void *kernel, size_t bytes) {
     return 0;
 }
 
-int build_tiles(lcf_problem *p, int l) {
-    if (p->tiles_built[l]) return 0;
-    const int ppt = 2 * (32 >> l);              // two points per lane
+// Tile table for lanes-per-point exponent lt (a tile = 2 * (32 >> lt) points of one filter), in the order of the points (filter by
+// filter); warp slot j of a launch takes the tiles j, j + P, j + 2P, ...  (Sorting the tiles by cost and dealing them in serpentine
+// order to balance the slots was measured this round: no gain on cfg1 / cfg4 / cfg5 -- profiles/round2_kernel_variants.jsonl -- so
+// the natural order stays.)  Problems of a flat-array batch share one allocation for all their tables (negative ntiles marks those).
+int get_tiles(lcf_problem *p, int lt, int period, TileDev *out) {
+    (void)period;
+    const int key = lt * 1024;
+    auto it = p->tile_tabs.find(key);
+    if (it != p->tile_tabs.end()) { *out = it->second; if (out->ntiles < 0) out->ntiles = -out->ntiles; return 0; }
+    const int ppt = 2 * (32 >> lt);              // two points per lane
     std::vector<int4> t;
     const int N = p->dev.npoints;
     int i = 0;
@@ -319,9 +326,11 @@ int build_tiles(lcf_problem *p, int l) {
     int rc = upload(t, &d);
     if (rc) return rc;
     p->allocs.push_back(d);
-    p->tiles[l].tiles = reinterpret_cast<const int4 *>(d);
-    p->tiles[l].ntiles = (int)t.size();
-    p->tiles_built[l] = true;
+    TileDev td;
+    td.tiles = reinterpret_cast<const int4 *>(d);
+    td.ntiles = (int)t.size();
+    p->tile_tabs[key] = td;
+    *out = td;
     return 0;
 }
 
@@ -352,9 +361,10 @@ int build_tiles_shared(const std::vector<lcf_problem *> &probs, void **block) {
     size_t k = 0;
     for (lcf_problem *p : probs)
         for (int l = 0; l < 6; ++l, ++k) {
-            p->tiles[l].tiles = reinterpret_cast<const int4 *>(*block) + first[k];
-            p->tiles[l].ntiles = count[k];
-            p->tiles_built[l] = true;
+            TileDev td;
+            td.tiles = reinterpret_cast<const int4 *>(*block) + first[k];
+            td.ntiles = -count[k];                        // negative: a natural-order table that serves every dealing period (get_tiles)
+            p->tile_tabs[l * 1024] = td;
         }
     return 0;
 }
@@ -442,8 +452,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
         if (g_tune_nw > 16 || g_tune_wpb > 32) return fail(LCF_ERR_ARG, "bad tuning override");
         return fail(LCF_ERR_ARG, "filter bank needs more than %zu bytes of shared memory: too many transmission samples", kSmemMax);
     }
-    int rc = build_tiles(p, bs.l + bs.ks);
-    if (rc) return rc;
+    int rc = 0;
     for (int plain = 0; plain < 2; ++plain) {
         PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
         if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
@@ -494,7 +503,9 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l + sh.ks], mv));
+    TileDev tiles;
+    if ((rc = get_tiles(p, sh.l + sh.ks, sh.nw * sh.cluster, &tiles))) return rc;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, mv));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
     if (launches) ++*launches;
@@ -553,6 +564,7 @@ int build_problem_arrays(const lcf_problem_desc *d, lcf_problem *p, double scale
         memcpy(&bmn, &fmn, 4);
         memcpy(&bmx, &fmx, 4);
         finfo[f] = make_int4(foff[f] >> 1, (foff[f + 1] - foff[f]) >> 1, bmn, bmx);
+        p->h_filter_records.push_back((foff[f + 1] - foff[f]) >> 1);
     }
     for (int i = 0; i < N; ++i) kept += (double)(foff[d->point_filter[i] + 1] - foff[d->point_filter[i]]);
     p->mean_samples = kept / std::max(1, N);                // device samples per photometry point (launch-shape model)
@@ -1261,8 +1273,8 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     if (!e->ring_ok) return 0;
     if (!e->d_ring_bar) CUDA_TRY(cudaMalloc(&e->d_ring_bar, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(e->d_ring_bar, 0, 2 * sizeof(unsigned int), e->stream));
-    rc = build_tiles(p, sh.l + sh.ks);
-    if (rc) return rc;
+    TileDev tiles;
+    if ((rc = get_tiles(p, sh.l + sh.ks, sh.nw * sh.cluster, &tiles))) return rc;
     RingDev G;
     memset(&G, 0, sizeof(G));
     G.coords = e->d_coords; G.logp = e->d_logp; G.accepted = e->d_acc; G.nanflag = e->d_nan;
@@ -1274,7 +1286,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     G.bar = e->d_ring_bar;
     G.wpb_log2 = sh.l;
     G.ks = sh.ks;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, p->tiles[sh.l + sh.ks], G));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, G));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3;
     e->last_launches += 1;
@@ -1701,16 +1713,16 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     b->ks = ks;
     std::vector<ProblemDev> hp(nproblems);
     std::vector<TileDev> ht(nproblems);
-    for (long long i = 0; i < nproblems; ++i) {
-        const int lt = std::min(l, 5) + ks;              // wide groups use the 32-walker tiles (two points per lane)
-        if ((rc = build_tiles(b->probs[i], lt))) { delete b; return rc; }
-        hp[i] = b->probs[i]->dev;
-        ht[i] = b->probs[i]->tiles[lt];
-        max_tiles = std::max(max_tiles, ht[i].ntiles);
-    }
+    const int lt = std::min(l, 5) + ks;                  // wide groups use the 32-walker tiles (two points per lane)
+    for (long long i = 0; i < nproblems; ++i) max_tiles = std::max(max_tiles, count_tiles(b->probs[i], lt));
     int nw = g_tune_nw > 0 ? g_tune_nw : std::min(8, max_tiles);
     nw = std::max(1, std::min(nw, 8));                    // k_chain is compiled for <= 256 threads
     if (l > 5) nw = 8;                                    // wide groups: 2^(l-5) walker columns of warps must divide nw
+    const int nstripes = l > 5 ? nw >> (l - 5) : nw;      // warps that share the tiles of one walker column: the dealing period
+    for (long long i = 0; i < nproblems; ++i) {
+        if ((rc = get_tiles(b->probs[i], lt, nstripes, &ht[i]))) { delete b; return rc; }
+        hp[i] = b->probs[i]->dev;
+    }
     smem = 0;
     for (lcf_problem *p : b->probs) smem = std::max(smem, smem_bytes(p, 1 << l, nw, 1));
     if (smem > kSmemMax) { delete b; return fail(LCF_ERR_ARG, "filter bank does not fit in shared memory"); }

@@ -1072,9 +1072,11 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     LCF_TICK(6);
     // 1b: one thread per (walker, term): FP64 transcendentals of the model constants, log-priors, ln z and ln u
     {
+        // one KIND of term per warp per pass (lanes = walkers): a warp never diverges into different double-precision routines, and
+        // with few walkers per CTA the kinds run concurrently on different warps instead of serially inside warp 0
         const int per = NT + D + 2;
-        for (int idx = tid; idx < wpb * per; idx += blockDim.x) {
-            const int k = idx >> wl2, w1 = idx & (wpb - 1);   // term-major: a warp works on one kind of term
+        for (int k = warp; k < per; k += nw)
+        for (int w1 = lane; w1 < wpb; w1 += 32) {
             if (g * wpb + w1 >= Mv.Ns) continue;
             const double *q = s_q + w1 * D;
             double *t = s_term + w1 * kTermStride;

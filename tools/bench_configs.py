@@ -62,7 +62,7 @@ def main():
     ap.add_argument('--nlc', type=int, default=1250)
     ap.add_argument('--nepochs', type=int, default=500)
     ap.add_argument('--only', default='')
-    ap.add_argument('--tune', default='', help='wpb,warps,cluster launch-shape override(s), separated by ;')
+    ap.add_argument('--tune', default='', help='wpb,warps,cluster[,sample chunks] launch-shape override(s), separated by ;')
     ap.add_argument('--short', action='store_true', help='fewer steps (shape sweeps)')
     args = ap.parse_args()
     import __graft_entry__ as g
@@ -74,7 +74,9 @@ def main():
     from lightcurve_fitting_b200 import _capi
     for tune in (args.tune.split(';') if args.tune else ['']):
         if tune:
-            _capi.check(_capi.lib().lcf_set_tuning_ex(*[int(x) for x in tune.split(',')]))
+            v = [int(x) for x in tune.split(',')]
+            _capi.check(_capi.lib().lcf_set_tuning_ex(*v[:3]))
+            _capi.check(_capi.lib().lcf_set_tuning_split(v[3] if len(v) > 3 else 0))      # optional 4th entry: sample chunks (split-K)
         run_configs(args, only, tune, synthetic, BatchSampler, EnsembleSampler)
 
 
