@@ -45,7 +45,7 @@ WALKERS_PER_GPU = 100_000
 NPOINTS = 2000
 MUFU_LANES_PER_CLK_SM = 16
 FP64_LANES_PER_CLK_SM = 64
-FP64_OPS_PER_SAMPLE = 14.75           # FP64-pipe instructions (DFMA+DMUL+DADD) per Planck sample of planck_quad_f64, counted in SASS (profiles/round2_sass_fp64_loop.txt)
+FP64_OPS_PER_SAMPLE = 11.75           # FP64-pipe instructions (DFMA+DMUL+DADD) per Planck sample of planck_quad_f64, counted in SASS (profiles/round2_sass_fp64_loop.txt)
 BALANCED_SAMPLES_PER_CLK_SM = 13.5    # FMA+MUFU balanced bound of the two-transcendental formulation
 SMS = 148
 MODEL_NAMES = {'sc3': 'ShockCooling3', 'sc4': 'ShockCooling4'}

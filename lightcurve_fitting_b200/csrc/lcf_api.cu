@@ -512,6 +512,21 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     return 0;
 }
 
+// 2^(j/256) table of the FP64 inner loop, written once per device (kernels copy it into shared memory)
+int ensure_e2tab() {
+    static std::mutex mu;
+    static std::map<int, bool> done;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return 0;
+    double h[kE2TabSize];
+    for (int j = 0; j < kE2TabSize; ++j) h[j] = std::exp2((double)j / (double)kE2TabSize);
+    CUDA_TRY(cudaMemcpyToSymbol(g_e2tab, h, sizeof(h)));
+    done[dev] = true;
+    return 0;
+}
+
 int check_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -701,6 +716,7 @@ static int problem_create_impl(const lcf_problem_desc *d, lcf_problem **out, boo
     int rc = check_device();
     if (rc) return rc;
 
+    if (d->precision == LCF_PRECISION_FP64 && (rc = ensure_e2tab())) return rc;
     lcf_problem *p = new lcf_problem();
     cudaGetDevice(&p->device);
     p->precision = d->precision;

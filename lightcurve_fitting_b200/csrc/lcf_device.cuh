@@ -617,23 +617,43 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
 // (h nu / k T = 173: such a sample is 1e-75 of its weight) so that four denominators multiply to < 2^1000; one division per
 // four samples.  ~21 FP64 pipe operations per Planck sample instead of ~55 (libm exp2 + one division each).
 // Callers guarantee every exponent >= 2^-10 (2^x - 1 then keeps 1e-13 relative accuracy).
-// 2^x - 1 for the FP64 loop, x in [0, 256): x = n + j/16 + f with |f| <= 1/32, 2^(j/16) from a 16-entry shared-memory
-// table (distinct j hit distinct banks), 2^f by a degree-6 polynomial (truncation 4e-16): 7 FP64 operations fewer than
-// the table-free exp2_core.
+// 2^x - 1 for the FP64 loop, x in [0, 256): x = n + j/1024 + f with |f| <= 2^-11, 2^(j/1024) from a 1024-entry (8 KB) shared-memory
+// table (filled from a device-global copy the host writes once per device), 2^f by its degree-3 Taylor polynomial (truncation
+// f^4 ln2^4 / 24 <= 5e-16): 8 FP64-pipe operations per exponential.  Measured on cfg2 (profiles/round2_kernel_variants.jsonl):
+// 16-entry table + degree 6 (round 1, 11 operations) 7.86 M walker-steps/s, 256 entries + degree 4 8.65 M, 1024 + degree 3 9.17 M.
+#ifndef LCF_E2T_BITS
+#define LCF_E2T_BITS 10
+#endif
+constexpr int kE2TabBits = LCF_E2T_BITS, kE2TabSize = 1 << kE2TabBits;
+__device__ double g_e2tab[kE2TabSize];                                    // 2^(j / kE2TabSize), written by the host (lcf_api.cu)
+__device__ __forceinline__ void stage_e2tab(double *dst) {               // every thread of the CTA; the caller synchronises
+    for (int j = threadIdx.x; j < kE2TabSize; j += blockDim.x) dst[j] = g_e2tab[j];
+}
 __device__ __forceinline__ double ex2m1_f64(double x, const double *__restrict__ e2t) {
-    const double magic = 422212465065984.0;                              // 1.5 * 2^48: adding it rounds x to a multiple of 1/16
+    const double magic = 6755399441055744.0 / (double)kE2TabSize;        // 1.5 * 2^(52 - bits): adding it rounds x to a multiple of 2^-bits
     const double r = x + magic;
-    const int k = __double2loint(r);                                     // 16 n + j
+    const int k = __double2loint(r);                                     // 2^bits n + j
     const double f = x - (r - magic);
+#if LCF_E2T_BITS >= 10
+    double p = 5.55041086648215800e-02;                                  // ln2^3/6  (|f| <= 2^-11: truncation f^4 ln2^4/24 = 5e-16)
+    p = fma(p, f, 2.40226506959100712e-01);                              // ln2^2/2
+    p = fma(p, f, 6.93147180559945309e-01);                              // ln2
+#elif LCF_E2T_BITS >= 8
+    double p = 9.61812910762847716e-03;                                  // ln2^4/24
+    p = fma(p, f, 5.55041086648215800e-02);                              // ln2^3/6
+    p = fma(p, f, 2.40226506959100712e-01);                              // ln2^2/2
+    p = fma(p, f, 6.93147180559945309e-01);                              // ln2
+#else
     double p = 1.54035303933816061e-04;
     p = fma(p, f, 1.33335581464284411e-03);
     p = fma(p, f, 9.61812910762847688e-03);
     p = fma(p, f, 5.55041086648215762e-02);
     p = fma(p, f, 2.40226506959100694e-01);
     p = fma(p, f, 6.93147180559945286e-01);
-    const double t = e2t[k & 15];
-    p = fma(t * f, p, t);                                                // 2^(j/16) (1 + f q(f))
-    return __hiloint2double(__double2hiint(p) + ((k >> 4) << 20), __double2loint(p)) - 1.0;
+#endif
+    const double t = e2t[k & (kE2TabSize - 1)];
+    p = fma(t * f, p, t);                                                // 2^(j/2^bits) (1 + f q(f))
+    return __hiloint2double(__double2hiint(p) + ((k >> kE2TabBits) << 20), __double2loint(p)) - 1.0;
 }
 
 // 1/x for a positive normal double: MUFU.RCP64H seed (20 bits) + two Newton steps; no special-case handling
@@ -956,7 +976,7 @@ template <typename R> struct SmemLayout {
     // ncluster: largest cluster that may share a walker group (1 in the chain kernel: no cluster partials to hold)
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster) {
         size_t o = 0;
-        off_e2t = o;  o += sizeof(R) == 8 ? 16 * sizeof(double) : 0;             // 2^(j/16), FP64 loop
+        off_e2t = o;  o += sizeof(R) == 8 ? (size_t)kE2TabSize * sizeof(double) : 0;   // 2^(j/1024), FP64 loop
         off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
         off_spl = o;  o += (size_t)nspl * 4 * sizeof(R);                          o = (o + 15) & ~(size_t)15;   // SiFTO cubic coefficients
         off_tab = o;  o += tab ? (size_t)nsamples * (wpb < 32 ? wpb : 32) * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][min(wpb, 32)]
@@ -1289,7 +1309,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
-    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
+    if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
     __syncthreads();
     // Programmatic dependent launch: this grid may have been scheduled while the previous half-step was still running
     // (its launch latency and the prologue above are hidden); nothing the previous kernel wrote is read before this point.
@@ -1349,7 +1369,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     SmemLayout<R> L(sP.nsamples, sP.nfilters, wpb, blockDim.x >> 5, sP.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? sP.nfilters * sP.spl_nint : 0, 1);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
-    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
+    if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
     __syncthreads();
     const int D = sP.ndim;
     MoveDev Mv;
@@ -1447,7 +1467,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
-    if (sizeof(R) == 8 && threadIdx.x < 16) reinterpret_cast<double *>(smem + L.off_e2t)[threadIdx.x] = exp2((double)threadIdx.x * 0.0625);
+    if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
     __syncthreads();
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     if (csize > 1) cluster_sync_all();

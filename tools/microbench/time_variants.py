@@ -27,7 +27,7 @@ def child(args):
     else:
         wl = synthetic.synthetic_sc4(bench.device_truth, npoints=2000, seed=1, filters=['U', 'B', 'V', 'R', 'I', 'g', 'r', 'i'])
         spe = 2 * 97000
-    prob = wl.device_problem('fp32')
+    prob = wl.device_problem(args.precision)
     p0 = wl.start(args.walkers, np.random.default_rng(1))
     for shape in args.shapes.split(';'):
         wpb, nw, cl = (int(x) for x in shape.split(','))
@@ -60,6 +60,7 @@ def main():
     ap.add_argument('--model', type=int, default=3)
     ap.add_argument('--walkers', type=int, default=100000)
     ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--precision', default='fp32')
     ap.add_argument('--shapes', default='0,0,0')
     ap.add_argument('--child', action='store_true')
     ap.add_argument('libs', nargs='*')
@@ -71,7 +72,7 @@ def main():
         if lib:
             env['LCF_B200_LIB'] = os.path.abspath(lib)
         cmd = [sys.executable, os.path.abspath(__file__), '--child', '--model', str(args.model), '--walkers', str(args.walkers),
-               '--steps', str(args.steps), '--shapes', args.shapes]
+               '--steps', str(args.steps), '--shapes', args.shapes, '--precision', args.precision]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         sys.stdout.write(r.stdout)
         if r.returncode:
