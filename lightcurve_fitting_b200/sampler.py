@@ -21,10 +21,28 @@ class AutocorrError(Exception):
 
 
 class State:
-    """Minimal ``emcee.State``: unpacks to ``(coords, log_prob, random_state)``."""
+    """Minimal ``emcee.State``: unpacks to ``(coords, log_prob, random_state)``.
 
-    def __init__(self, coords, log_prob, random_state=None):
-        self.coords, self.log_prob, self.random_state = coords, log_prob, random_state
+    The state ``run_mcmc`` returns is fetched from the device on first use (``fetch``: a callable returning
+    ``(coords, log_prob)``): a caller that streams the chain to host buffers already holds the final positions and does not
+    pay a second device-to-host copy.  The sampler materialises a pending state before it moves the ensemble again."""
+
+    def __init__(self, coords=None, log_prob=None, random_state=None, fetch=None):
+        self._coords, self._log_prob, self.random_state, self._fetch = coords, log_prob, random_state, fetch
+
+    def materialize(self):
+        if self._fetch is not None:
+            self._coords, self._log_prob = self._fetch()
+            self._fetch = None
+        return self
+
+    @property
+    def coords(self):
+        return self.materialize()._coords
+
+    @property
+    def log_prob(self):
+        return self.materialize()._log_prob
 
     def __iter__(self):
         return iter((self.coords, self.log_prob, self.random_state))
@@ -114,11 +132,24 @@ class EnsembleSampler:
         lp = None if log_prob is None else f64(log_prob)
         check(lib().lcf_ensemble_set_state(self.handle, dptr(coords), dptr(lp) if lp is not None else None))
 
-    def _state(self):
+    def _fetch_state(self):
         coords = np.empty((self.nwalkers, self.ndim))
         lp = np.empty(self.nwalkers)
         check(lib().lcf_ensemble_get_state(self.handle, dptr(coords), dptr(lp)))
-        return State(coords, lp, None)
+        return coords, lp
+
+    def _state(self, lazy=False):
+        if not lazy:
+            return State(*self._fetch_state())
+        self._pending = State(fetch=self._fetch_state)
+        return self._pending
+
+    def _settle(self):
+        """Materialise the state handed out by the previous run before the ensemble moves on."""
+        pending = getattr(self, '_pending', None)
+        if pending is not None:
+            pending.materialize()
+            self._pending = None
 
     def _timing(self):
         ms = C.c_double(0.)
@@ -133,6 +164,7 @@ class EnsembleSampler:
 
         ``chain_out`` [nsteps, nwalkers, ndim] and ``log_prob_out`` [nsteps, nwalkers] (C-contiguous float64, ideally
         page-locked) make the run stream every finished step to the host while the next ones are sampled."""
+        self._settle()
         if initial_state is not None:
             self._set_initial(initial_state, skip_initial_state_check)
         if chain_out is not None or log_prob_out is not None:
@@ -147,7 +179,7 @@ class EnsembleSampler:
             check(lib().lcf_ensemble_run(self.handle, int(nsteps), 1 if store else 0))
         self._timing()
         self.iteration += int(nsteps) if store else 0
-        return self._state()
+        return self._state(lazy=True)
 
     def run_replay(self, initial_state, draws, store=True):
         """Drive the move with injected draws in emcee's order (see ``lcf_ensemble_run_replay``).
@@ -155,6 +187,7 @@ class EnsembleSampler:
         ``draws`` is the list recorded by the oracle's ``StretchReplay``: one dict per step with ``inds`` (split
         label per walker) and ``halves`` = [{'z', 'rint', 'logu'}, ...] for split 0 and split 1.
         """
+        self._settle()
         if initial_state is not None:
             self._set_initial(initial_state, True)
         S, W = len(draws), self.nwalkers
@@ -171,6 +204,11 @@ class EnsembleSampler:
         self._timing()
         self.iteration += S if store else 0
         return self._state()
+
+    def reserve(self, nsteps):
+        """Make room in HBM for ``nsteps`` more stored steps now (otherwise the chain buffer grows inside ``run_mcmc``, like
+        emcee's ``Backend.grow``); additive, not part of the emcee surface."""
+        check(lib().lcf_ensemble_reserve(self.handle, int(nsteps)))
 
     def reset(self):
         check(lib().lcf_ensemble_reset(self.handle))
