@@ -268,6 +268,15 @@ int  lcf_set_tuning_ex(int walkers_per_cta, int warps_per_cta, int cluster_size)
 /* split-K override: the transmission samples of a (walker, point pair) are swept by `sample_chunks` lanes (power of two, walkers per
    CTA x chunks <= 32) whose partial sums are combined with warp shuffles -- small ensembles / SED epochs; 0 = heuristic.        */
 int  lcf_set_tuning_split(int sample_chunks);
+/* flat split of a half-step over the co-resident CTA slots of the device: the tile rows of every walker group are dealt to 8 units,
+   each CTA of a `slots`-CTA grid takes the same number of (group, unit) pairs and a group shared by several CTAs is finished by the
+   one that delivers its last units -- no partial last wave, no idle slots when there are fewer groups than slots.  The chi-square
+   sums keep one fixed order (units, then warps) whichever CTA computed what, so chains do not depend on the split.
+   -1 = the launch-shape cost model decides (default), 0 = never, 1 = whenever the shape allows it.                              */
+int  lcf_set_tuning_flat(int mode);
+/* lcf_problem_last_launch plus: walker groups of the launch and units of the structured sums (1: plain per-warp sums); a launch
+   with grid != groups x cluster_size was a flat split.                                                                          */
+int  lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,7 @@ struct NvtxRange {
 
 thread_local std::string g_err;
 int g_tune_wpb = 0, g_tune_nw = 0, g_tune_cluster = 0, g_tune_ks = -1;   // launch-shape overrides (0 / -1: heuristic)
+int g_tune_flat = -1;                                                    // flat split of the (group, unit) space: -1 cost model, 0 off, 1 on (when the shape allows it)
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -127,18 +128,21 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     std::map<int, TileDev> tile_tabs;           // key = lanes-per-point exponent * 1024 + dealing period (0: natural order), see get_tiles
     std::vector<int> h_filter_records;          // pair records of every filter (tile cost)
-    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0; size_t smem = 0; double cost = 0.; } shape_cache;
+    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0, nq = 1; long long flat = 0; size_t smem = 0; double cost = 0.; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
-    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0; long long grid = 0; } last_launch;   // lcf_problem_last_launch
+    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0, nq = 1; long long grid = 0, groups = 0; } last_launch;   // lcf_problem_last_launch
     double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
     int *d_eval_nan = nullptr;
     size_t eval_q_cap = 0, eval_out_cap = 0;
+    double *d_split_part = nullptr;             // flat-split scratch of the evaluation passes (ensembles own theirs)
+    unsigned int *d_split_tick = nullptr;
+    long long split_cap = 0;
     int device = 0;
     Arena *pending = nullptr;                   // device arrays not uploaded yet (problems of a batch share ONE allocation and copy)
     ~lcf_problem() {
         delete pending;
         for (void *p : allocs) cudaFree(p);
-        cudaFree(d_eval_q); cudaFree(d_eval_out); cudaFree(d_eval_nan);
+        cudaFree(d_eval_q); cudaFree(d_eval_out); cudaFree(d_eval_nan); cudaFree(d_split_part); cudaFree(d_split_tick);
     }
 };
 
@@ -172,10 +176,12 @@ struct lcf_ensemble {
     std::vector<void *> ipc_opened;             // mappings to close
     unsigned int epoch = 0;                     // fused half-steps launched so far (identical on every rank)
     unsigned int *d_ring_bar = nullptr;         // k_ring: arrival counter + generation word
+    double *d_split_part = nullptr;             // flat split: unit sums of walker groups shared by several CTAs, [kSplitUnits][W + 32]
+    unsigned int *d_split_tick = nullptr;       // [W + 1] arrival counters (zero between launches)
     int ring_ok = -1, ring_key = -1;            // -1 unknown, 0 the grid does not fit, 1 usable (cached per launch shape)
     ~lcf_ensemble() {
         for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
-        cudaFree(d_flags); cudaFree(d_ring_bar);
+        cudaFree(d_flags); cudaFree(d_ring_bar); cudaFree(d_split_part); cudaFree(d_split_tick);
         cudaFree(d_stage); cudaFree(d_stage_flag);
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
@@ -278,12 +284,14 @@ template <typename R> RingKernel ring_kernel_for(int model) {
 }
 #endif
 
-size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxCluster) {
+size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxCluster, int nq = 1) {
     const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
     if (p->precision == LCF_PRECISION_FP32)
-        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster).total;
-    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster).total;
+        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
+    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
 }
+
+constexpr int kSplitUnits = 8;        // units of the structured chi-square sums (MoveDev::nq) of the shapes that use them
 
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -391,13 +399,29 @@ int count_tiles(const lcf_problem *p, int l) {
     return tiles;
 }
 
-struct Shape { int l, nw, cluster; size_t smem; double cost; int ks; };
+struct Shape {
+    int l, nw, cluster; size_t smem; double cost; int ks;
+    int nq;             // units of the structured chi-square sums: kSplitUnits for unsplit shapes whose warps have >= 2 nq tile rows, else 1
+    long long flat;     // > 0: launch this many CTAs, each with the same share of the (group, unit) space (needs the caller's scratch)
+};
+
+bool sum_units_enabled() {                 // LCF_SUM_UNITS=1 (experiments): plain per-warp sums everywhere, no flat split
+    static const bool on = [] { const char *e = getenv("LCF_SUM_UNITS"); return !(e && e[0] == '1' && e[1] == 0); }();
+    return on;
+}
+
+int flat_mode() {                          // lcf_set_tuning_flat, else LCF_FLAT=0/1 from the environment, else the cost model (-1)
+    if (g_tune_flat >= 0) return g_tune_flat;
+    static const int env = [] { const char *e = getenv("LCF_FLAT"); return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1; }();
+    return env;
+}
 
 int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
-    const int tune = ((g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster) * 8 + (g_tune_ks + 1);
+    const int g_flat = flat_mode();
+    const int tune = (((g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster) * 8 + (g_tune_ks + 1)) * 4 + (g_flat + 1);
     if (p->shape_cache.Ns == Ns && p->shape_cache.tune == tune) {
         out->l = p->shape_cache.l; out->nw = p->shape_cache.nw; out->cluster = p->shape_cache.cluster; out->smem = p->shape_cache.smem;
-        out->cost = p->shape_cache.cost; out->ks = p->shape_cache.ks;
+        out->cost = p->shape_cache.cost; out->ks = p->shape_cache.ks; out->nq = p->shape_cache.nq; out->flat = p->shape_cache.flat;
         return 0;
     }
     int sms = 148;
@@ -408,7 +432,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
     const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
     double best = 1e300;
-    Shape bs = {5, 16, 1, 0, 0., 0};
+    Shape bs = {5, 16, 1, 0, 0., 0, 1, 0};
     for (int l = 5; l >= 0; --l) {
         if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
         const long long groups = (Ns + (1 << l) - 1) >> l;
@@ -422,11 +446,18 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
             const int nw_cand[5] = {16, 8, 4, 2, g_tune_nw};   // candidates; the last entry is the override
             for (int ci = (g_tune_nw > 0 ? 4 : 0); ci < (g_tune_nw > 0 ? 5 : 4); ++ci) {
                 const int nw = nw_cand[ci];
-                const size_t sm = smem_bytes(p, 1 << l, nw);
-                if (sm > kSmemMax) continue;
-                int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
-                occ = std::max(1, std::min(occ, 32));
+                // structured sums (and with them the flat split) for unsplit shapes whose warps see at least two tile rows per unit;
+                // a function of the problem and the shape only, never of Ns: chains do not depend on how an ensemble is sharded
+                const int rows = (ntiles + nw - 1) / nw;
+                int nq_s1 = (ks == 0 && rows >= 2 * kSplitUnits && sum_units_enabled()) ? kSplitUnits : 1;
+                if (nq_s1 > 1 && smem_bytes(p, 1 << l, nw, kMaxCluster, nq_s1) > kSmemMax) nq_s1 = 1;
+                const size_t sm_plain = smem_bytes(p, 1 << l, nw);
+                if (sm_plain > kSmemMax) continue;
                 for (int S = 1; S <= kMaxCluster; S <<= 1) {
+                    const int nq = S == 1 ? nq_s1 : 1;
+                    const size_t sm = nq > 1 ? smem_bytes(p, 1 << l, nw, kMaxCluster, nq) : sm_plain;
+                    int occ = (int)std::min<size_t>(kSmemMax / sm, (size_t)(f32 ? 1024 : 512) / (nw * 32));
+                    occ = std::max(1, std::min(occ, 32));
                     if (g_tune_cluster > 0 && S != g_tune_cluster) continue;
                     if (S > 1 && (long long)nw * S > 2LL * ntiles && g_tune_cluster == 0) break;    // nothing left to split
                     const double tiles_warp = (double)((ntiles + nw * S - 1) / (nw * S));
@@ -443,7 +474,27 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                     for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
                     if (nw < 8) cost *= 1.15;
                     if (ctas < sms) cost *= 1. + 0.25 * (1. - (double)ctas / sms);  // measured (cfg1 sweep): idle SMs cost more than the chain model says
-                    if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; bs.ks = ks; }
+                    // Flat split (one CTA per co-resident slot, each with groups / slots of the work) against the plain launch of the same
+                    // shape, in units of the time two co-resident CTAs need for a group each.  Measured on B200 (profiles/round2_flat_split.txt):
+                    // a CTA alone on its SM runs at 0.69 of the paired rate; the warp schedulers favour the older of two co-resident CTAs,
+                    // which finishes a statically split kernel at 0.64 of its duration and leaves the SM half empty (x 1.12); each CTA of a
+                    // flat grid repeats one more prologue than it has groups.  So the split pays with one CTA per SM (FP64: +3.4 % on cfg2),
+                    // and when the plain launch would spend most of its time in a partial wave (1.3 waves: +19 %); not at 5.3 waves (-3.4 %).
+                    long long flat = 0;
+                    if (nq > 1 && g_flat != 0 && ((occ <= 2 && l == 5) || g_flat == 1)) {   // (calibrated on the 32-walker shapes, one or two CTAs per SM)
+                        const long long slots = (long long)occ * sms;
+                        const double wv = (double)groups / (double)slots, full = std::floor(wv), frac = wv - full;
+                        double plain_rel;
+                        if (groups <= slots) plain_rel = occ == 1 ? 1. : (groups <= sms ? 0.72 : 0.72 + 0.28 * (double)(groups - sms) / (double)(slots - sms));
+                        else plain_rel = full + (frac <= 0. ? 0. : (occ == 1 || frac > 0.5 ? 1. : 0.72));
+                        const double fixed_rel = fixed / std::max(1., occ * tiles_cta * pipe_tile);
+                        const double flat_rel = wv * (occ > 1 ? 1.12 : 1.) + fixed_rel;
+                        if (groups * nq >= 2 * slots && groups != slots && (g_flat == 1 || flat_rel < 0.97 * plain_rel)) {
+                            cost *= std::min(1., flat_rel / plain_rel);       // (a forced split never changes the ranking of the shapes)
+                            flat = slots;
+                        }
+                    }
+                    if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; bs.ks = ks; bs.nq = nq; bs.flat = flat; }
                 }
             }
         }
@@ -460,10 +511,11 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune; p->shape_cache.cost = best; p->shape_cache.ks = bs.ks;
+    p->shape_cache.nq = bs.nq; p->shape_cache.flat = bs.flat;
     bs.cost = best;
     if (getenv("LCF_DEBUG_SHAPE"))
-        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, split-K %d, %zu B smem (model %d, modelled %.0f clk)\n",
-                Ns, 1 << bs.l, bs.nw, bs.cluster, 1 << bs.ks, bs.smem, p->dev.model, best);
+        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, split-K %d, %d sum units, flat grid %lld, %zu B smem (model %d, modelled %.0f clk)\n",
+                Ns, 1 << bs.l, bs.nw, bs.cluster, 1 << bs.ks, bs.nq, bs.flat, bs.smem, p->dev.model, best);
     *out = bs;
     return 0;
 }
@@ -476,11 +528,23 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     if (rc) return rc;
     mv.wpb_log2 = sh.l;
     mv.ks = sh.ks;
+    mv.nq = sh.nq;
+    {
+        const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
+        if (p->precision == LCF_PRECISION_FP32)
+            mv.lay = SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
+        else
+            mv.lay = SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
+        if (mv.lay.total != sh.smem) return fail(LCF_ERR_STATE, "shared-memory layout mismatch");
+    }
     const bool plain = mv.mode != MODE_MODEL && !p->dev.use_sigma;
     PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain)
                                                         : pass_kernel_for<double>(p->dev.model, sh.l, plain);
     const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
-    const long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
+    if (ngroups * sh.nq >= (1LL << 31)) return fail(LCF_ERR_ARG, "too many walker groups for one launch");
+    long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
+    if (sh.flat > 0 && sh.nq > 1 && mv.split_part && mv.split_tick && mv.mode != MODE_MODEL) clusters = sh.flat;   // equal shares of the (group, unit) space
+    else if (sh.nq > 1) { mv.split_part = nullptr; mv.split_tick = nullptr; }                                   // one whole group per CTA
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(clusters * sh.cluster), 1, 1);
@@ -508,6 +572,7 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, mv));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
+    p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups;
     if (launches) ++*launches;
     return 0;
 }
@@ -669,12 +734,23 @@ int lcf_debug_phase_clocks(unsigned long long *out) {   // experiment builds onl
     cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
     return 0;
 }
+int lcf_debug_cta_log(unsigned long long *out /* [4096][3] */) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_cta_log, sizeof(unsigned long long) * 3 * 4096);
+    return 0;
+}
 #endif
 
 int lcf_set_tuning_split(int sample_chunks) {
     if (sample_chunks < 0 || sample_chunks > 32 || (sample_chunks & (sample_chunks - 1))) return fail(LCF_ERR_ARG, "sample_chunks must be 0 or a power of two <= 32");
     g_tune_ks = -1;
     for (int k = 0; sample_chunks && k <= 5; ++k) if ((1 << k) == sample_chunks) g_tune_ks = k;
+    return 0;
+}
+
+int lcf_set_tuning_flat(int mode) {
+    if (mode < -1 || mode > 1) return fail(LCF_ERR_ARG, "flat-split mode must be -1 (cost model), 0 (off) or 1 (on)");
+    g_tune_flat = mode;
     return 0;
 }
 
@@ -818,6 +894,14 @@ int lcf_problem_last_launch(lcf_problem *p, int *walkers_per_cta, int *warps_per
     return 0;
 }
 
+int lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units) {
+    if (!p) return fail(LCF_ERR_ARG, "null problem");
+    if (p->last_launch.variant < 0) return fail(LCF_ERR_STATE, "no kernel has been launched for this problem yet");
+    if (groups) *groups = p->last_launch.groups;
+    if (sum_units) *sum_units = p->last_launch.nq;
+    return 0;
+}
+
 static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, const double *params, double *out, size_t out_per_set,
                        long long *nan_count) {
     NvtxRange r("lcf_eval");
@@ -850,6 +934,17 @@ static int eval_common(lcf_problem *p, int mode, long long nsets, int ncols, con
     mv.qin = d_q;
     mv.out = d_out;
     mv.nanflag = d_nan;
+    if (mode != MODE_MODEL && nsets >= 4096) {           // large batches may be launched as a flat split (scratch: grow-only, zeroed counters)
+        if (nsets > p->split_cap) {
+            cudaFree(p->d_split_part); cudaFree(p->d_split_tick); p->d_split_part = nullptr; p->d_split_tick = nullptr; p->split_cap = 0;
+            CUDA_TRY(cudaMalloc(&p->d_split_part, sizeof(double) * kSplitUnits * (nsets + 32)));
+            CUDA_TRY(cudaMalloc(&p->d_split_tick, sizeof(unsigned int) * (nsets + 1)));
+            CUDA_TRY(cudaMemset(p->d_split_tick, 0, sizeof(unsigned int) * (nsets + 1)));
+            p->split_cap = nsets;
+        }
+        mv.split_part = p->d_split_part;
+        mv.split_tick = p->d_split_tick;
+    }
     rc = launch_pass(p, mv, 0, nullptr);
     if (!rc) {
         cudaError_t e = cudaDeviceSynchronize();
@@ -923,6 +1018,8 @@ int lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int ran
         (ce = cudaMalloc(&e->d_acc, sizeof(unsigned long long) * e->W)) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_nan, 2 * sizeof(int))) != cudaSuccess ||
         (ce = cudaMalloc(&e->d_flags, 2 * (kMaxPeers + 1) * sizeof(unsigned int))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_split_part, sizeof(double) * kSplitUnits * (e->W + 32))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_split_tick, sizeof(unsigned int) * (e->W + 1))) != cudaSuccess ||
         (ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (ce = cudaEventCreate(&e->ev0)) != cudaSuccess || (ce = cudaEventCreate(&e->ev1)) != cudaSuccess) {
         delete e;
@@ -931,6 +1028,7 @@ int lcf_ensemble_create(lcf_problem *p, int64_t nwalkers, uint64_t seed, int ran
     cudaMemset(e->d_acc, 0, sizeof(unsigned long long) * e->W);
     cudaMemset(e->d_nan, 0, 2 * sizeof(int));
     cudaMemset(e->d_flags, 0, 2 * (kMaxPeers + 1) * sizeof(unsigned int));
+    cudaMemset(e->d_split_tick, 0, sizeof(unsigned int) * (e->W + 1));
     *out = e;
     return 0;
 }
@@ -983,6 +1081,8 @@ int lcf_ensemble_set_state(lcf_ensemble *e, const double *coords, const double *
         mv.qin = e->d_coords;
         mv.out = e->d_logp;
         mv.nanflag = e->d_nan;
+        mv.split_part = e->d_split_part;
+        mv.split_tick = e->d_split_tick;
         int rc = launch_pass(e->p, mv, e->stream, nullptr);
         if (rc) return rc;
         rc = check_nan(e);
@@ -1027,6 +1127,8 @@ int lcf_ensemble_set_state_slice(lcf_ensemble *e, int64_t first, int64_t count, 
         mv.qin = e->d_coords + row0 * D;
         mv.out = e->d_logp + row0;
         mv.nanflag = e->d_nan;
+        mv.split_part = e->d_split_part;
+        mv.split_tick = e->d_split_tick;
         int rc = launch_pass(e->p, mv, e->stream, nullptr);
         if (rc) return rc;
         if (e->npeers) {
@@ -1116,6 +1218,8 @@ static void fill_move(lcf_ensemble *e, int half, int store, MoveDev &mv) {
     mv.comp_base = half ? 0 : e->n0;
     mv.seed = e->seed;
     mv.ctr = (unsigned int)(2 * e->iteration + half);
+    mv.split_part = e->d_split_part;
+    mv.split_tick = e->d_split_tick;
     if (store) {
         // the kernel indexes by logical walker j: bias the step pointers by the first stored walker
         mv.chain_step = e->d_chain + (e->nstored * e->cw - e->cfirst) * e->D;
@@ -1241,6 +1345,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     Shape sh;
     int rc = choose_shape(p, std::max(e->n0, e->n1), &sh);
     if (rc) return rc;
+    if (sh.flat > 0) return 0;                                               // a flat split is a large ensemble by construction
     if (!(env && env[0] == '1') && sh.cost > 120000.) return 0;             // > ~60 us per half-step: launch latency is already hidden
     const bool f32 = p->precision == LCF_PRECISION_FP32;
     RingKernel k = f32 ? ring_kernel_for<float>(p->dev.model) : ring_kernel_for<double>(p->dev.model);
@@ -1302,9 +1407,10 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     G.bar = e->d_ring_bar;
     G.wpb_log2 = sh.l;
     G.ks = sh.ks;
+    G.nq = sh.nq;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, G));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
-    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3;
+    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3; p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups;
     e->last_launches += 1;
     e->iteration += nsteps;
     if (store) e->nstored += nsteps;

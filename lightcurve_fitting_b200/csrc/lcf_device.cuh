@@ -26,6 +26,9 @@ namespace lcf {
 
 #ifdef LCF_X_TIMING   // experiment builds: per-phase SM clocks summed over CTAs (thread 0), see tools/microbench
 __device__ unsigned long long g_phase_clk[10];
+__device__ unsigned long long g_cta_log[3 * 4096];    // per CTA of the last k_pass launch: start, end (globaltimer ns), SM id
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int smid() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define LCF_TICK(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 #define LCF_TICK_INIT long long _t0 = clock64()
 #else
@@ -73,7 +76,15 @@ struct TileDev {           // one tile table per WPB
     int ntiles;
 };
 
+// byte offsets of the shared-memory carve-up (SmemLayout below); k_pass receives them from the host in its parameter block
+// (MoveDev::lay), so that the per-tile code re-reads an offset from the constant bank instead of recomputing the layout arithmetic
+// (the hot kernels have no register to spare)
+struct SmemOffsets {
+    unsigned int off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_old, off_term, off_part, off_cpart, off_flag, off_bar, total;
+};
+
 struct MoveDev {
+    SmemOffsets lay;                 // filled by launch_pass for the chosen shape
     double *coords;                  // [W][D] colour-major rows
     double *logp;                    // [W]
     unsigned long long *accepted;    // [W] indexed by logical walker
@@ -81,6 +92,13 @@ struct MoveDev {
     long long W, n0;                 // n0 = rows of colour 0
     int mode, wpb_log2;
     int ks;                          // log2 of the sample chunks a (walker, point pair) is split into (split-K tiles, small problems)
+    // Structured chi-square sums (nq > 1): the tile rows of a light curve are dealt to nq "units" (row r belongs to unit r % nq), a
+    // walker's chi-square is  sum_q ( sum_warps P(q, warp) )  in that order whichever CTA computed which unit.  A launch may then give
+    // every CTA the same number of units (a flat split of the group x unit space: no partial last wave); a group shared by several
+    // CTAs is finished by the one that arrives last (partial sums in split_part, arrival counter in split_tick).
+    int nq;
+    double *split_part;              // [groups][nq][walkers per CTA] unit sums of the groups shared by several CTAs
+    unsigned int *split_tick;        // [groups] units delivered so far (zero between launches)
     // active set: physical row = act_rows ? act_rows[i] : act_base + i,  i in [0, Ns)
     long long Ns, act_base;
     const int *act_rows;
@@ -971,28 +989,29 @@ __device__ __forceinline__ void dsmem_store_f64(double *local, uint32_t rank, do
 constexpr int kMaxCluster = 8;      // portable cluster size limit
 constexpr int kTermStride = kMaxTerms + kMaxDim + 2;   // per walker: model terms, prior terms, ln z, ln u
 
-template <typename R> struct SmemLayout {
-    size_t off_e2t, off_bank, off_spl, off_tab, off_foff, off_wc, off_t, off_q, off_lp, off_z, off_old, off_term, off_part, off_cpart, off_flag, off_bar, total;
+template <typename R> struct SmemLayout : SmemOffsets {
+    __host__ __device__ explicit SmemLayout(const SmemOffsets &o) : SmemOffsets(o) {}
     // ncluster: largest cluster that may share a walker group (1 in the chain kernel: no cluster partials to hold)
-    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster) {
+    __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster, int nq = 1) {
         size_t o = 0;
-        off_e2t = o;  o += sizeof(R) == 8 ? (size_t)kE2TabSize * sizeof(double) : 0;   // 2^(j/1024), FP64 loop
-        off_bank = o; o += (size_t)nsamples * 2 * sizeof(R);                      o = (o + 15) & ~(size_t)15;
-        off_spl = o;  o += (size_t)nspl * 4 * sizeof(R);                          o = (o + 15) & ~(size_t)15;   // SiFTO cubic coefficients
-        off_tab = o;  o += tab ? (size_t)nsamples * (wpb < 32 ? wpb : 32) * sizeof(R) : 0;   o = (o + 15) & ~(size_t)15;   // R2[nsamples/2][min(wpb, 32)]
-        off_foff = o; o += (size_t)nfilters * sizeof(int4);                       o = (o + 15) & ~(size_t)15;
-        off_wc = o;   o += (size_t)wpb * kNumWC * sizeof(R);                      o = (o + 15) & ~(size_t)15;
-        off_t = o;    o += (size_t)wpb * 2 * sizeof(double);
-        off_q = o;    o += (size_t)wpb * ndim * sizeof(double);
-        off_lp = o;   o += (size_t)wpb * sizeof(double);
-        off_z = o;    o += (size_t)wpb * sizeof(double);
-        off_old = o;  o += (size_t)wpb * sizeof(double);                         // log-probability of the walker being moved (prefetched)
-        off_term = o; o += (size_t)wpb * kTermStride * sizeof(double);
-        off_part = o; o += (size_t)nwarps * wpb * sizeof(double);
-        off_cpart = o; o += ncluster > 1 ? (size_t)ncluster * wpb * sizeof(double) : 0;
-        off_flag = o; o += (size_t)wpb * sizeof(int);                             o = (o + 15) & ~(size_t)15;
-        off_bar = o;  o += 16;
-        total = o;
+        auto at = [&](size_t bytes, bool align) { const unsigned int here = (unsigned int)o; o += bytes; if (align) o = (o + 15) & ~(size_t)15; return here; };
+        off_e2t = at(sizeof(R) == 8 ? (size_t)kE2TabSize * sizeof(double) : 0, false);   // 2^(j/1024), FP64 loop
+        off_bank = at((size_t)nsamples * 2 * sizeof(R), true);
+        off_spl = at((size_t)nspl * 4 * sizeof(R), true);                                 // SiFTO cubic coefficients
+        off_tab = at(tab ? (size_t)nsamples * (wpb < 32 ? wpb : 32) * sizeof(R) : 0, true);   // R2[nsamples/2][min(wpb, 32)]
+        off_foff = at((size_t)nfilters * sizeof(int4), true);
+        off_wc = at((size_t)wpb * kNumWC * sizeof(R), true);
+        off_t = at((size_t)wpb * 2 * sizeof(double), false);
+        off_q = at((size_t)wpb * ndim * sizeof(double), false);
+        off_lp = at((size_t)wpb * sizeof(double), false);
+        off_z = at((size_t)wpb * sizeof(double), false);
+        off_old = at((size_t)wpb * sizeof(double), false);                               // log-probability of the walker being moved (prefetched)
+        off_term = at((size_t)wpb * kTermStride * sizeof(double), false);
+        off_part = at(nq > 1 ? (size_t)nq * nwarps * wpb * sizeof(R) : (size_t)nwarps * wpb * sizeof(double), true);
+        off_cpart = at(ncluster > 1 ? (size_t)ncluster * wpb * sizeof(double) : 0, false);
+        off_flag = at((size_t)wpb * sizeof(int), true);
+        off_bar = at(16, false);
+        total = (unsigned int)o;
     }
 };
 
@@ -1010,7 +1029,8 @@ template <typename R> struct SmemLayout {
 // the per-tile mode and use_sigma branches are compiled out.
 template <int MODEL, typename R, int WL = -1, bool PLAIN = false>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
-                                           unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize) {
+                                           unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize,
+                                           int q_lo = 0, int q_hi = 1) {
     typedef typename Vec2<R>::type R2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int wl2 = WL >= 0 ? WL : Mv.wpb_log2;
@@ -1176,8 +1196,13 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const R4 *pobs = reinterpret_cast<const R4 *>(P.obs);
     const R2 *s_tabw = s_tab + wl;
     const int4 *tiles = TL.tiles;
+    // units [q_lo, q_hi) of the group's tile rows (nq = 1: the whole light curve, rows dealt to the CTAs of the cluster)
+    const int nq = Mv.nq > 1 ? Mv.nq : 1;
+    R *s_qpart = reinterpret_cast<R *>(smem + L.off_part);
     R chi = 0;
-    for (int tile = crank * nstripes + stripe; tile < TL.ntiles; tile += nstripes * csize) {
+    for (int q = q_lo; q < q_hi; ++q) {
+    if (nq > 1) chi = 0;
+    for (int tile = (q * csize + crank) * nstripes + stripe; tile < TL.ntiles; tile += nstripes * csize * nq) {
         const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
         const bool active = !skip && slot < tl.y;
         const unsigned amask = ks ? __ballot_sync(0xffffffffu, active) : 0u;    // the chunk lanes of a point pair are active together
@@ -1232,16 +1257,54 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             }
         }
     }
+    if (nq > 1) {                                          // P(q, warp): this warp's share of unit q, per walker
+        double cq = (double)chi;
+        for (int off = 16; off >= wpb; off >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, off);
+        if (lane < wpb) s_qpart[((q - q_lo) * nw + warp) * wpb + lane] = (R)cq;
+    }
+    }
     LCF_TICK(3);
     if (!PLAIN && Mv.mode == MODE_MODEL) { __syncthreads(); return; }
 
     // ---- phase 3: reduce, accept, write back ----------------------------------------------
-    double chid = (double)chi;
-    for (int off = 16; off >= wpb; off >>= 1) chid += __shfl_xor_sync(0xffffffffu, chid, off);
     const int pw = wpb < 32 ? wpb : 32;                    // walkers per warp
-    if (lane < pw) s_part[warp * pw + lane] = chid;
+    if (nq == 1) {
+        double chid = (double)chi;
+        for (int off = 16; off >= wpb; off >>= 1) chid += __shfl_xor_sync(0xffffffffu, chid, off);
+        if (lane < pw) s_part[warp * pw + lane] = chid;
+    }
     __syncthreads();
     LCF_TICK(4);
+    // structured sums: unit totals in warp order; a group that this CTA holds completely is finished here, a shared one by the CTA
+    // that delivers the last units (arrival counter; the unit totals travel through global memory and are added in unit order)
+    double tot_q = 0.;
+    if (nq > 1) {
+        const bool whole = q_hi - q_lo == nq;
+        if (tid < wpb && g * wpb + tid < Mv.Ns) {
+            for (int q = q_lo; q < q_hi; ++q) {
+                double sq = 0.;
+                for (int w2 = 0; w2 < nw; ++w2) sq += (double)s_qpart[((q - q_lo) * nw + w2) * wpb + tid];
+                if (whole) tot_q += sq;
+                else Mv.split_part[(g * nq + q) * wpb + tid] = sq;
+            }
+        }
+        if (!whole) {
+            int *s_fin = reinterpret_cast<int *>(smem + L.off_bar) + 2;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int n = (unsigned int)(q_hi - q_lo);
+                const unsigned int prev = atomicAdd(Mv.split_tick + g, n);
+                const int fin = prev + n == (unsigned int)nq;
+                if (fin) { Mv.split_tick[g] = 0u; __threadfence(); }
+                *s_fin = fin;
+            }
+            __syncthreads();
+            if (!*s_fin) { __syncthreads(); return; }      // (barrier: s_fin is rewritten by the next group of this CTA)
+            if (tid < wpb && g * wpb + tid < Mv.Ns)
+                for (int q = 0; q < nq; ++q) tot_q += __ldcg(Mv.split_part + (g * nq + q) * wpb + tid);
+        }
+    }
     // partial sums of walker `tid`: over all warps (narrow) or over the stripes of its column (wide), in warp order
     auto cta_total = [&](int w) {
         double tot = 0.;
@@ -1260,7 +1323,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             double nlp = lp;
             if (!s_flag[tid]) {
                 double tot = 0.;
-                if (csize > 1) { for (int r = 0; r < csize; ++r) tot += s_cpart[r * wpb + tid]; }
+                if (nq > 1) tot = tot_q;
+                else if (csize > 1) { for (int r = 0; r < csize; ++r) tot += s_cpart[r * wpb + tid]; }
                 else tot = cta_total(tid);
                 nlp = lp + (-0.5 * (P.const_term + tot));
             }
@@ -1306,7 +1370,7 @@ template <int MODEL, typename R, int WL, bool PLAIN>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
-    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
+    const SmemLayout<R> L(Mv.lay);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
@@ -1320,11 +1384,28 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
     const long long nclusters = cluster_count_x();
     if (Mv.npeers) peers_wait(Mv);
+#ifdef LCF_X_TIMING
+    const unsigned long long t_cta0 = gtimer();
+#endif
     bool first = true;
-    for (long long g = cluster_id_x(); g < ngroups; g += nclusters) {
-        group_pass<MODEL, R, WL, PLAIN>(P, TL, Mv, g, smem, L, first, crank, csize);
+    // Cluster b takes the units [b U / B, (b + 1) U / B) of the (group, unit) space, U = groups x nq, B = clusters of the grid.  With
+    // B = groups every cluster holds one whole group (plain sums, nq = 1: always); a flat split launches B = the co-resident CTA slots
+    // of the device, so that all CTAs finish together (no partial last wave) -- a group shared by several CTAs is finished by the
+    // one that delivers its last units.
+    const int nq = Mv.nq > 1 ? Mv.nq : 1;
+    const long long U = ngroups * nq, b = cluster_id_x();       // U < 2^31 (checked by the host)
+    int u = (int)((b * U) / nclusters);
+    const int u1 = (int)(((b + 1) * U) / nclusters);
+    while (u < u1) {
+        const int g = u / nq, qa = u - g * nq;
+        const int qb = min(nq, qa + (u1 - u));
+        group_pass<MODEL, R, WL, PLAIN>(P, TL, Mv, (long long)g, smem, L, first, crank, csize, qa, qb);
         first = false;
+        u += qb - qa;
     }
+#ifdef LCF_X_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 4096) { g_cta_log[3 * blockIdx.x] = t_cta0; g_cta_log[3 * blockIdx.x + 1] = gtimer(); g_cta_log[3 * blockIdx.x + 2] = smid(); }
+#endif
     if (Mv.npeers) peers_publish(Mv);
 }
 
@@ -1380,6 +1461,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     Mv.nanflag = B.status + prob;
     Mv.W = B.W; Mv.n0 = B.n0;
     Mv.wpb_log2 = B.wpb_log2; Mv.ks = B.ks;
+    Mv.nq = 1; Mv.split_part = nullptr; Mv.split_tick = nullptr;
     Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
     Mv.npeers = 0;
@@ -1433,6 +1515,7 @@ struct RingDev {
     unsigned long long seed;
     unsigned int *bar;                 // [2]: arrival counter, generation (zeroed before the launch)
     int wpb_log2, ks;
+    int nq;                            // units of the structured chi-square sums (same value as the k_pass launches of this shape)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -1464,7 +1547,7 @@ template <int MODEL, typename R>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const ProblemDev P, const TileDev TL, const RingDev G) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << G.wpb_log2;
-    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0);
+    SmemLayout<R> L(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0, kMaxCluster, G.nq);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
@@ -1478,6 +1561,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     Mv.nanflag = G.nanflag;
     Mv.W = G.W; Mv.n0 = G.n0;
     Mv.mode = MODE_MOVE; Mv.wpb_log2 = G.wpb_log2; Mv.ks = G.ks;
+    Mv.nq = G.nq > 1 ? G.nq : 1; Mv.split_part = nullptr; Mv.split_tick = nullptr;   // every CTA holds whole groups here
     Mv.act_rows = nullptr; Mv.comp_rows = nullptr;
     Mv.zin = nullptr; Mv.rin = nullptr; Mv.luin = nullptr;
     Mv.npeers = 0;
@@ -1497,7 +1581,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
             Mv.Nc = half ? G.n0 : n1;
             Mv.comp_base = half ? 0 : G.n0;
             const long long ng = (Mv.Ns + wpb - 1) / wpb;
-            for (long long g = cid; g < ng; g += nclusters) { group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize); first = false; }
+            for (long long g = cid; g < ng; g += nclusters) { group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize, 0, Mv.nq); first = false; }
 #ifdef LCF_X_TIMING
             const long long tb0 = clock64();
 #endif

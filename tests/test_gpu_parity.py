@@ -852,7 +852,11 @@ def test_cfg2_shape_native_moves_on_the_benchmark_kernel(precision):
     s.run_mcmc(p0, 5, skip_initial_state_check=True)
     launch = prob.last_launch()
     assert launch['kernel'] == 'k_pass<32 walkers, plain>' and launch['walkers_per_cta'] == 32 and launch['warps_per_cta'] == 16
-    assert launch['grid'] == (nw // 2 + 31) // 32 and launch['cluster'] == 1
+    assert launch['groups'] == (nw // 2 + 31) // 32 and launch['cluster'] == 1 and launch['sum_units'] == 8
+    if launch['flat']:                                           # one CTA per co-resident slot, each with the same share of the work
+        assert launch['grid'] % _sm_count() == 0 and launch['grid'] < launch['groups']
+    else:
+        assert launch['grid'] == launch['groups']
     chain, lnp = s.get_chain(), s.get_log_prob()
     assert chain.shape == (5, nw, wl.ndim)
     acc = s.acceptance_fraction
@@ -877,7 +881,7 @@ def test_cfg4_shape_native_moves(precision='fp32'):
     s = EnsembleSampler(nw, wl.ndim, prob, seed=12)
     s.run_mcmc(wl.start(nw, np.random.default_rng(3)), 4, skip_initial_state_check=True)
     launch = prob.last_launch()
-    assert launch['grid'] * launch['walkers_per_cta'] >= nw // 2
+    assert launch['groups'] * launch['walkers_per_cta'] >= nw // 2
     chain, lnp = s.get_chain(), s.get_log_prob()
     assert 0.05 < s.acceptance_fraction.mean() < 0.95
     _check_chain_rows_against_oracle(wl, chain, lnp, precision, 16, 6)
@@ -1260,3 +1264,44 @@ def test_split_k_persistent_kernel_and_batches(monkeypatch):
     chain, lnp = b.get_chain(), b.get_log_prob()
     for k, w in enumerate(wls):
         _check_chain_rows_against_oracle(w, chain[k], lnp[k], 'fp64', 10, k)
+
+
+def _sm_count():
+    import torch
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'fp64'])
+@pytest.mark.parametrize('name,nw,shape', [('sc3_synth', 20000, (32, 16, 1)), ('sc4_synth', 9001, (16, 8, 1)), ('cs3_synth', 12000, (32, 8, 1))])
+def test_flat_split_chains_are_bit_identical_to_one_group_per_cta(name, nw, shape, precision):
+    """Flat split (every CTA of a slots-sized grid takes the same share of the (group, unit) space; groups shared by several CTAs are
+    finished by the last one to deliver) against the plain launch of the same shape (one whole group per CTA): the structured sums
+    have one order whichever CTA computed which unit, so chains, log-probabilities, acceptance counts and the initial evaluation must be
+    bit-identical; odd walker counts leave a partial last group."""
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    wl = {'sc3_synth': lambda: W.synthetic_sc3(npoints=1100), 'sc4_synth': lambda: W.synthetic_sc4(npoints=1200),
+          'cs3_synth': lambda: W.synthetic_cs3(npoints=1000)}[name]()
+    prob = wl.device_problem(precision)
+    p0 = wl.start(nw, np.random.default_rng(8))
+    out = {}
+    check(lib().lcf_set_tuning_ex(*shape))
+    check(lib().lcf_set_tuning_split(1))                          # no split-K either: the launch shape is pinned completely
+    try:
+        for flat in (0, 1):
+            check(lib().lcf_set_tuning_flat(flat))
+            s = EnsembleSampler(nw, wl.ndim, prob, seed=21)
+            s.run_mcmc(p0, 6, skip_initial_state_check=True)
+            launch = prob.last_launch()
+            assert launch['sum_units'] == 8, launch
+            assert launch['flat'] == bool(flat), launch
+            lp = prob.log_posterior(p0[:5000])
+            out[flat] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction, lp)
+    finally:
+        check(lib().lcf_set_tuning_flat(-1))
+        check(lib().lcf_set_tuning_split(0))
+        check(lib().lcf_set_tuning_ex(0, 0, 0))
+    assert 0.02 < out[1][2].mean() < 0.98
+    for a, b in zip(out[0], out[1]):
+        np.testing.assert_array_equal(a, b)
+    _check_chain_rows_against_oracle(wl, out[1][0], out[1][1], precision, 8, 3)

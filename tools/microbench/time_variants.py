@@ -47,7 +47,20 @@ def child(args):
             L.lcf_debug_phase_clocks(buf)                      # reset
             s.run_mcmc(None, 1, skip_initial_state_check=True, store=False)
             L.lcf_debug_phase_clocks(buf)
-            extra['phase_clk_per_cta_launch'] = [int(v) for v in buf[:6]]
+            extra['phase_clk_sums'] = [int(v) for v in buf[:10]]
+            if hasattr(L, 'lcf_debug_cta_log'):
+                log = (C.c_uint64 * (3 * 4096))()
+                L.lcf_debug_cta_log(log)
+                a = np.array(log[:], dtype=np.uint64).reshape(4096, 3)
+                grid = int(prob.last_launch()['grid'])
+                a = a[:min(grid, 4096)].astype(np.int64)
+                t0 = a[:, 0].min()
+                np.save(os.path.join(ROOT, 'gpurun_out', 'cta_log_flat%s.npy' % os.environ.get('LCF_FLAT', 'x')), a)
+                dur = (a[:, 1] - a[:, 0]) / 1e3
+                per_sm = np.bincount(a[:, 2], minlength=148)
+                extra['cta_log'] = {'grid': grid, 'kernel_us': float((a[:, 1].max() - t0) / 1e3), 'start_spread_us': float((a[:, 0].max() - t0) / 1e3),
+                                    'end_min_us': float((a[:, 1].min() - t0) / 1e3), 'dur_us_min_med_max': [float(dur.min()), float(np.median(dur)), float(dur.max())],
+                                    'ctas_per_sm_min_max': [int(per_sm.min()), int(per_sm.max())], 'sms_used': int((per_sm > 0).sum())}
         sps = args.walkers / 2 * spe / (ms * 1e-3)
         print(json.dumps({'lib': os.path.basename(os.environ.get('LCF_B200_LIB', 'default')), 'shape': shape, 'model': args.model,
                           'ms_half_step': round(ms, 4), 'walker_steps_per_s': round(args.walkers / (2 * ms * 1e-3)),
