@@ -274,9 +274,10 @@ int  lcf_set_tuning_split(int sample_chunks);
    sums keep one fixed order (units, then warps) whichever CTA computed what, so chains do not depend on the split.
    -1 = the launch-shape cost model decides (default), 0 = never, 1 = whenever the shape allows it.                              */
 int  lcf_set_tuning_flat(int mode);
-/* lcf_problem_last_launch plus: walker groups of the launch and units of the structured sums (1: plain per-warp sums); a launch
-   with grid != groups x cluster_size was a flat split.                                                                          */
-int  lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units);
+/* lcf_problem_last_launch plus: walker groups of the launch, units of the structured sums (1: plain per-warp sums) and photometry
+   points per lane and tile (4 in the 32-walker plain FP32 kernels of ShockCooling 1-3, else 2); a launch with
+   grid != groups x cluster_size was a flat split.                                                                               */
+int  lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units, int *points_per_lane);
 
 #ifdef __cplusplus
 }

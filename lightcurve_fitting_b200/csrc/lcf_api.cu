@@ -130,7 +130,7 @@ struct lcf_problem {
     std::vector<int> h_filter_records;          // pair records of every filter (tile cost)
     struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0, nq = 1; long long flat = 0; size_t smem = 0; double cost = 0.; } shape_cache;
     double mean_samples = 0.;                   // mean transmission samples per photometry point
-    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0, nq = 1; long long grid = 0, groups = 0; } last_launch;   // lcf_problem_last_launch
+    struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0, nq = 1, ppl = 2; long long grid = 0, groups = 0; } last_launch;   // lcf_problem_last_launch
     double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
     int *d_eval_nan = nullptr;
     size_t eval_q_cap = 0, eval_out_cap = 0;
@@ -237,8 +237,9 @@ typedef void (*RingKernel)(const ProblemDev, const TileDev, const RingDev);
 // LCF_DEV_ONLY_MODEL=<id> (tools/microbench builds): instantiate the FP32 half-step kernel of one model only, so that a
 // kernel experiment compiles in seconds.  Never defined for the shipped library.
 #ifdef LCF_DEV_ONLY_MODEL
-template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false) {
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false, int ppl = 2) {
     if (model != LCF_DEV_ONLY_MODEL) return nullptr;
+    if constexpr (sizeof(R) == 4 && LCF_DEV_ONLY_MODEL <= 3) if (l == 5 && plain && ppl == 4) return k_pass<LCF_DEV_ONLY_MODEL, R, 5, true, 4>;
     if (l == 5) return plain ? k_pass<LCF_DEV_ONLY_MODEL, R, 5, true> : k_pass<LCF_DEV_ONLY_MODEL, R, 5, false>;
     return k_pass<LCF_DEV_ONLY_MODEL, R, -1, false>;
 }
@@ -247,8 +248,13 @@ template <typename R> RingKernel ring_kernel_for(int model) { return model == LC
 #else
 // l = walkers-per-CTA exponent of the launch: 5 (32 walkers, every large ensemble) has its own instantiation
 // and, for it, one more without the per-tile mode / use_sigma branches (plain = no intrinsic scatter, not a model evaluation)
-template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false) {
+template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool plain = false, int ppl = 2) {
 #define LCF_PASS_CASE(M) case M: return l == 5 ? (plain ? k_pass<M, R, 5, true> : k_pass<M, R, 5, false>) : k_pass<M, R, -1, false>;
+    if constexpr (sizeof(R) == 4) if (l == 5 && plain && ppl == 4) {   // four points per lane (points_per_lane below)
+        if (model == 1) return k_pass<1, R, 5, true, 4>;
+        if (model == 2) return k_pass<2, R, 5, true, 4>;
+        if (model == 3) return k_pass<3, R, 5, true, 4>;
+    }
     switch (model) {
         LCF_PASS_CASE(1) LCF_PASS_CASE(2) LCF_PASS_CASE(3) LCF_PASS_CASE(4)
         LCF_PASS_CASE(5) LCF_PASS_CASE(6) LCF_PASS_CASE(7) LCF_PASS_CASE(8)
@@ -315,12 +321,19 @@ int ensure_dynamic_smem(const void *kernel, size_t bytes) {
 // filter); warp slot j of a launch takes the tiles j, j + P, j + 2P, ...  (Sorting the tiles by cost and dealing them in serpentine
 // order to balance the slots was measured this round: no gain on cfg1 / cfg4 / cfg5 -- profiles/round2_kernel_variants.jsonl -- so
 // the natural order stays.)  Problems of a flat-array batch share one allocation for all their tables (negative ntiles marks those).
-int get_tiles(lcf_problem *p, int lt, int period, TileDev *out) {
+// Photometry points per lane and tile: 4 in the 32-walker plain FP32 launches of the one-blackbody models (ShockCooling 1-3: the
+// per-tile work is paid once per four points), else 2.  LCF_PPL=2 (experiments) keeps two everywhere.
+int points_per_lane(const lcf_problem *p, int l, bool plain) {
+    static const bool two = [] { const char *e = getenv("LCF_PPL"); return e && e[0] == '2'; }();
+    return (!two && l == 5 && plain && p->precision == LCF_PRECISION_FP32 && p->dev.model >= 1 && p->dev.model <= 3) ? 4 : 2;
+}
+
+int get_tiles(lcf_problem *p, int lt, int period, TileDev *out, int ppl = 2) {
     (void)period;
-    const int key = lt * 1024;
+    const int key = lt * 1024 + (ppl == 2 ? 0 : ppl);
     auto it = p->tile_tabs.find(key);
     if (it != p->tile_tabs.end()) { *out = it->second; if (out->ntiles < 0) out->ntiles = -out->ntiles; return 0; }
-    const int ppt = 2 * (32 >> lt);              // two points per lane
+    const int ppt = ppl * (32 >> lt);            // `ppl` points per lane
     std::vector<int4> t;
     const int N = p->dev.npoints;
     int i = 0;
@@ -387,8 +400,8 @@ int build_tiles_shared(const std::vector<lcf_problem *> &probs, void **block) {
 //   * a tile is always 64 (walker, point) pairs of ONE filter, so small wpb wastes lanes when a filter has few points:
 //     that is in ntiles(l);
 //   * clusters and very small CTAs carry measured penalties (redundant setup per CTA, co-scheduling constraints).
-int count_tiles(const lcf_problem *p, int l) {
-    const int slots = 2 * (32 >> l), N = p->dev.npoints;
+int count_tiles(const lcf_problem *p, int l, int ppl = 2) {
+    const int slots = ppl * (32 >> l), N = p->dev.npoints;
     int tiles = 0, i = 0;
     while (i < N) {
         int f = p->h_point_filter[i], j = i;
@@ -448,7 +461,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                 const int nw = nw_cand[ci];
                 // structured sums (and with them the flat split) for unsplit shapes whose warps see at least two tile rows per unit;
                 // a function of the problem and the shape only, never of Ns: chains do not depend on how an ensemble is sharded
-                const int rows = (ntiles + nw - 1) / nw;
+                const int rows = (count_tiles(p, l + ks, ks == 0 ? points_per_lane(p, l, true) : 2) + nw - 1) / nw;   // (of the coarsest tile table a launch of this shape uses)
                 int nq_s1 = (ks == 0 && rows >= 2 * kSplitUnits && sum_units_enabled()) ? kSplitUnits : 1;
                 if (nq_s1 > 1 && smem_bytes(p, 1 << l, nw, kMaxCluster, nq_s1) > kSmemMax) nq_s1 = 1;
                 const size_t sm_plain = smem_bytes(p, 1 << l, nw);
@@ -505,7 +518,8 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     }
     int rc = 0;
     for (int plain = 0; plain < 2; ++plain) {
-        PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain) : pass_kernel_for<double>(p->dev.model, bs.l, plain);
+        const int ppl = points_per_lane(p, bs.l, plain != 0);
+        PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain, ppl) : pass_kernel_for<double>(p->dev.model, bs.l, plain, ppl);
         if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
         if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), bs.smem))) return rc;
     }
@@ -538,8 +552,9 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
         if (mv.lay.total != sh.smem) return fail(LCF_ERR_STATE, "shared-memory layout mismatch");
     }
     const bool plain = mv.mode != MODE_MODEL && !p->dev.use_sigma;
-    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain)
-                                                        : pass_kernel_for<double>(p->dev.model, sh.l, plain);
+    const int ppl = points_per_lane(p, sh.l, plain);
+    PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain, ppl)
+                                                        : pass_kernel_for<double>(p->dev.model, sh.l, plain, ppl);
     const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
     if (ngroups * sh.nq >= (1LL << 31)) return fail(LCF_ERR_ARG, "too many walker groups for one launch");
     long long clusters = std::min<long long>(ngroups, (1LL << 30) / sh.cluster);
@@ -568,11 +583,11 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     TileDev tiles;
-    if ((rc = get_tiles(p, sh.l + sh.ks, sh.nw * sh.cluster, &tiles))) return rc;
+    if ((rc = get_tiles(p, sh.l + sh.ks, sh.nw * sh.cluster, &tiles, ppl))) return rc;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, mv));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
     p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
-    p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups;
+    p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups; p->last_launch.ppl = ppl;
     if (launches) ++*launches;
     return 0;
 }
@@ -894,11 +909,12 @@ int lcf_problem_last_launch(lcf_problem *p, int *walkers_per_cta, int *warps_per
     return 0;
 }
 
-int lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units) {
+int lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units, int *points_per_lane) {
     if (!p) return fail(LCF_ERR_ARG, "null problem");
     if (p->last_launch.variant < 0) return fail(LCF_ERR_STATE, "no kernel has been launched for this problem yet");
     if (groups) *groups = p->last_launch.groups;
     if (sum_units) *sum_units = p->last_launch.nq;
+    if (points_per_lane) *points_per_lane = p->last_launch.ppl;
     return 0;
 }
 
@@ -1410,7 +1426,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     G.nq = sh.nq;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, G));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
-    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3; p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups;
+    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3; p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups; p->last_launch.ppl = 2;
     e->last_launches += 1;
     e->iteration += nsteps;
     if (store) e->nstored += nsteps;

@@ -630,6 +630,36 @@ __device__ __forceinline__ void planck_quad_sc4_f32(const float4 *__restrict__ b
     SA = a.x + a.y; SAs = as.x + as.y; SB = bb.x + bb.y; SBs = bs.x + bs.y;
 }
 
+// (c) four points of one walker (A, B, C, D) at ONE sample per quad, the two samples of a pair record side by side in the packed lanes:
+//     the ShockCooling4 loop with four independent temperatures and, for ShockCooling3, the per-walker weight table.  Used by the
+//     32-walker plain kernels of the one-blackbody models (PPL = 4): per-tile work (descriptor, guards, loop set-up) is paid once per
+//     four points instead of once per two.
+template <bool TAB, bool WIEN, int TS>
+__device__ __forceinline__ void planck_quad4_f32(const float4 *__restrict__ b4, int K2, float iA, float iB, float iC, float iD,
+                                                 const float2 *__restrict__ tab, int ts_rt, float &SA, float &SB, float &SC, float &SD) {
+    const int ts = TS > 0 ? TS : ts_rt;
+    const float sA = WIEN ? -iA : iA, sB = WIEN ? -iB : iB, sC = WIEN ? -iC : iC, sD = WIEN ? -iD : iD;
+    const float2 iA2 = make_float2(sA, sA), iB2 = make_float2(sB, sB), iC2 = make_float2(sC, sC), iD2 = make_float2(sD, sD);
+    float2 a = make_float2(0.f, 0.f), b = a, c = a, d = a;
+#pragma unroll 2
+    for (const float4 *pb = b4, *const pe = b4 + K2; pb < pe; ++pb) {
+        float2 x, w;
+        if (TAB) { x = *reinterpret_cast<const float2 *>(pb); w = *tab; tab += ts; }
+        else { const float4 s = *pb; x = make_float2(s.x, s.y); w = make_float2(s.z, s.w); }
+        float2 dA, dB, dC, dD, eA, eB, eC, eD;
+        ex2_terms<WIEN>(x, iA2, dA, eA); ex2_terms<WIEN>(x, iB2, dB, eB);
+        ex2_terms<WIEN>(x, iC2, dC, eC); ex2_terms<WIEN>(x, iD2, dD, eD);
+        const float2 pAB = __fmul2_rn(dA, dB), pCD = __fmul2_rn(dC, dD);
+        const float2 r = rcp_newton2(__fmul2_rn(pAB, pCD));
+        const float2 tAB = __fmul2_rn(w, __fmul2_rn(r, pCD)), tCD = __fmul2_rn(w, __fmul2_rn(r, pAB));   // w/(dA dB), w/(dC dD)
+        a = __ffma2_rn(WIEN ? __fmul2_rn(tAB, eA) : tAB, dB, a);
+        b = __ffma2_rn(WIEN ? __fmul2_rn(tAB, eB) : tAB, dA, b);
+        c = __ffma2_rn(WIEN ? __fmul2_rn(tCD, eC) : tCD, dD, c);
+        d = __ffma2_rn(WIEN ? __fmul2_rn(tCD, eD) : tCD, dC, d);
+    }
+    SA = a.x + a.y; SB = b.x + b.y; SC = c.x + c.y; SD = d.x + d.y;
+}
+
 // FP64 fast path: the same quad structure in double precision.  2^x by range reduction (x = n + f, |f| <= 1/2) and a
 // degree-12 Taylor polynomial of exp(f ln 2) (truncation 2e-16), n added to the exponent field; exponents capped at 250
 // (h nu / k T = 173: such a sample is 1e-75 of its weight) so that four denominators multiply to < 2^1000; one division per
@@ -928,6 +958,37 @@ __device__ __forceinline__ R blackbody_value(const PointFE<R> &f, bool n, R S, R
     return f.amp * S;
 }
 
+// Planck x transmission sums of up to FOUR points of one filter for one walker (FP32, one-blackbody models, whole filter): the
+// same guards as blackbody_sums on the four temperatures (inactive points borrow an active one's and their sums are dropped).
+template <int MODEL, int TS>
+__device__ __forceinline__ void blackbody_sums4(const float4 *bank, const int4 fi, const PointFE<float> (&f)[4], const bool (&n)[4],
+                                                const float2 *tab, int ts_rt, float (&S)[4]) {
+    const int ts = TS > 0 ? TS : ts_rt;
+    const float4 *b = bank + fi.x;
+    const float2 *tb = tab + (size_t)fi.x * ts;
+    const int K2 = fi.y;
+    S[0] = S[1] = S[2] = S[3] = 0.f;
+    if (!(n[0] || n[1] || n[2] || n[3]) || K2 <= 0) return;
+    const float iref = n[0] ? f[0].invT : (n[1] ? f[1].invT : (n[2] ? f[2].invT : f[3].invT));
+    const float i0 = n[0] ? f[0].invT : iref, i1 = n[1] ? f[1].invT : iref, i2 = n[2] ? f[2].invT : iref, i3 = n[3] ? f[3].invT : iref;
+    const float2 rng = make_float2(__int_as_float(fi.z), __int_as_float(fi.w));   // (a_min, a_max) of the filter
+    const float imin = fminf(fminf(i0, i1), fminf(i2, i3));
+    if (rng.x * imin >= 0.0625f) {                       // no cancellation in 2^x - 1 anywhere in the filter
+        const bool clamp = rng.y * ((i0 + i1) + (i2 + i3)) > 124.f;   // the product of four denominators could overflow: Wien form
+        if (MODEL == 3) {
+            if (clamp) planck_quad4_f32<true, true, TS>(b, K2, i0, i1, i2, i3, tb, ts, S[0], S[1], S[2], S[3]);
+            else planck_quad4_f32<true, false, TS>(b, K2, i0, i1, i2, i3, tb, ts, S[0], S[1], S[2], S[3]);
+        } else {
+            if (clamp) planck_quad4_f32<false, true, TS>(b, K2, i0, i1, i2, i3, nullptr, ts, S[0], S[1], S[2], S[3]);
+            else planck_quad4_f32<false, false, TS>(b, K2, i0, i1, i2, i3, nullptr, ts, S[0], S[1], S[2], S[3]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)                          // careful path (Rayleigh-Jeans regime)
+        if (n[k]) S[k] = (MODEL == 3) ? planck_sum_safe<float, true>(b, K2, f[k].invT, tb, ts) : planck_sum_safe<float, false>(b, K2, f[k].invT, nullptr, 0);
+}
+
 // ---------------------------------------------------------------------------------------
 // system-scope flag helpers for the fused multi-GPU exchange
 // ---------------------------------------------------------------------------------------
@@ -1027,7 +1088,8 @@ template <typename R> struct SmemLayout : SmemOffsets {
 // the lane arithmetic slot / ppt / wl and the tile guards fold to constants); WL = -1: read from Mv.wpb_log2.
 // PLAIN: the launch is a move / log-posterior / log-likelihood pass without the intrinsic-scatter term (the reference's default):
 // the per-tile mode and use_sigma branches are compiled out.
-template <int MODEL, typename R, int WL = -1, bool PLAIN = false>
+// PPL: photometry points per lane and tile (2; 4 in the 32-walker plain FP32 kernels of the one-blackbody models, see planck_quad4_f32).
+template <int MODEL, typename R, int WL = -1, bool PLAIN = false, int PPL = 2>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
                                            unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize,
                                            int q_lo = 0, int q_hi = 1) {
@@ -1206,6 +1268,38 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
         const bool active = !skip && slot < tl.y;
         const unsigned amask = ks ? __ballot_sync(0xffffffffu, active) : 0u;    // the chunk lanes of a point pair are active together
+        if constexpr (PPL == 4 && sizeof(R) == 4) {
+            // four points of the tile's filter per lane (32 walkers per CTA: lane = walker, no point slots, no split-K, plain chi-square)
+            if (active) {
+                typedef PointFE<float> FE;
+                const float4 *pobs4 = reinterpret_cast<const float4 *>(P.obs);
+                const LaneWalker<float> &lwf = reinterpret_cast<const LaneWalker<float> &>(lw);
+                const int4 fi = s_finfo[tl.z];
+                FE f[4];
+                bool n[4];
+                float2 ob[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pk = tl.x + (k < tl.y ? k : 0);
+                    const float4 o = pobs4[pk];
+                    ob[k] = make_float2(o.x, o.y);
+                    float addk;
+                    front_end<MODEL, float>(P, lwf, pk, f[k].invT, f[k].amp, addk, reinterpret_cast<const float4 *>(s_spl));
+                    n[k] = k < tl.y && f[k].invT > 0.f;
+                }
+                float S[4];
+                blackbody_sums4<MODEL, (WL == 5 ? kTabStride : 0)>(reinterpret_cast<const float4 *>(s_bank), fi, f, n,
+                                                                    reinterpret_cast<const float2 *>(s_tabw), tstride, S);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < tl.y) {
+                        const float yk = n[k] ? f[k].amp * S[k] : f[k].amp;
+                        const float rk = (ob[k].x - yk) * ob[k].y;                  // models.py:135
+                        chi = fma((R)rk, (R)rk, chi);
+                    }
+                }
+            }
+        } else
         if (active) {
             const int pa = tl.x + slot;
             const bool two = slot + ppt < tl.y;
@@ -1366,7 +1460,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
 // Kernel A: one launch = one half-step (or one evaluation pass) of ONE ensemble.
 // Grid = walker groups x cluster size (cluster dimension set by the launch attribute; 1 for large ensembles).
 // ---------------------------------------------------------------------------------------
-template <int MODEL, typename R, int WL, bool PLAIN>
+template <int MODEL, typename R, int WL, bool PLAIN, int PPL = 2>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
@@ -1399,7 +1493,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
     while (u < u1) {
         const int g = u / nq, qa = u - g * nq;
         const int qb = min(nq, qa + (u1 - u));
-        group_pass<MODEL, R, WL, PLAIN>(P, TL, Mv, (long long)g, smem, L, first, crank, csize, qa, qb);
+        group_pass<MODEL, R, WL, PLAIN, PPL>(P, TL, Mv, (long long)g, smem, L, first, crank, csize, qa, qb);
         first = false;
         u += qb - qa;
     }

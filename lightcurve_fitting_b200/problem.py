@@ -162,10 +162,10 @@ class DeviceProblem:
         a, b, c, v = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         g = C.c_int64()
         check(lib().lcf_problem_last_launch(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(g), C.byref(v)))
-        ng, nq = C.c_int64(), C.c_int()
-        check(lib().lcf_problem_last_launch_ex(self.handle, C.byref(ng), C.byref(nq)))
+        ng, nq, ppl = C.c_int64(), C.c_int(), C.c_int()
+        check(lib().lcf_problem_last_launch_ex(self.handle, C.byref(ng), C.byref(nq), C.byref(ppl)))
         return {'walkers_per_cta': a.value, 'warps_per_cta': b.value, 'cluster': c.value, 'grid': g.value,
-                'groups': ng.value, 'sum_units': nq.value, 'flat': v.value != 3 and g.value != ng.value * c.value,
+                'groups': ng.value, 'sum_units': nq.value, 'points_per_lane': ppl.value, 'flat': v.value != 3 and g.value != ng.value * c.value,
                 'kernel': {0: 'k_pass<generic>', 1: 'k_pass<32 walkers>', 2: 'k_pass<32 walkers, plain>', 3: 'k_ring'}[v.value]}
 
     # -- evaluation entry points ----------------------------------------------------------
