@@ -45,7 +45,7 @@ WALKERS_PER_GPU = 100_000
 NPOINTS = 2000
 MUFU_LANES_PER_CLK_SM = 16
 FP64_LANES_PER_CLK_SM = 64
-FP64_OPS_PER_SAMPLE = 11.75           # FP64-pipe instructions (DFMA+DMUL+DADD) per Planck sample of planck_quad_f64, counted in SASS (profiles/round2_sass_fp64_loop.txt)
+FP64_OPS_PER_SAMPLE = 10.75           # FP64-pipe instructions (DFMA+DMUL+DADD) per Planck sample of planck_quad_f64, counted in SASS (profiles/round2_sass_fp64_loop.txt)
 BALANCED_SAMPLES_PER_CLK_SM = 13.5    # FMA+MUFU balanced bound of the two-transcendental formulation
 SMS = 148
 MODEL_NAMES = {'sc3': 'ShockCooling3', 'sc4': 'ShockCooling4'}
@@ -554,9 +554,13 @@ def measure_cfg3(ctx, nepochs=500):
         warnings.simplefilter('ignore')
         calculate_bolometric(lc.copy(), res=1., seed=2)                       # warm-up (filter packing caches, kernel load)
         clocks = ctx.clocks().start(0.1)
-        t0 = time.perf_counter()
-        t, timing = calculate_bolometric(lc.copy(), res=1., seed=3, return_timing=True)
-        dt = time.perf_counter() - t0
+        runs = []
+        for rep in range(3):                                                  # host timing jitters: the median run of three is reported
+            t0 = time.perf_counter()
+            t, timing = calculate_bolometric(lc.copy(), res=1., seed=3, return_timing=True)
+            runs.append((time.perf_counter() - t0, t, timing))
+        runs.sort(key=lambda r: r[0])
+        dt, t, timing = runs[1]
         clk = clocks.stop()
     n = len(t)
     steps = 300

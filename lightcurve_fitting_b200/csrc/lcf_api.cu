@@ -462,7 +462,9 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                 // structured sums (and with them the flat split) for unsplit shapes whose warps see at least two tile rows per unit;
                 // a function of the problem and the shape only, never of Ns: chains do not depend on how an ensemble is sharded
                 const int rows = (count_tiles(p, l + ks, ks == 0 ? points_per_lane(p, l, true) : 2) + nw - 1) / nw;   // (of the coarsest tile table a launch of this shape uses)
-                int nq_s1 = (ks == 0 && rows >= 2 * kSplitUnits && sum_units_enabled()) ? kSplitUnits : 1;
+                // (FP32: measured on cfg2, the unit loop costs ShockCooling3 1.2 % and a flat split only pays at 1-2 waves, so the
+                //  cost model keeps plain sums there unless lcf_set_tuning_flat / LCF_FLAT asks for the structured ones)
+                int nq_s1 = (ks == 0 && rows >= 2 * kSplitUnits && sum_units_enabled() && (!f32 || g_flat >= 0)) ? kSplitUnits : 1;
                 if (nq_s1 > 1 && smem_bytes(p, 1 << l, nw, kMaxCluster, nq_s1) > kSmemMax) nq_s1 = 1;
                 const size_t sm_plain = smem_bytes(p, 1 << l, nw);
                 if (sm_plain > kSmemMax) continue;

@@ -665,12 +665,13 @@ __device__ __forceinline__ void planck_quad4_f32(const float4 *__restrict__ b4, 
 // (h nu / k T = 173: such a sample is 1e-75 of its weight) so that four denominators multiply to < 2^1000; one division per
 // four samples.  ~21 FP64 pipe operations per Planck sample instead of ~55 (libm exp2 + one division each).
 // Callers guarantee every exponent >= 2^-10 (2^x - 1 then keeps 1e-13 relative accuracy).
-// 2^x - 1 for the FP64 loop, x in [0, 256): x = n + j/1024 + f with |f| <= 2^-11, 2^(j/1024) from a 1024-entry (8 KB) shared-memory
-// table (filled from a device-global copy the host writes once per device), 2^f by its degree-3 Taylor polynomial (truncation
-// f^4 ln2^4 / 24 <= 5e-16): 8 FP64-pipe operations per exponential.  Measured on cfg2 (profiles/round2_kernel_variants.jsonl):
-// 16-entry table + degree 6 (round 1, 11 operations) 7.86 M walker-steps/s, 256 entries + degree 4 8.65 M, 1024 + degree 3 9.17 M.
+// 2^x - 1 for the FP64 loop, x in [0, 256): x = n + j/4096 + f with |f| <= 2^-13, 2^(j/4096) from a 4096-entry (32 KB) shared-memory
+// table (filled from a device-global copy the host writes once per device), 2^f by its degree-2 Taylor polynomial (truncation
+// f^3 ln2^3 / 6 <= 1.0e-13): 7 FP64-pipe operations per exponential, 86 per loop iteration of 8 samples (SASS count).  Measured on cfg2
+// (profiles/round2_kernel_variants.jsonl): 16-entry table + degree 6 (round 1, 11 operations) 7.86 M walker-steps/s, 256 entries +
+// degree 4 8.65 M, 1024 + degree 3 9.17 M (9.55 M with the flat split), 4096 + degree 2 9.97 M, 8192 + degree 2 9.94 M.
 #ifndef LCF_E2T_BITS
-#define LCF_E2T_BITS 10
+#define LCF_E2T_BITS 12
 #endif
 constexpr int kE2TabBits = LCF_E2T_BITS, kE2TabSize = 1 << kE2TabBits;
 __device__ double g_e2tab[kE2TabSize];                                    // 2^(j / kE2TabSize), written by the host (lcf_api.cu)
@@ -682,7 +683,10 @@ __device__ __forceinline__ double ex2m1_f64(double x, const double *__restrict__
     const double r = x + magic;
     const int k = __double2loint(r);                                     // 2^bits n + j
     const double f = x - (r - magic);
-#if LCF_E2T_BITS >= 10
+#if LCF_E2T_BITS >= 12
+    double p = 2.40226506959100712e-01;                                  // ln2^2/2  (12 bits: |f| <= 2^-13, truncation f^3 ln2^3/6 = 1.0e-13; 13 bits: 1.3e-14)
+    p = fma(p, f, 6.93147180559945309e-01);                              // ln2
+#elif LCF_E2T_BITS >= 10
     double p = 5.55041086648215800e-02;                                  // ln2^3/6  (|f| <= 2^-11: truncation f^4 ln2^4/24 = 5e-16)
     p = fma(p, f, 2.40226506959100712e-01);                              // ln2^2/2
     p = fma(p, f, 6.93147180559945309e-01);                              // ln2
@@ -1056,7 +1060,7 @@ template <typename R> struct SmemLayout : SmemOffsets {
     __host__ __device__ SmemLayout(int nsamples, int nfilters, int wpb, int nwarps, int ndim, bool tab, int nspl, int ncluster = kMaxCluster, int nq = 1) {
         size_t o = 0;
         auto at = [&](size_t bytes, bool align) { const unsigned int here = (unsigned int)o; o += bytes; if (align) o = (o + 15) & ~(size_t)15; return here; };
-        off_e2t = at(sizeof(R) == 8 ? (size_t)kE2TabSize * sizeof(double) : 0, false);   // 2^(j/1024), FP64 loop
+        off_e2t = at(sizeof(R) == 8 ? (size_t)kE2TabSize * sizeof(double) : 0, false);   // 2^(j/4096), FP64 loop
         off_bank = at((size_t)nsamples * 2 * sizeof(R), true);
         off_spl = at((size_t)nspl * 4 * sizeof(R), true);                                 // SiFTO cubic coefficients
         off_tab = at(tab ? (size_t)nsamples * (wpb < 32 ? wpb : 32) * sizeof(R) : 0, true);   // R2[nsamples/2][min(wpb, 32)]
@@ -1464,7 +1468,16 @@ template <int MODEL, typename R, int WL, bool PLAIN, int PPL = 2>
 __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const ProblemDev P, const TileDev TL, const MoveDev Mv) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int wpb = 1 << (WL >= 0 ? WL : Mv.wpb_log2);
-    const SmemLayout<R> L(Mv.lay);
+    // carve-up offsets: from the parameter block (constant bank), except in the ShockCooling4 32-walker kernels, where recomputing
+    // them measured 1.6 % faster (ShockCooling3: reading them is 4.5 % faster; profiles/round2_kernel_variants.jsonl x8)
+#ifndef LCF_X_LAYOUT_INKERNEL
+    constexpr bool lay_in_kernel = MODEL == 4 && WL == 5 && sizeof(R) == 4;
+#else
+    constexpr bool lay_in_kernel = true;
+#endif
+    const SmemLayout<R> L = lay_in_kernel
+        ? SmemLayout<R>(P.nsamples, P.nfilters, wpb, blockDim.x >> 5, P.ndim, MODEL == 3, (MODEL >= 5 && MODEL <= 7) ? P.nfilters * P.spl_nint : 0, kMaxCluster, Mv.nq)
+        : SmemLayout<R>(Mv.lay);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));

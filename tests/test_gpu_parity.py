@@ -852,7 +852,8 @@ def test_cfg2_shape_native_moves_on_the_benchmark_kernel(precision):
     s.run_mcmc(p0, 5, skip_initial_state_check=True)
     launch = prob.last_launch()
     assert launch['kernel'] == 'k_pass<32 walkers, plain>' and launch['walkers_per_cta'] == 32 and launch['warps_per_cta'] == 16
-    assert launch['groups'] == (nw // 2 + 31) // 32 and launch['cluster'] == 1 and launch['sum_units'] == 8
+    assert launch['groups'] == (nw // 2 + 31) // 32 and launch['cluster'] == 1
+    assert launch['sum_units'] == (8 if precision == 'fp64' else 1) and launch['points_per_lane'] == (4 if precision == 'fp32' else 2)
     if launch['flat']:                                           # one CTA per co-resident slot, each with the same share of the work
         assert launch['grid'] % _sm_count() == 0 and launch['grid'] < launch['groups']
     else:
