@@ -1364,6 +1364,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     int rc = choose_shape(p, std::max(e->n0, e->n1), &sh);
     if (rc) return rc;
     if (sh.flat > 0) return 0;                                               // a flat split is a large ensemble by construction
+    if (points_per_lane(p, sh.l, !p->dev.use_sigma) != 2) return 0;          // k_ring runs the two-points-per-lane code: same arithmetic as the launches it replaces
     if (!(env && env[0] == '1') && sh.cost > 120000.) return 0;             // > ~60 us per half-step: launch latency is already hidden
     const bool f32 = p->precision == LCF_PRECISION_FP32;
     RingKernel k = f32 ? ring_kernel_for<float>(p->dev.model) : ring_kernel_for<double>(p->dev.model);
