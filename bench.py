@@ -285,7 +285,7 @@ def roofline_block(ctx, model, precision, samples_per_eval, value_per_gpu, ms, h
     fp64 = precision == 'fp64'
     samples_per_s = value_per_gpu * samples_per_eval
     peak = (FP64_LANES_PER_CLK_SM / FP64_OPS_PER_SAMPLE if fp64 else MUFU_LANES_PER_CLK_SM) * SMS * sm_mhz * 1e6
-    kernel = 'lcf::k_pass<%d,%s,5,true>' % (3 if model == 'sc3' else 4, 'double' if fp64 else 'float')
+    kernel = 'lcf::k_pass<%d,%s,5,true,%d>' % (3 if model == 'sc3' else 4, 'double' if fp64 else 'float', 4 if (model == 'sc3' and not fp64) else 2)
     tr = ctx.traffic.get('%s@cfg2' % kernel) if walkers == WALKERS_PER_GPU else None
     return {
         'bound': ('fp64 pipe (no dense contraction, ~72 B of HBM per walker-step)' if fp64 else
