@@ -179,9 +179,11 @@ struct lcf_ensemble {
     double *d_split_part = nullptr;             // flat split: unit sums of walker groups shared by several CTAs, [kSplitUnits][W + 32]
     unsigned int *d_split_tick = nullptr;       // [W + 1] arrival counters (zero between launches)
     int ring_ok = -1, ring_key = -1;            // -1 unknown, 0 the grid does not fit, 1 usable (cached per launch shape)
+    int ring_spec = 0;                          // the cached decision covers the look-ahead grid (n0 + 2 n1 virtual walkers)
+    double *d_spec = nullptr;                   // look-ahead rounds of k_ring: xbuf, sq, snlp, smeta (double-buffered) + a NaN counter
     ~lcf_ensemble() {
         for (void *m : ipc_opened) cudaIpcCloseMemHandle(m);
-        cudaFree(d_flags); cudaFree(d_ring_bar); cudaFree(d_split_part); cudaFree(d_split_tick);
+        cudaFree(d_flags); cudaFree(d_ring_bar); cudaFree(d_split_part); cudaFree(d_split_tick); cudaFree(d_spec);
         cudaFree(d_stage); cudaFree(d_stage_flag);
         cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_acc); cudaFree(d_nan); cudaFree(d_chain); cudaFree(d_lnp);
         if (ev0) cudaEventDestroy(ev0);
@@ -1353,7 +1355,8 @@ int lcf_ensemble_end_step(lcf_ensemble *e, int store) {
 
 // Small ensembles: the whole run as ONE cooperative launch of the persistent kernel k_ring (device-side barrier between half-steps)
 // instead of two k_pass launches per step.  Used when the grid of the chosen launch shape is co-resident and a half-step is short
-// enough to be launch-bound (cost model of choose_shape); LCF_RING=0 / 1 forces it off / on (when it fits).
+// enough to be launch-bound (cost model of choose_shape); LCF_RING=0 forces it off, 1 / 2 on (when it fits): 1 with one half-step per
+// grid barrier, 2 with look-ahead rounds (the default whenever their larger grid is co-resident and leaves every SM at most two CTAs).
 static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     *used = false;
     lcf_problem *p = e->p;
@@ -1365,12 +1368,20 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     if (rc) return rc;
     if (sh.flat > 0) return 0;                                               // a flat split is a large ensemble by construction
     if (points_per_lane(p, sh.l, !p->dev.use_sigma) != 2) return 0;          // k_ring runs the two-points-per-lane code: same arithmetic as the launches it replaces
-    if (!(env && env[0] == '1') && sh.cost > 120000.) return 0;             // > ~60 us per half-step: launch latency is already hidden
+    if (!(env && (env[0] == '1' || env[0] == '2')) && sh.cost > 120000.) return 0;   // > ~60 us per half-step: launch latency is already hidden
     const bool f32 = p->precision == LCF_PRECISION_FP32;
     RingKernel k = f32 ? ring_kernel_for<float>(p->dev.model) : ring_kernel_for<double>(p->dev.model);
     if (!k) return 0;
     if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), sh.smem))) return rc;
-    const long long ngroups = (std::max(e->n0, e->n1) + (1 << sh.l) - 1) >> sh.l;
+    // Look-ahead rounds (k_ring, spec_prephase): a whole step per grid barrier, for n0 + 2 n1 virtual walkers.  Worth 1.5x the
+    // arithmetic only while the device is latency-bound, i.e. while the larger grid still leaves every SM at most two CTAs.
+    // LCF_RING=1 keeps one half-step per barrier, LCF_RING=2 asks for the look-ahead whenever its grid is co-resident.
+    const long long NV = e->n0 + 2 * e->n1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const long long ngroups_spec = (NV + (1 << sh.l) - 1) >> sh.l;
+    bool spec = e->n1 > 0 && !(env && env[0] == '1') && ((env && env[0] == '2') || ngroups_spec * sh.cluster <= 2LL * sms);
+    long long ngroups = spec ? ngroups_spec : (std::max(e->n0, e->n1) + (1 << sh.l) - 1) >> sh.l;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(ngroups * sh.cluster), 1, 1);
@@ -1391,7 +1402,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const int ring_key = ((sh.l * 64 + sh.nw) * 16 + sh.cluster) * 8 + sh.ks;
+    const int ring_key = (((sh.l * 64 + sh.nw) * 16 + sh.cluster) * 8 + sh.ks) * 4 + (env ? (env[0] & 3) : 0);
     if (e->ring_ok < 0 || e->ring_key != ring_key) {            // does the whole grid fit on the device at once?
         e->ring_key = ring_key;
         long long capacity = 0;
@@ -1400,17 +1411,27 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
             if (cudaOccupancyMaxActiveClusters(&ncl, k, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
             capacity = (long long)ncl * sh.cluster;
         } else {
-            int nb = 0, sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+            int nb = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, sh.nw * 32, sh.smem) != cudaSuccess) { cudaGetLastError(); nb = 0; }
             capacity = (long long)nb * sms;
         }
+        if (spec && ngroups * sh.cluster > capacity) {          // the look-ahead grid does not fit: one half-step per barrier
+            spec = false;
+            ngroups = (std::max(e->n0, e->n1) + (1 << sh.l) - 1) >> sh.l;
+        }
+        e->ring_spec = spec ? 1 : 0;
         e->ring_ok = (ngroups * sh.cluster <= capacity) ? 1 : 0;
         if (getenv("LCF_DEBUG_SHAPE"))
-            fprintf(stderr, "[lcf] persistent chain kernel: grid %lld CTAs, co-resident capacity %lld -> %s\n", ngroups * sh.cluster, capacity,
-                    e->ring_ok ? "used" : "not used");
+            fprintf(stderr, "[lcf] persistent chain kernel%s: grid %lld CTAs, co-resident capacity %lld -> %s\n", spec ? " (look-ahead rounds)" : "",
+                    ngroups * sh.cluster, capacity, e->ring_ok ? "used" : "not used");
+    } else if (spec != (e->ring_spec != 0)) {
+        spec = e->ring_spec != 0;
+        ngroups = spec ? ngroups_spec : (std::max(e->n0, e->n1) + (1 << sh.l) - 1) >> sh.l;
     }
     if (!e->ring_ok) return 0;
+    cfg.gridDim = dim3((unsigned)(ngroups * sh.cluster), 1, 1);
+    const size_t nx = 2 * (size_t)e->W * (e->D + 1), nq = 2 * (size_t)NV * e->D, nl = 2 * (size_t)NV, nm = 4 * (size_t)e->W;
+    if (spec && !e->d_spec) CUDA_TRY(cudaMalloc(&e->d_spec, (nx + nq + nl + nm + 2) * sizeof(double)));
     if (!e->d_ring_bar) CUDA_TRY(cudaMalloc(&e->d_ring_bar, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(e->d_ring_bar, 0, 2 * sizeof(unsigned int), e->stream));
     TileDev tiles;
@@ -1427,9 +1448,14 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     G.wpb_log2 = sh.l;
     G.ks = sh.ks;
     G.nq = sh.nq;
+    G.spec = spec ? 1 : 0;
+    if (spec) {
+        G.xbuf = e->d_spec; G.sq = G.xbuf + nx; G.snlp = G.sq + nq; G.smeta = G.snlp + nl;
+        G.nan_scratch = reinterpret_cast<int *>(G.smeta + nm);
+    }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, G));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
-    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = 3; p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups; p->last_launch.ppl = 2;
+    p->last_launch.grid = ngroups * sh.cluster; p->last_launch.variant = spec ? 4 : 3; p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups; p->last_launch.ppl = 2;
     e->last_launches += 1;
     e->iteration += nsteps;
     if (store) e->nstored += nsteps;

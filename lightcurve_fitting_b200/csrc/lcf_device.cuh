@@ -209,6 +209,22 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// The draws of one stretch move (emcee's StretchMove with a = 2): z = ((a - 1) u + 1)^2 / a, the partner's index in the complementary
+// half-ensemble of Nc walkers, and the uniform number of the accept test; keyed by (seed, 2 iteration + half, logical walker).
+__device__ __forceinline__ void stretch_draw(unsigned long long seed, unsigned int ctr, long long j, long long Nc, double &z, long long &pr, double &uacc) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)j, ctr, (uint32_t)(j >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    double u = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
+    double a = u + 1.;                   // ((a-1) u + 1)^2 / a with a = 2
+    z = a * a * 0.5;
+    pr = (long long)(((unsigned long long)r[2] * (unsigned long long)Nc) >> 32);
+    uacc = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);
+}
+// accept test of the stretch move: (D - 1) ln z + ln p' - ln p > ln u
+__device__ __forceinline__ bool accept_test(int D, double lnz, double nlp, double old, double logu) {
+    const double lnpdiff = (double)(D - 1) * lnz + nlp - old;
+    return lnpdiff > logu;
+}
 
 // ---------------------------------------------------------------------------------------
 // Lean FP64 pow for the per-walker model constants.  libm's pow is a ~300-instruction dependent chain (it carries
@@ -791,9 +807,66 @@ __device__ __forceinline__ R sifto_eval(const ProblemDev &P, const typename Vec4
 // exponential of the front end: FP32 builds with LCF_FE_POLY keep it off the XU pipe (arguments clamped to the polynomial's range:
 // 2^-126 stands for an underflow to zero, 2^126 for an overflow whose only use is exp(-huge)); a NaN argument must be
 // handled by the caller (the polynomial does not propagate it)
-template <typename R> __device__ __forceinline__ R fe_ex2(R x) { return Mth<R>::ex2(x); }
+// FP64 builds: libm's exp2 / log2 are ~40- and ~60-instruction dependent chains with fix-up branches, and four to six of them per
+// (walker, point) were a third of the FP64 kernel's warp time (ncu source page, profiles/round2_ncu_fp64.txt: 32 % of the samples in the
+// 537 instructions of the per-tile code).  The front end therefore uses the inner loop's own 2^x (the shared-memory table 2^(j/4096) and a
+// degree-2 polynomial, truncation 1.0e-13: 7 FP64 operations) and a lean log2 (atanh series on the mantissa, truncation 1e-15, its
+// division by MUFU.RCP64H + two Newton steps); anything unusual (|x| >= 1000 or NaN; a non-positive, subnormal or non-finite argument
+// of the logarithm) still goes to libm, so the special values are libm's.  LCF_FE_LIBM = 1 restores the libm calls.
+#ifndef LCF_FE_LIBM
+#define LCF_FE_LIBM 0
+#endif
+__device__ __forceinline__ double ex2_tab_f64(double x, const double *__restrict__ e2t) {   // |x| < 1000
+    // (explicit roundings: x is usually a product, and whether the compiler contracts it into these two additions depended on the
+    //  kernel the front end was inlined into -- k_ring and k_pass then differed in the last bit of a log-posterior)
+    const double magic = 6755399441055744.0 / (double)kE2TabSize;
+    const double r = __dadd_rn(x, magic);
+    const int k = __double2loint(r);                                     // 2^bits n + j (two's complement: j >= 0 for either sign of x)
+    const double f = __dsub_rn(x, __dsub_rn(r, magic));
+#if LCF_E2T_BITS >= 12
+    double p = 2.40226506959100712e-01;
+    p = fma(p, f, 6.93147180559945309e-01);
+#else
+    double p = 9.61812910762847716e-03;
+    p = fma(p, f, 5.55041086648215800e-02);
+    p = fma(p, f, 2.40226506959100712e-01);
+    p = fma(p, f, 6.93147180559945309e-01);
+#endif
+    const double t = e2t[k & (kE2TabSize - 1)];
+    p = fma(t * f, p, t);
+    return __hiloint2double(__double2hiint(p) + ((k >> kE2TabBits) << 20), __double2loint(p));
+}
+__device__ __forceinline__ double log2_lean(double x) {                  // x positive, finite, normal
+    const int hi = __double2hiint(x);
+    const bool up = (hi & 0x000fffff) > 0x0006a09e;                      // mantissa above sqrt 2 (to 2^-20: the series only needs |s| small)
+    const int e = (hi >> 20) - 1023 + (up ? 1 : 0);
+    const double m = __hiloint2double((hi & 0x000fffff) | (up ? 0x3fe00000 : 0x3ff00000), __double2loint(x));   // [0.7071, 1.4143)
+    const double s = (m - 1.0) * rcp_f64(m + 1.0), s2 = s * s;            // |s| <= 0.1716
+    double p = 1. / 19.;
+    p = fma(p, s2, 1. / 17.);
+    p = fma(p, s2, 1. / 15.);
+    p = fma(p, s2, 1. / 13.);
+    p = fma(p, s2, 1. / 11.);
+    p = fma(p, s2, 1. / 9.);
+    p = fma(p, s2, 1. / 7.);
+    p = fma(p, s2, 1. / 5.);
+    p = fma(p, s2, 1. / 3.);
+    p = fma(p, s2, 1.);
+    return fma(2.8853900817779268 * s, p, (double)e);                   // e + (2 / ln 2) atanh(s)
+}
+template <typename R> __device__ __forceinline__ R fe_ex2(R x, const double *) { return Mth<R>::ex2(x); }
+template <typename R> __device__ __forceinline__ R fe_lg2(R x) { return Mth<R>::lg2(x); }
+#if !LCF_FE_LIBM
+template <> __device__ __forceinline__ double fe_ex2<double>(double x, const double *e2t) {
+    return (fabs(x) < 1000.) ? ex2_tab_f64(x, e2t) : exp2(x);
+}
+template <> __device__ __forceinline__ double fe_lg2<double>(double x) {
+    const int hi = __double2hiint(x);
+    return (hi >= 0x00100000 && hi < 0x7ff00000) ? log2_lean(x) : log2(x);
+}
+#endif
 #if LCF_FE_POLY
-template <> __device__ __forceinline__ float fe_ex2<float>(float x) { return ex2_fma(fminf(fmaxf(x, -126.f), 126.f)); }
+template <> __device__ __forceinline__ float fe_ex2<float>(float x, const double *) { return ex2_fma(fminf(fmaxf(x, -126.f), 126.f)); }
 #endif
 
 // Front end of one (walker, point): the model value is
@@ -809,7 +882,7 @@ template <> __device__ __forceinline__ float fe_ex2<float>(float x) { return ex2
 //   SED: wc0 = 1/T, wc1 = R^2
 template <int MODEL, typename R>
 __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<R> &w, int p, R &inv, R &amp, R &add,
-                                          const typename Vec4<R>::type *__restrict__ s_spl) {
+                                          const typename Vec4<R>::type *__restrict__ s_spl, const double *__restrict__ e2t) {
     typedef Mth<R> M;
     add = (R)0;
     if (MODEL == 8) {
@@ -823,14 +896,14 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
 #ifdef LCF_X_FE_STUB   // experiment: what the kernel costs without the front-end transcendentals (results are wrong)
     inv = w.wc[4] * (R)0.5 * (dt > (R)3 ? (R)1.1 : (R)1); amp = w.wc[5]; return;
 #endif
-    const R lt = M::lg2(pos ? dt : (R)1);
+    const R lt = fe_lg2<R>(pos ? dt : (R)1);
     R i, a;
     if (MODEL >= 1 && MODEL <= 3) {
         // 4 transcendentals: lg2(t), (a t/t_tr)^alpha, L/T^4, 1/T
         const R epsT = kconst<R>(P, 0), epsA = kconst<R>(P, 1), alpha = kconst<R>(P, 2);
-        const R pw_ = (w.wc[2] > -M::inf()) ? fe_ex2<R>(alpha * (lt + w.wc[2])) : (R)0;
-        a = w.wc[5] * fe_ex2<R>(epsA * lt - (R)kLog2e * pw_);
-        i = w.wc[4] * fe_ex2<R>(-epsT * lt);
+        const R pw_ = (w.wc[2] > -M::inf()) ? fe_ex2<R>(alpha * (lt + w.wc[2]), e2t) : (R)0;
+        a = w.wc[5] * fe_ex2<R>(epsA * lt - (R)kLog2e * pw_, e2t);
+        i = w.wc[4] * fe_ex2<R>(-epsT * lt, e2t);
         if (!(w.wc[4] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : w.wc[1] * (R)0; }   // T <= 0
         if (w.wc[1] < (R)0) { i = (R)0; a = M::nan(); }                       // L < 0: L ** 0.5 is NaN (models.py:268)
         if (!pos) { i = (R)0; a = (w.wc[0] * w.wc[1]) * (R)0; }                // t <= t_exp: zero (NaN constants propagate)
@@ -838,11 +911,11 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
         // 6 transcendentals: lg2(t), suppression (2), two powers of ttilde for L, one for 1/T (branch selected)
         const R A = kconst<R>(P, 0), alpha = kconst<R>(P, 1);
         const R ltt = lt + w.wc[2];                              // log2(ttilde); NaN when t_br is invalid
-        const R sup = (w.wc[3] > -M::inf()) ? fe_ex2<R>((R)(-kLog2e) * fe_ex2<R>(alpha * (lt + w.wc[3]))) : (R)1;
-        const R L = w.wc[1] * (fe_ex2<R>((R)(-4. / 3.) * ltt) + A * sup * fe_ex2<R>((R)(-0.17) * ltt));
+        const R sup = (w.wc[3] > -M::inf()) ? fe_ex2<R>((R)(-kLog2e) * fe_ex2<R>(alpha * (lt + w.wc[3]), e2t), e2t) : (R)1;
+        const R L = w.wc[1] * (fe_ex2<R>((R)(-4. / 3.) * ltt, e2t) + A * sup * fe_ex2<R>((R)(-0.17) * ltt, e2t));
         // T = T_br min(0.97 u^-1/3, u^-0.45): the first branch is the smaller one for log2(u) < -log2(0.97)/(0.45-1/3)
         const bool early = ltt < (R)0.37665701296944757;
-        i = (early ? w.wc[4] : w.wc[5]) * fe_ex2<R>((early ? (R)(1. / 3.) : (R)0.45) * ltt);
+        i = (early ? w.wc[4] : w.wc[5]) * fe_ex2<R>((early ? (R)(1. / 3.) : (R)0.45) * ltt, e2t);
         if (LCF_FE_POLY && sizeof(R) == 4) i = (w.wc[2] != w.wc[2]) ? M::nan() : i;   // invalid t_br: the polynomial does not propagate the NaN
         const R i2 = i * i;
         a = L * (i2 * i2);
@@ -851,8 +924,8 @@ __device__ __forceinline__ void front_end(const ProblemDev &P, const LaneWalker<
         if (!pos) { a = (w.wc[0] * w.wc[1]) * (R)0; i = (R)0; }
     } else {
         // Kasen, models.py:752-754: 3 transcendentals, then the SiFTO template and the per-filter factors
-        i = w.wc[8] * fe_ex2<R>((R)(74. / 144.) * lt);
-        a = w.wc[1] * fe_ex2<R>((R)(14. / 9.) * lt);               // = R^2 here
+        i = w.wc[8] * fe_ex2<R>((R)(74. / 144.) * lt, e2t);
+        a = w.wc[1] * fe_ex2<R>((R)(14. / 9.) * lt, e2t);               // = R^2 here
         if (!(w.wc[8] > (R)0)) { i = (R)0; a = (w.wc[0] != w.wc[0]) ? M::nan() : (R)0; }
         if (!pos) { i = (R)0; a = (R)0; }
         const int f = P.pfilt[p];
@@ -1151,13 +1224,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                     z = Mv.zin[i];
                     pr = Mv.rin[i];
                 } else {
-                    uint32_t r[4];
-                    philox4x32_10((uint32_t)j, Mv.ctr, (uint32_t)(j >> 32), 0u, (uint32_t)Mv.seed, (uint32_t)(Mv.seed >> 32), r);
-                    double u = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0);
-                    double a = u + 1.;                   // ((a-1) u + 1)^2 / a with a = 2
-                    z = a * a * 0.5;
-                    pr = (long long)(((unsigned long long)r[2] * (unsigned long long)Mv.Nc) >> 32);
-                    s_term[tid * kTermStride + NT + kMaxDim + 1] = ((double)r[3] + 0.5) * (1.0 / 4294967296.0);   // u of the accept test
+                    double ua;
+                    stretch_draw(Mv.seed, Mv.ctr, j, Mv.Nc, z, pr, ua);
+                    s_term[tid * kTermStride + NT + kMaxDim + 1] = ua;   // u of the accept test
                 }
                 const long long crow = Mv.comp_rows ? (long long)Mv.comp_rows[pr] : Mv.comp_base + pr;
                 const double *s = Mv.coords + row * D, *c = Mv.coords + crow * D;
@@ -1168,7 +1237,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             } else {
                 const int nq = (Mv.mode == MODE_MODEL) ? P.nmodel : D;
                 const long long qs = Mv.qstride ? Mv.qstride : nq;
-                for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * qs + d];
+                if (Mv.qin) { for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * qs + d]; }
+                else { for (int d = 0; d < nq; ++d) q[d] = s_q[tid * D + d]; }      // k_ring look-ahead rounds: written by spec_apply
                 for (int d = nq; d < D; ++d) q[d] = 0.;
             }
             for (int d = 0; d < D; ++d) s_q[tid * D + d] = q[d];
@@ -1234,8 +1304,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             const R ebv = s_wc[wl * kNumWC + 3];
             const R4 rec = s_bank[kp];
             R2 v;
-            v.x = rec.z * Mth<R>::ex2(-ebv * kap[2 * kp]);
-            v.y = rec.w * Mth<R>::ex2(-ebv * kap[2 * kp + 1]);
+            v.x = rec.z * fe_ex2<R>(-ebv * kap[2 * kp], s_e2t);
+            v.y = rec.w * fe_ex2<R>(-ebv * kap[2 * kp + 1], s_e2t);
             s_tab[kp * tstride + wl] = v;
         }
         __syncthreads();
@@ -1288,7 +1358,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                     const float4 o = pobs4[pk];
                     ob[k] = make_float2(o.x, o.y);
                     float addk;
-                    front_end<MODEL, float>(P, lwf, pk, f[k].invT, f[k].amp, addk, reinterpret_cast<const float4 *>(s_spl));
+                    front_end<MODEL, float>(P, lwf, pk, f[k].invT, f[k].amp, addk, reinterpret_cast<const float4 *>(s_spl), nullptr);
                     n[k] = k < tl.y && f[k].invT > 0.f;
                 }
                 float S[4];
@@ -1313,8 +1383,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             const int4 fi = s_finfo[tl.z];
             PointFE<R> fa, fb;
             R adda, addb;
-            front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda, s_spl);      // branch-free: the two MUFU chains interleave
-            front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb, s_spl);
+            front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda, s_spl, s_e2t);      // branch-free: the two MUFU chains interleave
+            front_end<MODEL, R>(P, lw, pb, fb.invT, fb.amp, addb, s_spl, s_e2t);
             fa.state = fa.invT > (R)0 ? 1 : 0;
             fb.state = fb.invT > (R)0 ? 1 : 0;
             const bool na = fa.state == 1, nb = two && fb.state == 1;
@@ -1435,8 +1505,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                 const double logu = Mv.luin ? Mv.luin[i] : s_term[tid * kTermStride + NT + kMaxDim + 1];
                 if (nlp != nlp) atomicAdd(Mv.nanflag, 1);           // emcee: "Probability function returned NaN"
                 const double old = s_old[tid];
-                const double lnpdiff = (double)(D - 1) * s_term[tid * kTermStride + NT + kMaxDim] + nlp - old;
-                const bool acc = lnpdiff > logu;
+                const bool acc = accept_test(D, s_term[tid * kTermStride + NT + kMaxDim], nlp, old, logu);
                 double *crd = Mv.coords + row * D;
                 if (acc) {
                     for (int d = 0; d < D; ++d) crd[d] = s_q[tid * D + d];
@@ -1623,6 +1692,13 @@ struct RingDev {
     unsigned int *bar;                 // [2]: arrival counter, generation (zeroed before the launch)
     int wpb_log2, ks;
     int nq;                            // units of the structured chi-square sums (same value as the k_pass launches of this shape)
+    // look-ahead rounds (spec != 0, see spec_prephase): double-buffered by round parity
+    int spec;
+    double *xbuf;                      // [2][W][D + 1]  positions and log-probabilities at the start of the round
+    double *sq;                        // [2][NV][D]     proposals of the NV = n0 + 2 n1 virtual walkers of the round
+    double *snlp;                      // [2][NV]        their log-posteriors
+    double *smeta;                     // [2][W][2]      ln z and ln u of the walker's move of the round
+    int *nan_scratch;                  // NaN counter of the evaluation passes (only SELECTED evaluations count, see spec_state)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -1633,21 +1709,191 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
 __device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// every CTA of the (co-resident) grid has finished its part of the half-step and its global writes are visible
-__device__ __forceinline__ void ring_barrier(unsigned int *bar, unsigned int &gen) {
+// Grid barrier of the persistent kernel, split in two so that data-independent work of the next round can run in its shadow:
+// every CTA adds one to a monotonic counter (red.release.gpu: its global writes are visible to whoever acquires the count) and
+// round `gen` is complete when the counter reaches gen * gridDim.x -- no reset, no "last arriver" hop (an atomic's round trip,
+// then a flag store, then the pollers' next load), one L2 word polled by one thread per CTA.
+__device__ __forceinline__ void ring_arrive(unsigned int *bar, unsigned int &gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
         gen += 1u;
-        __threadfence();
-        const unsigned int prev = atomicAdd(bar, 1u);
-        if (prev == gridDim.x - 1u) {
-            bar[0] = 0u;                                   // nobody arrives again before seeing the new generation
-            st_release_gpu(bar + 1, gen);
-        } else {
-            while (ld_acquire_gpu(bar + 1) != gen) { }
-        }
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    }
+}
+__device__ __forceinline__ void ring_wait(const unsigned int *bar, unsigned int gen) {
+    if (threadIdx.x == 0) {
+        const unsigned int target = gen * gridDim.x;
+        while ((int)(ld_acquire_gpu(bar) - target) < 0) { }
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Look-ahead rounds: one grid barrier per STEP instead of one per half-step.
+// A half-step of a 100-walker ensemble is a ~10 us dependent chain (partner's position -> proposal -> FP64 constants -> tiles ->
+// accept -> barrier) on a GPU that is 99 % idle, and the second half-step of a step can only start when the first has finished,
+// because its proposals use the UPDATED positions of the first colour.  But an updated position is one of exactly two values known
+// from the start of the step: the walker's old position, or its proposal.  So a round evaluates, concurrently,
+//     n0 proposals of the first colour                       (virtual walkers [0, n0)), and
+//     2 n1 proposals of the second colour: for BOTH outcomes of the partner's move   ([n0, n0 + n1): rejected, [n0 + n1, NV): accepted),
+// stores proposals and log-posteriors, and passes ONE barrier.  Nothing else is written: at the start of the next round every CTA
+// derives the positions it needs from the previous round's records (spec_state: a first-colour walker moved iff its accept test
+// passed; a second-colour walker selects the evaluation that matches its partner's outcome, then takes its own test).  The owner of a
+// walker (its first virtual walker) also materialises the state into xbuf, the chain row of the finished step, the acceptance count and
+// the NaN flag.  1.5x the arithmetic of the plain scheme for half its serial chain; same draws, same proposals (bit for bit), same
+// evaluation code (group_pass in MODE_LOGPOST on the same launch shape), same accept expression: the chain is bit-identical.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool spec_acc_first(const RingDev &G, int pb, long long a, int D, long long NV) {   // did first-colour row a move in the previous round?
+    const double nlp = __ldcg(G.snlp + pb * NV + a);
+    const double *m = G.smeta + ((long long)pb * G.W + a) * 2;
+    const double old = __ldcg(G.xbuf + ((long long)pb * G.W + a) * (D + 1) + D);
+    return accept_test(D, __ldcg(m), nlp, old, __ldcg(m + 1));
+}
+// position c[D] and log-probability lp of physical row `row` at the start of round rd; acc / isnan: its move of round rd - 1
+__device__ __forceinline__ long long spec_prev_partner(const RingDev &G, long long rd, long long row) {   // first-colour row that second-colour `row` moved against in round rd - 1
+    if (rd <= 0 || row < G.n0) return -1;
+    double z, u;
+    long long pr;
+    stretch_draw(G.seed, (unsigned int)(2 * (G.iter0 + rd - 1) + 1), 2 * (row - G.n0) + 1, G.n0, z, pr, u);
+    return pr;
+}
+__device__ __forceinline__ void spec_state(const RingDev &G, long long rd, long long row, long long prev_partner, int D, long long NV, double *c, double &lp, bool &acc, bool &isnan) {
+    acc = false; isnan = false;
+    if (rd == 0) {
+        for (int d = 0; d < D; ++d) c[d] = __ldcg(G.coords + row * D + d);
+        lp = __ldcg(G.logp + row);
+        return;
+    }
+    const int pb = (int)((rd - 1) & 1);
+    const long long n1 = G.W - G.n0;
+    const double *m = G.smeta + ((long long)pb * G.W + row) * 2;
+    const double *xo = G.xbuf + ((long long)pb * G.W + row) * (D + 1);
+    const double lnz = __ldcg(m), logu = __ldcg(m + 1), old = __ldcg(xo + D);
+    double cold[kMaxDim];
+    for (int d = 0; d < D; ++d) cold[d] = __ldcg(xo + d);
+    if (row < G.n0) {
+        const double nlp = __ldcg(G.snlp + pb * NV + row);
+        const double *q = G.sq + ((long long)pb * NV + row) * D;
+        double cq[kMaxDim];
+        for (int d = 0; d < D; ++d) cq[d] = __ldcg(q + d);
+        acc = accept_test(D, lnz, nlp, old, logu);
+        isnan = nlp != nlp;
+        for (int d = 0; d < D; ++d) c[d] = acc ? cq[d] : cold[d];
+        lp = acc ? nlp : old;
+    } else {
+        // both evaluations of the second-colour walker are fetched before the partner's outcome is known (one L2 round trip)
+        const long long k = row - G.n0, v0 = G.n0 + k, v1 = v0 + n1;
+        const double nlp0 = __ldcg(G.snlp + pb * NV + v0), nlp1 = __ldcg(G.snlp + pb * NV + v1);
+        const double *q0 = G.sq + ((long long)pb * NV + v0) * D, *q1 = G.sq + ((long long)pb * NV + v1) * D;
+        double c0[kMaxDim], c1[kMaxDim];
+        for (int d = 0; d < D; ++d) { c0[d] = __ldcg(q0 + d); c1[d] = __ldcg(q1 + d); }
+        const bool sel = spec_acc_first(G, pb, prev_partner, D, NV);
+        const double nlp = sel ? nlp1 : nlp0;
+        acc = accept_test(D, lnz, nlp, old, logu);
+        isnan = nlp != nlp;
+        for (int d = 0; d < D; ++d) c[d] = acc ? (sel ? c1[d] : c0[d]) : cold[d];
+        lp = acc ? nlp : old;
+    }
+}
+// what the owner of `row` records when it derives the row's state at the start of round rd (rd = nsteps: the final state)
+__device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long long row, int D, const double *c, double lp, bool acc, bool isnan) {
+    const long long j = (row < G.n0) ? 2 * row : 2 * (row - G.n0) + 1;
+    if (rd < G.nsteps) {
+        double *xo = G.xbuf + ((long long)(rd & 1) * G.W + row) * (D + 1);
+        for (int d = 0; d < D; ++d) xo[d] = c[d];
+        xo[D] = lp;
+    } else {
+        for (int d = 0; d < D; ++d) G.coords[row * D + d] = c[d];
+        G.logp[row] = lp;
+    }
+    if (rd > 0) {
+        if (isnan) atomicAdd(G.nanflag, 1);                    // emcee: "Probability function returned NaN" (selected evaluations only)
+        if (G.chain) {
+            double *cs = G.chain + ((rd - 1) * G.W + j) * D;
+            for (int d = 0; d < D; ++d) cs[d] = c[d];
+            G.lnp[(rd - 1) * G.W + j] = lp;
+            if (acc) G.accepted[j] += 1ull;
+        }
+    }
+}
+// A virtual walker's round in two parts.  spec_plan: everything that does not depend on the other walkers' outcomes -- the Philox
+// draws of its own move, of its partner's move (second variant) and of the previous-round moves it will have to resolve, and (second
+// warp) ln z, ln u -- computed in the shadow of the grid barrier, kept in registers.  spec_apply (after the barrier): one round trip
+// to L2 for the previous round's records, the selects, the proposal.
+struct SpecPlan {
+    long long v, row, prow, pprow;     // virtual walker, own physical row, partner row, (variant 1) the partner's partner row
+    long long prev_own, prev_part, prev_pp;   // spec_prev_partner of those rows
+    double z, za;                      // stretch factors of the own move and (variant 1) of the partner's move of this round
+    double lnz, lnu;                   // (meta threads)
+    int sel;                           // 0: first colour, or second colour against the partner's OLD position; 1: against its proposal
+    bool main_thread, meta_thread, valid;
+};
+__device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long long g, int wpb, SpecPlan &pl) {
+    const int tid = threadIdx.x;
+    const long long n0 = G.n0, n1 = G.W - n0, NV = n0 + 2 * n1;
+    const unsigned int ctr0 = (unsigned int)(2 * (G.iter0 + rd));
+    const bool two_warps = blockDim.x >= 64;
+    pl.main_thread = tid < wpb;
+    pl.meta_thread = two_warps ? (tid >= 32 && tid < 32 + wpb) : pl.main_thread;
+    pl.valid = false;
+    if (!pl.main_thread && !pl.meta_thread) return;
+    const long long v = g * wpb + (pl.main_thread ? tid : tid - 32);
+    if (v >= NV) return;
+    pl.valid = true;
+    pl.v = v;
+    long long j, Nc, comp_base;
+    unsigned int ctr;
+    pl.sel = 0;
+    if (v < n0) { pl.row = v; j = 2 * v; ctr = ctr0; Nc = n1; comp_base = n0; }
+    else {
+        const long long k = (v - n0) % n1;
+        pl.sel = (int)((v - n0) / n1);
+        pl.row = n0 + k; j = 2 * k + 1; ctr = ctr0 + 1u; Nc = n0; comp_base = 0;
+    }
+    double u;
+    long long pr;
+    stretch_draw(G.seed, ctr, j, Nc, pl.z, pr, u);
+    pl.prow = comp_base + pr;
+    if (pl.meta_thread && pl.sel == 0) { pl.lnz = log(pl.z); pl.lnu = log(u); }
+    if (!pl.main_thread) return;
+    pl.prev_own = spec_prev_partner(G, rd, pl.row);
+    pl.prev_part = spec_prev_partner(G, rd, pl.prow);
+    pl.pprow = -1; pl.prev_pp = -1; pl.za = 0.;
+    if (pl.sel == 1) {                                           // the partner's own move of this round (it moves in the first half)
+        double ua;
+        long long pra;
+        stretch_draw(G.seed, ctr0, 2 * pl.prow, n1, pl.za, pra, ua);
+        pl.pprow = n0 + pra;
+        pl.prev_pp = spec_prev_partner(G, rd, pl.pprow);
+    }
+}
+// s_q: the CTA's proposal rows in shared memory (group_pass reads them there when Mv.qin is NULL)
+__device__ __forceinline__ void spec_apply(const RingDev &G, long long rd, const SpecPlan &pl, int D, int crank, double *s_q) {
+    if (!pl.valid) return;
+    const long long n1 = G.W - G.n0, NV = G.n0 + 2 * n1;
+    const int cb = (int)(rd & 1);
+    if (pl.meta_thread && pl.sel == 0) {
+        double *m = G.smeta + ((long long)cb * G.W + pl.row) * 2;
+        m[0] = pl.lnz;
+        m[1] = pl.lnu;
+    }
+    if (!pl.main_thread) return;
+    double own[kMaxDim], c[kMaxDim], lp, lpp;
+    bool acc, isnan, a2, n2;
+    spec_state(G, rd, pl.row, pl.prev_own, D, NV, own, lp, acc, isnan);
+    if (pl.sel == 0 && crank == 0) spec_commit(G, rd, pl.row, D, own, lp, acc, isnan);
+    spec_state(G, rd, pl.prow, pl.prev_part, D, NV, c, lpp, a2, n2);          // the partner at the start of the round
+    if (pl.sel == 1) {                                                         // ... and after its own move of this round, had it been accepted
+        double cc[kMaxDim];
+        spec_state(G, rd, pl.pprow, pl.prev_pp, D, NV, cc, lpp, a2, n2);
+        for (int d = 0; d < D; ++d) c[d] = __dsub_rn(cc[d], __dmul_rn(__dsub_rn(cc[d], c[d]), pl.za));
+    }
+    double *qo = G.sq + ((long long)cb * NV + pl.v) * D, *qs = s_q + threadIdx.x * D;
+    for (int d = 0; d < D; ++d) {
+        const double q = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], own[d]), pl.z));   // q = c - (c - s) z, numpy op order, no FMA
+        qo[d] = q;
+        qs[d] = q;
+    }
 }
 
 template <int MODEL, typename R>
@@ -1677,25 +1923,66 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     const long long n1 = G.W - G.n0;
     unsigned int gen = 0u;
     bool first = true;
-    for (long long it = 0; it < G.nsteps; ++it) {
-        Mv.accepted = G.chain ? G.accepted : nullptr;      // acceptance counts cover stored steps only (emcee's Backend)
-        Mv.chain_step = G.chain ? G.chain + it * G.W * D : nullptr;
-        Mv.lnp_step = G.chain ? G.lnp + it * G.W : nullptr;
-        for (int half = 0; half < 2; ++half) {
+    // rounds: a half-step each, or (look-ahead) a whole step each; ONE group_pass call site serves both
+    const bool spec = G.spec != 0;
+    const long long NV = G.n0 + 2 * n1, nrounds = spec ? G.nsteps : 2 * G.nsteps;
+    Mv.accepted = nullptr; Mv.chain_step = nullptr; Mv.lnp_step = nullptr;
+    Mv.Ns = 0; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0; Mv.ctr = 0u;
+    SpecPlan plan;
+    plan.valid = false;
+    if (spec && cid < (NV + wpb - 1) / wpb) spec_plan(G, 0, cid, wpb, plan);
+    for (long long rd = 0; rd < nrounds; ++rd) {
+        if (spec) {
+            const int cb = (int)(rd & 1);
+            Mv.mode = MODE_LOGPOST;
+            Mv.Ns = NV;
+            Mv.qin = nullptr;                                  // the proposals are already in shared memory (spec_apply)
+            Mv.out = G.snlp + (long long)cb * NV;
+            Mv.nanflag = G.nan_scratch;
+        } else {
+            const long long it = rd >> 1;
+            const int half = (int)(rd & 1);
+            Mv.accepted = G.chain ? G.accepted : nullptr;      // acceptance counts cover stored steps only (emcee's Backend)
+            Mv.chain_step = G.chain ? G.chain + it * G.W * D : nullptr;
+            Mv.lnp_step = G.chain ? G.lnp + it * G.W : nullptr;
             Mv.ctr = (unsigned int)(2 * (G.iter0 + it) + half);
             Mv.Ns = half ? n1 : G.n0;
             Mv.act_base = half ? G.n0 : 0;
             Mv.Nc = half ? G.n0 : n1;
             Mv.comp_base = half ? 0 : G.n0;
-            const long long ng = (Mv.Ns + wpb - 1) / wpb;
-            for (long long g = cid; g < ng; g += nclusters) { group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize, 0, Mv.nq); first = false; }
+        }
+        const long long ng = (Mv.Ns + wpb - 1) / wpb;
+        for (long long g = cid; g < ng; g += nclusters) {      // (look-ahead: the host launches one cluster per group)
 #ifdef LCF_X_TIMING
-            const long long tb0 = clock64();
+            const long long ta0 = clock64();
 #endif
-            ring_barrier(G.bar, gen);
+            if (spec) spec_apply(G, rd, plan, D, crank, reinterpret_cast<double *>(smem + L.off_q));
 #ifdef LCF_X_TIMING
-            if (threadIdx.x == 0) atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - tb0));
+            if (threadIdx.x == 0) atomicAdd(&g_phase_clk[9], (unsigned long long)(clock64() - ta0));
 #endif
+            group_pass<MODEL, R>(P, TL, Mv, g, smem, L, first, crank, csize, 0, Mv.nq);
+            first = false;
+        }
+#ifdef LCF_X_TIMING
+        const long long tb0 = clock64();
+#endif
+        ring_arrive(G.bar, gen);
+        if (spec && rd + 1 < nrounds && cid < ng) spec_plan(G, rd + 1, cid, wpb, plan);   // in the shadow of the barrier
+        ring_wait(G.bar, gen);
+#ifdef LCF_X_TIMING
+        if (threadIdx.x == 0) atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - tb0));
+#endif
+    }
+    if (spec && crank == 0) {                               // final state, last chain row
+        const long long ng = (NV + wpb - 1) / wpb;
+        for (long long g = cid; g < ng; g += nclusters) {
+            const long long v = g * wpb + threadIdx.x;
+            if ((int)threadIdx.x < wpb && v < G.n0 + n1) {      // the owners: first virtual walker of every row (v = row)
+                double c[kMaxDim], lp;
+                bool acc, isnan;
+                spec_state(G, G.nsteps, v, spec_prev_partner(G, G.nsteps, v), D, NV, c, lp, acc, isnan);
+                spec_commit(G, G.nsteps, v, D, c, lp, acc, isnan);
+            }
         }
     }
 }

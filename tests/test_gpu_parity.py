@@ -1070,8 +1070,9 @@ def test_calculate_bolometric_device_summaries_match_host_post_processing():
 @pytest.mark.parametrize('shape', [(0, 0, 0), (1, 8, 4), (4, 4, 2), (8, 8, 1)])
 def test_persistent_chain_kernel_matches_half_step_launches(shape, monkeypatch):
     """cfg1-sized ensembles (100 walkers) run as ONE cooperative launch of the persistent kernel k_ring, with a device-side
-    barrier between half-steps.  The chain must be bit-identical to the one produced by one k_pass launch per half-step
-    (LCF_RING=0) with the same launch shape, in both precisions, with and without the intrinsic-scatter parameter."""
+    barrier between half-steps (LCF_RING=1) or -- look-ahead rounds, LCF_RING=2 and the default -- one per step.  The chain,
+    the final state and the acceptance counts must be bit-identical to those of one k_pass launch per half-step (LCF_RING=0)
+    with the same launch shape, in both precisions, with and without the intrinsic-scatter parameter."""
     from lightcurve_fitting_b200._capi import lib, check
     from lightcurve_fitting_b200.sampler import EnsembleSampler
     check(lib().lcf_set_tuning_ex(*shape))
@@ -1081,18 +1082,25 @@ def test_persistent_chain_kernel_matches_half_step_launches(shape, monkeypatch):
             prob = wl.device_problem(precision)
             p0 = wl.start(100, np.random.default_rng(5))
             out = {}
-            for ring in ('0', '1'):
+            for ring in ('0', '1', '2'):
                 monkeypatch.setenv('LCF_RING', ring)
                 s = EnsembleSampler(100, wl.ndim, prob, seed=31)
                 s.run_mcmc(p0, 7, store=False)
                 s.run_mcmc(None, 9)
                 s.run_mcmc(None, 4)                                   # a second stored run appends to the chain
-                out[ring] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction, prob.last_launch())
+                st = s.run_mcmc(None, 1)                              # a single round: the final state comes from the drain alone
+                out[ring] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction, prob.last_launch(),
+                             np.array(st.coords), np.array(st.log_prob))
             assert out['1'][3]['kernel'] == 'k_ring' and out['0'][3]['kernel'].startswith('k_pass')
-            assert out['1'][0].shape == (13, 100, wl.ndim)
-            np.testing.assert_array_equal(out['1'][0], out['0'][0])
-            np.testing.assert_array_equal(out['1'][1], out['0'][1])
-            np.testing.assert_array_equal(out['1'][2], out['0'][2])
+            # LCF_RING=2: look-ahead rounds (one grid barrier per step, both outcomes of the partner's move evaluated) whenever the
+            # grid of n0 + 2 n1 = 150 virtual walkers is co-resident; else one half-step per barrier
+            look_ahead = (precision == 'fp32' and shape != (1, 8, 4)) or shape in ((4, 4, 2), (8, 8, 1))
+            assert out['2'][3]['kernel'] == ('k_ring<look-ahead>' if look_ahead else out['2'][3]['kernel'])
+            assert out['2'][3]['kernel'] in ('k_ring', 'k_ring<look-ahead>')
+            assert out['1'][0].shape == (14, 100, wl.ndim)
+            for ring in ('1', '2'):
+                for k in (0, 1, 2, 4, 5):
+                    np.testing.assert_array_equal(out[ring][k], out['0'][k])
         # a large ensemble does not use the persistent kernel (its grid is not co-resident / not launch-bound)
         monkeypatch.delenv('LCF_RING')
         wl = W.synthetic_sc3(npoints=400)
