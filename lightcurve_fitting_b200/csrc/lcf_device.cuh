@@ -1749,7 +1749,6 @@ __device__ __forceinline__ bool spec_acc_first(const RingDev &G, int pb, long lo
     const double old = __ldcg(G.xbuf + ((long long)pb * G.W + a) * (D + 1) + D);
     return accept_test(D, __ldcg(m), nlp, old, __ldcg(m + 1));
 }
-// position c[D] and log-probability lp of physical row `row` at the start of round rd; acc / isnan: its move of round rd - 1
 __device__ __forceinline__ long long spec_prev_partner(const RingDev &G, long long rd, long long row) {   // first-colour row that second-colour `row` moved against in round rd - 1
     if (rd <= 0 || row < G.n0) return -1;
     double z, u;
@@ -1757,143 +1756,147 @@ __device__ __forceinline__ long long spec_prev_partner(const RingDev &G, long lo
     stretch_draw(G.seed, (unsigned int)(2 * (G.iter0 + rd - 1) + 1), 2 * (row - G.n0) + 1, G.n0, z, pr, u);
     return pr;
 }
-__device__ __forceinline__ void spec_state(const RingDev &G, long long rd, long long row, long long prev_partner, int D, long long NV, double *c, double &lp, bool &acc, bool &isnan) {
-    acc = false; isnan = false;
+// Coordinate d and log-probability of physical row `row` at the start of round rd; acc / isnan: its move of round rd - 1.
+// One thread per (walker, coordinate): every load is an independent scalar, so a state costs ONE round trip to L2 (a thread that
+// walked the D coordinates of three candidate positions in loops paid one per element: 6 us of a 16 us round).
+struct SpecElem { double x, lp; bool acc, isnan; };
+__device__ __forceinline__ SpecElem spec_state(const RingDev &G, long long rd, long long row, long long prev_partner, int d, int D, long long NV) {
+    SpecElem e;
+    e.acc = false; e.isnan = false;
     if (rd == 0) {
-        for (int d = 0; d < D; ++d) c[d] = __ldcg(G.coords + row * D + d);
-        lp = __ldcg(G.logp + row);
-        return;
+        e.x = __ldcg(G.coords + row * D + d);
+        e.lp = __ldcg(G.logp + row);
+        return e;
     }
     const int pb = (int)((rd - 1) & 1);
     const long long n1 = G.W - G.n0;
     const double *m = G.smeta + ((long long)pb * G.W + row) * 2;
     const double *xo = G.xbuf + ((long long)pb * G.W + row) * (D + 1);
-    const double lnz = __ldcg(m), logu = __ldcg(m + 1), old = __ldcg(xo + D);
-    double cold[kMaxDim];
-    for (int d = 0; d < D; ++d) cold[d] = __ldcg(xo + d);
+    const double lnz = __ldcg(m), logu = __ldcg(m + 1), old = __ldcg(xo + D), xold = __ldcg(xo + d);
+    double nlp, xq;
     if (row < G.n0) {
-        const double nlp = __ldcg(G.snlp + pb * NV + row);
-        const double *q = G.sq + ((long long)pb * NV + row) * D;
-        double cq[kMaxDim];
-        for (int d = 0; d < D; ++d) cq[d] = __ldcg(q + d);
-        acc = accept_test(D, lnz, nlp, old, logu);
-        isnan = nlp != nlp;
-        for (int d = 0; d < D; ++d) c[d] = acc ? cq[d] : cold[d];
-        lp = acc ? nlp : old;
+        nlp = __ldcg(G.snlp + pb * NV + row);
+        xq = __ldcg(G.sq + ((long long)pb * NV + row) * D + d);
     } else {
-        // both evaluations of the second-colour walker are fetched before the partner's outcome is known (one L2 round trip)
-        const long long k = row - G.n0, v0 = G.n0 + k, v1 = v0 + n1;
+        // both evaluations of the second-colour walker are fetched before the partner's outcome is known
+        const long long v0 = row, v1 = row + n1;
         const double nlp0 = __ldcg(G.snlp + pb * NV + v0), nlp1 = __ldcg(G.snlp + pb * NV + v1);
-        const double *q0 = G.sq + ((long long)pb * NV + v0) * D, *q1 = G.sq + ((long long)pb * NV + v1) * D;
-        double c0[kMaxDim], c1[kMaxDim];
-        for (int d = 0; d < D; ++d) { c0[d] = __ldcg(q0 + d); c1[d] = __ldcg(q1 + d); }
+        const double x0 = __ldcg(G.sq + ((long long)pb * NV + v0) * D + d), x1 = __ldcg(G.sq + ((long long)pb * NV + v1) * D + d);
         const bool sel = spec_acc_first(G, pb, prev_partner, D, NV);
-        const double nlp = sel ? nlp1 : nlp0;
-        acc = accept_test(D, lnz, nlp, old, logu);
-        isnan = nlp != nlp;
-        for (int d = 0; d < D; ++d) c[d] = acc ? (sel ? c1[d] : c0[d]) : cold[d];
-        lp = acc ? nlp : old;
+        nlp = sel ? nlp1 : nlp0;
+        xq = sel ? x1 : x0;
     }
+    e.acc = accept_test(D, lnz, nlp, old, logu);
+    e.isnan = nlp != nlp;
+    e.x = e.acc ? xq : xold;
+    e.lp = e.acc ? nlp : old;
+    return e;
 }
 // what the owner of `row` records when it derives the row's state at the start of round rd (rd = nsteps: the final state)
-__device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long long row, int D, const double *c, double lp, bool acc, bool isnan) {
+__device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long long row, int d, int D, const SpecElem &e) {
     const long long j = (row < G.n0) ? 2 * row : 2 * (row - G.n0) + 1;
     if (rd < G.nsteps) {
         double *xo = G.xbuf + ((long long)(rd & 1) * G.W + row) * (D + 1);
-        for (int d = 0; d < D; ++d) xo[d] = c[d];
-        xo[D] = lp;
+        xo[d] = e.x;
+        if (d == 0) xo[D] = e.lp;
     } else {
-        for (int d = 0; d < D; ++d) G.coords[row * D + d] = c[d];
-        G.logp[row] = lp;
+        G.coords[row * D + d] = e.x;
+        if (d == 0) G.logp[row] = e.lp;
     }
     if (rd > 0) {
-        if (isnan) atomicAdd(G.nanflag, 1);                    // emcee: "Probability function returned NaN" (selected evaluations only)
+        if (d == 0 && e.isnan) atomicAdd(G.nanflag, 1);        // emcee: "Probability function returned NaN" (selected evaluations only)
         if (G.chain) {
-            double *cs = G.chain + ((rd - 1) * G.W + j) * D;
-            for (int d = 0; d < D; ++d) cs[d] = c[d];
-            G.lnp[(rd - 1) * G.W + j] = lp;
-            if (acc) G.accepted[j] += 1ull;
+            G.chain[((rd - 1) * G.W + j) * D + d] = e.x;
+            if (d == 0) {
+                G.lnp[(rd - 1) * G.W + j] = e.lp;
+                if (e.acc) G.accepted[j] += 1ull;
+            }
         }
     }
 }
-// A virtual walker's round in two parts.  spec_plan: everything that does not depend on the other walkers' outcomes -- the Philox
-// draws of its own move, of its partner's move (second variant) and of the previous-round moves it will have to resolve, and (second
-// warp) ln z, ln u -- computed in the shadow of the grid barrier, kept in registers.  spec_apply (after the barrier): one round trip
-// to L2 for the previous round's records, the selects, the proposal.
-struct SpecPlan {
-    long long v, row, prow, pprow;     // virtual walker, own physical row, partner row, (variant 1) the partner's partner row
-    long long prev_own, prev_part, prev_pp;   // spec_prev_partner of those rows
-    double z, za;                      // stretch factors of the own move and (variant 1) of the partner's move of this round
-    double lnz, lnu;                   // (meta threads)
-    int sel;                           // 0: first colour, or second colour against the partner's OLD position; 1: against its proposal
-    bool main_thread, meta_thread, valid;
-};
-__device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long long g, int wpb, SpecPlan &pl) {
-    const int tid = threadIdx.x;
+// A virtual walker's round in two parts.  spec_plan (one thread per virtual walker, a second warp for the logarithms): everything
+// that does not depend on the other walkers' outcomes -- the Philox draws of its own move, of its partner's move (second variant) and
+// of the previous-round moves it will have to resolve, ln z, ln u -- computed in the shadow of the grid barrier and parked in shared
+// memory (the walker's row of the term scratch, free between two passes).  spec_apply (after the barrier, one thread per (virtual
+// walker, coordinate)): one round trip to L2 for the previous round's records, the selects, the proposal.
+constexpr int kSpecDims = 16;            // threads per virtual walker in spec_apply (>= kMaxDim)
+static_assert(kSpecDims >= kMaxDim && kTermStride >= 12, "spec_plan parks 12 words per walker in the term scratch");
+__device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long long g, int wpb, double *s_plan) {
+    // lane = virtual walker of the group, warp = role: the up to five Philox draws of a walker's plan form chains (own draw -> partner
+    // -> the partner's draw -> its partner -> that one's previous move); five warps walk them side by side (depth 3 instead of 5)
+    const int tid = threadIdx.x, w = tid & 31, role = tid >> 5;
+    const int nroles = blockDim.x >= 160 ? 5 : (blockDim.x >= 64 ? 2 : 1);
+    if (w >= wpb || role >= nroles) return;
+    const bool r_main = role == 0, r_meta = role == (nroles >= 2 ? 1 : 0);
+    const bool r_part = role == (nroles == 5 ? 2 : 0), r_own = role == (nroles == 5 ? 3 : 0), r_pp = role == (nroles == 5 ? 4 : 0);
     const long long n0 = G.n0, n1 = G.W - n0, NV = n0 + 2 * n1;
     const unsigned int ctr0 = (unsigned int)(2 * (G.iter0 + rd));
-    const bool two_warps = blockDim.x >= 64;
-    pl.main_thread = tid < wpb;
-    pl.meta_thread = two_warps ? (tid >= 32 && tid < 32 + wpb) : pl.main_thread;
-    pl.valid = false;
-    if (!pl.main_thread && !pl.meta_thread) return;
-    const long long v = g * wpb + (pl.main_thread ? tid : tid - 32);
-    if (v >= NV) return;
-    pl.valid = true;
-    pl.v = v;
-    long long j, Nc, comp_base;
+    double *pd = s_plan + w * kTermStride;
+    long long *pl = reinterpret_cast<long long *>(pd);
+    const long long v = g * wpb + w;
+    if (v >= NV) { if (r_main) pl[0] = -1; return; }
+    long long row, j, Nc, comp_base;
     unsigned int ctr;
-    pl.sel = 0;
-    if (v < n0) { pl.row = v; j = 2 * v; ctr = ctr0; Nc = n1; comp_base = n0; }
+    int sel = 0;
+    if (v < n0) { row = v; j = 2 * v; ctr = ctr0; Nc = n1; comp_base = n0; }
     else {
         const long long k = (v - n0) % n1;
-        pl.sel = (int)((v - n0) / n1);
-        pl.row = n0 + k; j = 2 * k + 1; ctr = ctr0 + 1u; Nc = n0; comp_base = 0;
+        sel = (int)((v - n0) / n1);
+        row = n0 + k; j = 2 * k + 1; ctr = ctr0 + 1u; Nc = n0; comp_base = 0;
     }
-    double u;
+    if (r_own) pl[4] = spec_prev_partner(G, rd, row);
+    if (!(r_main || r_meta || r_part || r_pp)) return;
+    double z, u;
     long long pr;
-    stretch_draw(G.seed, ctr, j, Nc, pl.z, pr, u);
-    pl.prow = comp_base + pr;
-    if (pl.meta_thread && pl.sel == 0) { pl.lnz = log(pl.z); pl.lnu = log(u); }
-    if (!pl.main_thread) return;
-    pl.prev_own = spec_prev_partner(G, rd, pl.row);
-    pl.prev_part = spec_prev_partner(G, rd, pl.prow);
-    pl.pprow = -1; pl.prev_pp = -1; pl.za = 0.;
-    if (pl.sel == 1) {                                           // the partner's own move of this round (it moves in the first half)
-        double ua;
-        long long pra;
-        stretch_draw(G.seed, ctr0, 2 * pl.prow, n1, pl.za, pra, ua);
-        pl.pprow = n0 + pra;
-        pl.prev_pp = spec_prev_partner(G, rd, pl.pprow);
+    stretch_draw(G.seed, ctr, j, Nc, z, pr, u);
+    const long long prow = comp_base + pr;
+    if (r_meta && sel == 0) { pd[10] = log(z); pd[11] = log(u); }
+    if (r_main) { pl[0] = v; pl[1] = row; pl[2] = prow; pl[7] = sel; pd[8] = z; }
+    if (r_part) pl[5] = spec_prev_partner(G, rd, prow);
+    if (r_main || r_pp) {
+        long long pprow = -1;
+        double za = 0.;
+        if (sel == 1) {                                          // the partner's own move of this round (it moves in the first half)
+            double ua;
+            long long pra;
+            stretch_draw(G.seed, ctr0, 2 * prow, n1, za, pra, ua);
+            pprow = n0 + pra;
+        }
+        if (r_main) { pl[3] = pprow; pd[9] = za; }
+        if (r_pp) pl[6] = sel == 1 ? spec_prev_partner(G, rd, pprow) : -1;
     }
 }
-// s_q: the CTA's proposal rows in shared memory (group_pass reads them there when Mv.qin is NULL)
-__device__ __forceinline__ void spec_apply(const RingDev &G, long long rd, const SpecPlan &pl, int D, int crank, double *s_q) {
-    if (!pl.valid) return;
+// s_q: the CTA's proposal rows in shared memory (group_pass reads them there when Mv.qin is NULL); ends with a CTA barrier
+__device__ __forceinline__ void spec_apply(const RingDev &G, long long rd, int wpb, int D, int crank, const double *s_plan, double *s_q) {
     const long long n1 = G.W - G.n0, NV = G.n0 + 2 * n1;
     const int cb = (int)(rd & 1);
-    if (pl.meta_thread && pl.sel == 0) {
-        double *m = G.smeta + ((long long)cb * G.W + pl.row) * 2;
-        m[0] = pl.lnz;
-        m[1] = pl.lnu;
+    for (int t = threadIdx.x; t < wpb * kSpecDims; t += blockDim.x) {
+        const int w = t / kSpecDims, d = t % kSpecDims;
+        const double *pd = s_plan + w * kTermStride;
+        const long long *pl = reinterpret_cast<const long long *>(pd);
+        const long long v = pl[0];
+        if (v < 0 || d >= D) continue;
+        const long long row = pl[1], prow = pl[2];
+        const int sel = (int)pl[7];
+        // (all loads before the first store: the compiler keeps loads behind stores that may alias, and a second round trip to L2
+        //  is 700 clocks of a 24 000-clock round)
+        const SpecElem own = spec_state(G, rd, row, pl[4], d, D, NV);
+        double c = spec_state(G, rd, prow, pl[5], d, D, NV).x;     // the partner at the start of the round
+        if (sel == 1) {                                          // ... and after its own move of this round, had it been accepted
+            const double cc = spec_state(G, rd, pl[3], pl[6], d, D, NV).x;
+            c = __dsub_rn(cc, __dmul_rn(__dsub_rn(cc, c), pd[9]));
+        }
+        const double q = __dsub_rn(c, __dmul_rn(__dsub_rn(c, own.x), pd[8]));   // q = c - (c - s) z, numpy op order, no FMA
+        s_q[w * D + d] = q;
+        G.sq[((long long)cb * NV + v) * D + d] = q;
+        if (d == 0 && sel == 0) {                                // ln z, ln u of this round's move of `row`
+            double *m = G.smeta + ((long long)cb * G.W + row) * 2;
+            m[0] = pd[10];
+            m[1] = pd[11];
+        }
+        if (sel == 0 && crank == 0) spec_commit(G, rd, row, d, D, own);
     }
-    if (!pl.main_thread) return;
-    double own[kMaxDim], c[kMaxDim], lp, lpp;
-    bool acc, isnan, a2, n2;
-    spec_state(G, rd, pl.row, pl.prev_own, D, NV, own, lp, acc, isnan);
-    if (pl.sel == 0 && crank == 0) spec_commit(G, rd, pl.row, D, own, lp, acc, isnan);
-    spec_state(G, rd, pl.prow, pl.prev_part, D, NV, c, lpp, a2, n2);          // the partner at the start of the round
-    if (pl.sel == 1) {                                                         // ... and after its own move of this round, had it been accepted
-        double cc[kMaxDim];
-        spec_state(G, rd, pl.pprow, pl.prev_pp, D, NV, cc, lpp, a2, n2);
-        for (int d = 0; d < D; ++d) c[d] = __dsub_rn(cc[d], __dmul_rn(__dsub_rn(cc[d], c[d]), pl.za));
-    }
-    double *qo = G.sq + ((long long)cb * NV + pl.v) * D, *qs = s_q + threadIdx.x * D;
-    for (int d = 0; d < D; ++d) {
-        const double q = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], own[d]), pl.z));   // q = c - (c - s) z, numpy op order, no FMA
-        qo[d] = q;
-        qs[d] = q;
-    }
+    __syncthreads();
 }
 
 template <int MODEL, typename R>
@@ -1928,9 +1931,9 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     const long long NV = G.n0 + 2 * n1, nrounds = spec ? G.nsteps : 2 * G.nsteps;
     Mv.accepted = nullptr; Mv.chain_step = nullptr; Mv.lnp_step = nullptr;
     Mv.Ns = 0; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0; Mv.ctr = 0u;
-    SpecPlan plan;
-    plan.valid = false;
-    if (spec && cid < (NV + wpb - 1) / wpb) spec_plan(G, 0, cid, wpb, plan);
+    double *s_plan = reinterpret_cast<double *>(smem + L.off_term);       // (the term scratch is free between two passes)
+    if (spec && cid < (NV + wpb - 1) / wpb) spec_plan(G, 0, cid, wpb, s_plan);
+    __syncthreads();
     for (long long rd = 0; rd < nrounds; ++rd) {
         if (spec) {
             const int cb = (int)(rd & 1);
@@ -1956,7 +1959,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
 #ifdef LCF_X_TIMING
             const long long ta0 = clock64();
 #endif
-            if (spec) spec_apply(G, rd, plan, D, crank, reinterpret_cast<double *>(smem + L.off_q));
+            if (spec) spec_apply(G, rd, wpb, D, crank, s_plan, reinterpret_cast<double *>(smem + L.off_q));
 #ifdef LCF_X_TIMING
             if (threadIdx.x == 0) atomicAdd(&g_phase_clk[9], (unsigned long long)(clock64() - ta0));
 #endif
@@ -1967,7 +1970,7 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
         const long long tb0 = clock64();
 #endif
         ring_arrive(G.bar, gen);
-        if (spec && rd + 1 < nrounds && cid < ng) spec_plan(G, rd + 1, cid, wpb, plan);   // in the shadow of the barrier
+        if (spec && rd + 1 < nrounds && cid < ng) spec_plan(G, rd + 1, cid, wpb, s_plan);   // in the shadow of the barrier
         ring_wait(G.bar, gen);
 #ifdef LCF_X_TIMING
         if (threadIdx.x == 0) atomicAdd(&g_phase_clk[8], (unsigned long long)(clock64() - tb0));
@@ -1975,15 +1978,13 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
     }
     if (spec && crank == 0) {                               // final state, last chain row
         const long long ng = (NV + wpb - 1) / wpb;
-        for (long long g = cid; g < ng; g += nclusters) {
-            const long long v = g * wpb + threadIdx.x;
-            if ((int)threadIdx.x < wpb && v < G.n0 + n1) {      // the owners: first virtual walker of every row (v = row)
-                double c[kMaxDim], lp;
-                bool acc, isnan;
-                spec_state(G, G.nsteps, v, spec_prev_partner(G, G.nsteps, v), D, NV, c, lp, acc, isnan);
-                spec_commit(G, G.nsteps, v, D, c, lp, acc, isnan);
+        for (long long g = cid; g < ng; g += nclusters)
+            for (int t = threadIdx.x; t < wpb * kSpecDims; t += blockDim.x) {
+                const long long v = g * wpb + t / kSpecDims;
+                const int d = t % kSpecDims;
+                if (v < G.n0 + n1 && d < D)                         // the owners: first virtual walker of every row (v = row)
+                    spec_commit(G, G.nsteps, v, d, D, spec_state(G, G.nsteps, v, spec_prev_partner(G, G.nsteps, v), d, D, NV));
             }
-        }
     }
 }
 
