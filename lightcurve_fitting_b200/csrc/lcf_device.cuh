@@ -1743,12 +1743,6 @@ __device__ __forceinline__ void ring_wait(const unsigned int *bar, unsigned int 
 // the NaN flag.  1.5x the arithmetic of the plain scheme for half its serial chain; same draws, same proposals (bit for bit), same
 // evaluation code (group_pass in MODE_LOGPOST on the same launch shape), same accept expression: the chain is bit-identical.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool spec_acc_first(const RingDev &G, int pb, long long a, int D, long long NV) {   // did first-colour row a move in the previous round?
-    const double nlp = __ldcg(G.snlp + pb * NV + a);
-    const double *m = G.smeta + ((long long)pb * G.W + a) * 2;
-    const double old = __ldcg(G.xbuf + ((long long)pb * G.W + a) * (D + 1) + D);
-    return accept_test(D, __ldcg(m), nlp, old, __ldcg(m + 1));
-}
 __device__ __forceinline__ long long spec_prev_partner(const RingDev &G, long long rd, long long row) {   // first-colour row that second-colour `row` moved against in round rd - 1
     if (rd <= 0 || row < G.n0) return -1;
     double z, u;
@@ -1760,32 +1754,38 @@ __device__ __forceinline__ long long spec_prev_partner(const RingDev &G, long lo
 // One thread per (walker, coordinate): every load is an independent scalar, so a state costs ONE round trip to L2 (a thread that
 // walked the D coordinates of three candidate positions in loops paid one per element: 6 us of a 16 us round).
 struct SpecElem { double x, lp; bool acc, isnan; };
-__device__ __forceinline__ SpecElem spec_state(const RingDev &G, long long rd, long long row, long long prev_partner, int d, int D, long long NV) {
+struct SpecBase {                      // the previous round's records (32-bit offsets from here: the apply phase is one warp's
+    const double *meta, *x, *nlp, *sq; //  dependent instruction stream, and 64-bit index arithmetic was most of it)
+    int n0, n1, D;
+    bool initial;                      // round 0: the state is the ensemble's (coords, logp)
+    __device__ __forceinline__ SpecBase(const RingDev &G, long long rd, int D_) {
+        const long long pb = (rd - 1) & 1, NV = G.n0 + 2 * (G.W - G.n0);
+        initial = rd == 0;
+        meta = G.smeta + pb * G.W * 2; x = G.xbuf + pb * G.W * (D_ + 1); nlp = G.snlp + pb * NV; sq = G.sq + pb * NV * D_;
+        if (initial) { x = G.coords; nlp = G.logp; }
+        n0 = (int)G.n0; n1 = (int)(G.W - G.n0); D = D_;
+    }
+};
+// plain form (round 0 and the final state): every lane fetches everything it needs
+__device__ __forceinline__ SpecElem spec_state(const SpecBase &B, int row, int prev_partner, int d) {
     SpecElem e;
     e.acc = false; e.isnan = false;
-    if (rd == 0) {
-        e.x = __ldcg(G.coords + row * D + d);
-        e.lp = __ldcg(G.logp + row);
+    const int D = B.D;
+    if (B.initial) {                                             // (uniform)
+        e.x = __ldcg(B.x + row * D + d);
+        e.lp = __ldcg(B.nlp + row);
         return e;
     }
-    const int pb = (int)((rd - 1) & 1);
-    const long long n1 = G.W - G.n0;
-    const double *m = G.smeta + ((long long)pb * G.W + row) * 2;
-    const double *xo = G.xbuf + ((long long)pb * G.W + row) * (D + 1);
+    // a first-colour row has one evaluation (v = row), a second-colour row two (v = row: partner rejected, v = row + n1: accepted)
+    const bool second = row >= B.n0;
+    const int vb = second ? row + B.n1 : row, a = second ? prev_partner : row;
+    const double *m = B.meta + row * 2, *ma = B.meta + a * 2, *xo = B.x + row * (D + 1);
     const double lnz = __ldcg(m), logu = __ldcg(m + 1), old = __ldcg(xo + D), xold = __ldcg(xo + d);
-    double nlp, xq;
-    if (row < G.n0) {
-        nlp = __ldcg(G.snlp + pb * NV + row);
-        xq = __ldcg(G.sq + ((long long)pb * NV + row) * D + d);
-    } else {
-        // both evaluations of the second-colour walker are fetched before the partner's outcome is known
-        const long long v0 = row, v1 = row + n1;
-        const double nlp0 = __ldcg(G.snlp + pb * NV + v0), nlp1 = __ldcg(G.snlp + pb * NV + v1);
-        const double x0 = __ldcg(G.sq + ((long long)pb * NV + v0) * D + d), x1 = __ldcg(G.sq + ((long long)pb * NV + v1) * D + d);
-        const bool sel = spec_acc_first(G, pb, prev_partner, D, NV);
-        nlp = sel ? nlp1 : nlp0;
-        xq = sel ? x1 : x0;
-    }
+    const double nlp0 = __ldcg(B.nlp + row), nlp1 = __ldcg(B.nlp + vb);
+    const double x0 = __ldcg(B.sq + row * D + d), x1 = __ldcg(B.sq + vb * D + d);
+    const double a_nlp = __ldcg(B.nlp + a), a_lnz = __ldcg(ma), a_logu = __ldcg(ma + 1), a_old = __ldcg(B.x + a * (D + 1) + D);
+    const bool sel = second && accept_test(D, a_lnz, a_nlp, a_old, a_logu);   // did the first-colour partner move in the previous round?
+    const double nlp = sel ? nlp1 : nlp0, xq = sel ? x1 : x0;
     e.acc = accept_test(D, lnz, nlp, old, logu);
     e.isnan = nlp != nlp;
     e.x = e.acc ? xq : xold;
@@ -1793,10 +1793,11 @@ __device__ __forceinline__ SpecElem spec_state(const RingDev &G, long long rd, l
     return e;
 }
 // what the owner of `row` records when it derives the row's state at the start of round rd (rd = nsteps: the final state)
-__device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long long row, int d, int D, const SpecElem &e) {
-    const long long j = (row < G.n0) ? 2 * row : 2 * (row - G.n0) + 1;
+__device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, int row, int d, int D, const SpecElem &e) {
+    const int W = (int)G.W, n0 = (int)G.n0;
+    const int j = (row < n0) ? 2 * row : 2 * (row - n0) + 1;
     if (rd < G.nsteps) {
-        double *xo = G.xbuf + ((long long)(rd & 1) * G.W + row) * (D + 1);
+        double *xo = G.xbuf + (rd & 1) * (long long)(W * (D + 1)) + row * (D + 1);
         xo[d] = e.x;
         if (d == 0) xo[D] = e.lp;
     } else {
@@ -1806,10 +1807,10 @@ __device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long
     if (rd > 0) {
         if (d == 0 && e.isnan) atomicAdd(G.nanflag, 1);        // emcee: "Probability function returned NaN" (selected evaluations only)
         if (G.chain) {
-            G.chain[((rd - 1) * G.W + j) * D + d] = e.x;
+            G.chain[((rd - 1) * W + j) * D + d] = e.x;
             if (d == 0) {
-                G.lnp[(rd - 1) * G.W + j] = e.lp;
-                if (e.acc) G.accepted[j] += 1ull;
+                G.lnp[(rd - 1) * W + j] = e.lp;
+                if (e.acc) atomicAdd(G.accepted + j, 1ull);      // (a reduction: nothing waits for the old count)
             }
         }
     }
@@ -1820,7 +1821,7 @@ __device__ __forceinline__ void spec_commit(const RingDev &G, long long rd, long
 // memory (the walker's row of the term scratch, free between two passes).  spec_apply (after the barrier, one thread per (virtual
 // walker, coordinate)): one round trip to L2 for the previous round's records, the selects, the proposal.
 constexpr int kSpecDims = 16;            // threads per virtual walker in spec_apply (>= kMaxDim)
-static_assert(kSpecDims >= kMaxDim && kTermStride >= 12, "spec_plan parks 12 words per walker in the term scratch");
+static_assert(kSpecDims >= kMaxDim && kMaxDim <= 13 && kTermStride >= 12, "spec_plan parks 12 words per walker in the term scratch; lanes 13..15 of a walker are the scalar lanes of spec_apply");
 __device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long long g, int wpb, double *s_plan) {
     // lane = virtual walker of the group, warp = role: the up to five Philox draws of a walker's plan form chains (own draw -> partner
     // -> the partner's draw -> its partner -> that one's previous move); five warps walk them side by side (depth 3 instead of 5)
@@ -1831,8 +1832,8 @@ __device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long l
     const bool r_part = role == (nroles == 5 ? 2 : 0), r_own = role == (nroles == 5 ? 3 : 0), r_pp = role == (nroles == 5 ? 4 : 0);
     const long long n0 = G.n0, n1 = G.W - n0, NV = n0 + 2 * n1;
     const unsigned int ctr0 = (unsigned int)(2 * (G.iter0 + rd));
-    double *pd = s_plan + w * kTermStride;
-    long long *pl = reinterpret_cast<long long *>(pd);
+    double *pd = s_plan + w * kTermStride;                       // words 0..7: eight ints (pl[0..7]); 8..11: z, za, ln z, ln u
+    int *pl = reinterpret_cast<int *>(pd);
     const long long v = g * wpb + w;
     if (v >= NV) { if (r_main) pl[0] = -1; return; }
     long long row, j, Nc, comp_base;
@@ -1844,15 +1845,15 @@ __device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long l
         sel = (int)((v - n0) / n1);
         row = n0 + k; j = 2 * k + 1; ctr = ctr0 + 1u; Nc = n0; comp_base = 0;
     }
-    if (r_own) pl[4] = spec_prev_partner(G, rd, row);
+    if (r_own) pl[4] = (int)spec_prev_partner(G, rd, row);
     if (!(r_main || r_meta || r_part || r_pp)) return;
     double z, u;
     long long pr;
     stretch_draw(G.seed, ctr, j, Nc, z, pr, u);
     const long long prow = comp_base + pr;
     if (r_meta && sel == 0) { pd[10] = log(z); pd[11] = log(u); }
-    if (r_main) { pl[0] = v; pl[1] = row; pl[2] = prow; pl[7] = sel; pd[8] = z; }
-    if (r_part) pl[5] = spec_prev_partner(G, rd, prow);
+    if (r_main) { pl[0] = (int)v; pl[1] = (int)row; pl[2] = (int)prow; pl[7] = sel; pd[8] = z; }
+    if (r_part) pl[5] = (int)spec_prev_partner(G, rd, prow);
     if (r_main || r_pp) {
         long long pprow = -1;
         double za = 0.;
@@ -1862,40 +1863,99 @@ __device__ __forceinline__ void spec_plan(const RingDev &G, long long rd, long l
             stretch_draw(G.seed, ctr0, 2 * prow, n1, za, pra, ua);
             pprow = n0 + pra;
         }
-        if (r_main) { pl[3] = pprow; pd[9] = za; }
-        if (r_pp) pl[6] = sel == 1 ? spec_prev_partner(G, rd, pprow) : -1;
+        if (r_main) { pl[3] = (int)pprow; pd[9] = za; }
+        if (r_pp) pl[6] = sel == 1 ? (int)spec_prev_partner(G, rd, pprow) : -1;
     }
 }
 // s_q: the CTA's proposal rows in shared memory (group_pass reads them there when Mv.qin is NULL); ends with a CTA barrier
 __device__ __forceinline__ void spec_apply(const RingDev &G, long long rd, int wpb, int D, int crank, const double *s_plan, double *s_q) {
-    const long long n1 = G.W - G.n0, NV = G.n0 + 2 * n1;
-    const int cb = (int)(rd & 1);
+    const int NV = (int)(G.n0 + 2 * (G.W - G.n0)), W = (int)G.W, n0 = (int)G.n0, n1 = W - n0;
+#ifdef LCF_X_TIMING
+    const long long tx0 = clock64();
+#endif
+    double *sq_out = G.sq + (rd & 1) * (long long)(NV * D), *meta_out = G.smeta + (rd & 1) * (long long)(2 * W);
+    // The previous round's records live in ONE allocation (xbuf, sq, snlp, smeta): 32-bit offsets from its start.
+    const double *base = G.xbuf;
+    const int pb = (int)((rd - 1) & 1);
+    const int xb = pb * W * (D + 1), sqb = (int)(G.sq - base) + pb * NV * D, nb = (int)(G.snlp - base) + pb * NV, mb = (int)(G.smeta - base) + pb * 2 * W;
+    const unsigned int gmask = 0xFFFFu << (threadIdx.x & 16);    // the 16 lanes of this thread's walker
+    const int g0 = threadIdx.x & 16;
     for (int t = threadIdx.x; t < wpb * kSpecDims; t += blockDim.x) {
         const int w = t / kSpecDims, d = t % kSpecDims;
         const double *pd = s_plan + w * kTermStride;
-        const long long *pl = reinterpret_cast<const long long *>(pd);
-        const long long v = pl[0];
-        if (v < 0 || d >= D) continue;
-        const long long row = pl[1], prow = pl[2];
-        const int sel = (int)pl[7];
-        // (all loads before the first store: the compiler keeps loads behind stores that may alias, and a second round trip to L2
-        //  is 700 clocks of a 24 000-clock round)
-        const SpecElem own = spec_state(G, rd, row, pl[4], d, D, NV);
-        double c = spec_state(G, rd, prow, pl[5], d, D, NV).x;     // the partner at the start of the round
-        if (sel == 1) {                                          // ... and after its own move of this round, had it been accepted
-            const double cc = spec_state(G, rd, pl[3], pl[6], d, D, NV).x;
-            c = __dsub_rn(cc, __dmul_rn(__dsub_rn(cc, c), pd[9]));
+        const int *pl = reinterpret_cast<const int *>(pd);
+        const int v = pl[0];
+        if (v < 0) continue;                                     // (the whole group)
+        const int sel = pl[7];
+        SpecElem own;
+        double c, cc;
+        if (rd == 0) {                                           // (uniform) the ensemble's own arrays
+            const SpecBase B(G, rd, D);
+            const int dd = d < D ? d : 0;
+            own = spec_state(B, pl[1], -1, dd);
+            c = spec_state(B, pl[2], -1, dd).x;
+            cc = spec_state(B, sel == 1 ? pl[3] : pl[2], -1, dd).x;
+        } else {
+            // Three states per proposal: the walker's own, its partner's, and (variant 1; variant 0 repeats the partner) the partner's
+            // partner's.  A state is one of up to three stored positions, chosen by two accept tests on nine scalars.  Lanes 13..15 of
+            // the walker's 16 fetch the nine scalars of one state each and take its tests; lanes d < D fetch the three candidate
+            // coordinates of each state: NINE independent loads per lane whatever its role -- the same straight-line code with
+            // per-lane offsets, one batch, one round trip to L2 -- then three shuffles hand the outcomes to the coordinate lanes.
+            // (Each lane fetching everything was 36 loads against 64 registers: three to four round trips, 2 800 clocks.)
+            const int r[3] = {pl[1], pl[2], sel == 1 ? pl[3] : pl[2]}, pp[3] = {pl[4], pl[5], sel == 1 ? pl[6] : pl[5]};
+            const bool srole = d >= 13;
+            const int ss = d - 13, dd = d < D ? d : 0;
+            int o[9];
+            {
+                const int rs = ss == 0 ? r[0] : (ss == 1 ? r[1] : r[2]), ps = ss == 0 ? pp[0] : (ss == 1 ? pp[1] : pp[2]);
+                const bool sec = rs >= n0;
+                const int vbs = sec ? rs + n1 : rs, as = sec ? ps : rs;
+                const int os[9] = {mb + 2 * rs, mb + 2 * rs + 1, xb + rs * (D + 1) + D, nb + rs, nb + vbs, nb + as, mb + 2 * as, mb + 2 * as + 1,
+                                   xb + as * (D + 1) + D};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int vbk = r[k] >= n0 ? r[k] + n1 : r[k];
+                    o[3 * k] = srole ? os[3 * k] : xb + r[k] * (D + 1) + dd;
+                    o[3 * k + 1] = srole ? os[3 * k + 1] : sqb + r[k] * D + dd;
+                    o[3 * k + 2] = srole ? os[3 * k + 2] : sqb + vbk * D + dd;
+                }
+            }
+            double x[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) x[k] = __ldcg(base + o[k]);
+            // scalar lanes: x = (ln z, ln u, old, nlp0, nlp1, partner's nlp, ln z, ln u, old)
+            const int rs = ss == 0 ? r[0] : (ss == 1 ? r[1] : r[2]);
+            const bool s_sel = rs >= n0 && accept_test(D, x[6], x[5], x[8], x[7]);
+            const double s_nlp = s_sel ? x[4] : x[3];
+            const bool s_acc = accept_test(D, x[0], s_nlp, x[2], x[1]);
+            const int bits = (s_sel ? 1 : 0) | (s_acc ? 2 : 0) | (s_nlp != s_nlp ? 4 : 0);
+            const double s_lp = s_acc ? s_nlp : x[2];
+            const int b0 = __shfl_sync(gmask, bits, g0 + 13), b1 = __shfl_sync(gmask, bits, g0 + 14), b2 = __shfl_sync(gmask, bits, g0 + 15);
+            own.lp = __shfl_sync(gmask, s_lp, g0 + 13);
+            own.acc = (b0 & 2) != 0; own.isnan = (b0 & 4) != 0;
+            // coordinate lanes: x = (old, evaluation 0, evaluation 1) x three states
+            own.x = (b0 & 2) ? ((b0 & 1) ? x[2] : x[1]) : x[0];
+            c = (b1 & 2) ? ((b1 & 1) ? x[5] : x[4]) : x[3];
+            cc = (b2 & 2) ? ((b2 & 1) ? x[8] : x[7]) : x[6];
         }
+        if (sel == 1) c = __dsub_rn(cc, __dmul_rn(__dsub_rn(cc, c), pd[9]));   // the partner after its own move of this round, had it been accepted
         const double q = __dsub_rn(c, __dmul_rn(__dsub_rn(c, own.x), pd[8]));   // q = c - (c - s) z, numpy op order, no FMA
+#ifdef LCF_X_TIMING
+        if (threadIdx.x == 0 && q == q) atomicAdd(&g_phase_clk[1], (unsigned long long)(clock64() - tx0));
+#endif
+        if (d >= D) continue;
+        const int row = pl[1];
         s_q[w * D + d] = q;
-        G.sq[((long long)cb * NV + v) * D + d] = q;
+        sq_out[v * D + d] = q;
         if (d == 0 && sel == 0) {                                // ln z, ln u of this round's move of `row`
-            double *m = G.smeta + ((long long)cb * G.W + row) * 2;
-            m[0] = pd[10];
-            m[1] = pd[11];
+            meta_out[row * 2] = pd[10];
+            meta_out[row * 2 + 1] = pd[11];
         }
         if (sel == 0 && crank == 0) spec_commit(G, rd, row, d, D, own);
     }
+#ifdef LCF_X_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_phase_clk[2], (unsigned long long)(clock64() - tx0));
+#endif
     __syncthreads();
 }
 
@@ -1982,8 +2042,9 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_ring(const Pr
             for (int t = threadIdx.x; t < wpb * kSpecDims; t += blockDim.x) {
                 const long long v = g * wpb + t / kSpecDims;
                 const int d = t % kSpecDims;
-                if (v < G.n0 + n1 && d < D)                         // the owners: first virtual walker of every row (v = row)
-                    spec_commit(G, G.nsteps, v, d, D, spec_state(G, G.nsteps, v, spec_prev_partner(G, G.nsteps, v), d, D, NV));
+                if (v < G.n0 + n1) {                                // the owners: first virtual walker of every row (v = row)
+                    if (d < D) spec_commit(G, G.nsteps, (int)v, d, D, spec_state(SpecBase(G, G.nsteps, D), (int)v, (int)spec_prev_partner(G, G.nsteps, v), d));
+                }
             }
     }
 }

@@ -47,7 +47,7 @@ def emit(name, walkers, steps, ms, samples_per_eval, extra=None):
         import ctypes as C
         buf = (C.c_uint64 * 10)()
         L.lcf_debug_phase_clocks(buf)
-        extra = dict(extra or {}, phase_clk_sum=[int(v) for v in buf[:5]] + [int(buf[5]) & ((1 << 40) - 1)], sub=[int(buf[6]), int(buf[7])], ring_barrier=int(buf[8]),
+        extra = dict(extra or {}, phase_clk_sum=[int(v) for v in buf[:5]] + [int(buf[5]) & ((1 << 40) - 1)], sub=[int(buf[6]), int(buf[7])], ring_barrier=int(buf[8]), ring_apply=int(buf[9]),
                      lane_tiles={'fast': int(buf[6]), 'clamped': int(buf[7]), 'careful': int(buf[5]) >> 40})
     ws = walkers * steps / (ms * 1e-3)
     out = {'config': name, 'walker_steps_per_s': ws, 'ms': ms, 'walkers': walkers, 'steps': steps,
