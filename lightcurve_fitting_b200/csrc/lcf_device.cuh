@@ -1211,7 +1211,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // 1a: one thread per walker: stretch-move draw and proposal
     constexpr int NT = ModelTerms<MODEL>::value;
     const bool with_prior = Mv.mode == MODE_MOVE || Mv.mode == MODE_LOGPOST;
-    if (tid < wpb) {
+    const bool q_ready = Mv.mode == MODE_LOGPOST && !Mv.qin;   // k_ring look-ahead rounds: spec_apply left the proposals in s_q (and synchronised)
+    if (tid < wpb && !q_ready) {
         const long long i = g * wpb + tid;
         if (i < Mv.Ns) {
             double q[kMaxDim];
@@ -1237,14 +1238,13 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             } else {
                 const int nq = (Mv.mode == MODE_MODEL) ? P.nmodel : D;
                 const long long qs = Mv.qstride ? Mv.qstride : nq;
-                if (Mv.qin) { for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * qs + d]; }
-                else { for (int d = 0; d < nq; ++d) q[d] = s_q[tid * D + d]; }      // k_ring look-ahead rounds: written by spec_apply
+                for (int d = 0; d < nq; ++d) q[d] = Mv.qin[i * qs + d];
                 for (int d = nq; d < D; ++d) q[d] = 0.;
             }
             for (int d = 0; d < D; ++d) s_q[tid * D + d] = q[d];
         }
     }
-    __syncthreads();
+    if (!q_ready) __syncthreads();
     LCF_TICK(6);
     // 1b: one thread per (walker, term): FP64 transcendentals of the model constants, log-priors, ln z and ln u
     {
