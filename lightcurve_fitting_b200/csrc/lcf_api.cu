@@ -216,9 +216,11 @@ struct lcf_batch {
     size_t chain_cap = 0, lnp_cap = 0;            // grow-only chain buffers
     double *d_lpseudo = nullptr, *d_summary = nullptr;
     size_t lpseudo_cap = 0;
+    int spec = 0;                                 // look-ahead rounds in k_chain (small ensembles)
+    double *d_spec = nullptr;                     // [nprob][32] log-posteriors of a round's virtual walkers + a NaN counter
     ~lcf_batch() {
         for (lcf_problem *p : owned) delete p;
-        cudaFree(d_shared); cudaFree(d_shared_tiles); cudaFree(d_lpseudo); cudaFree(d_summary);
+        cudaFree(d_shared); cudaFree(d_shared_tiles); cudaFree(d_lpseudo); cudaFree(d_summary); cudaFree(d_spec);
         cudaFree(d_probs); cudaFree(d_tiles); cudaFree(d_order); cudaFree(d_coords); cudaFree(d_logp); cudaFree(d_chain); cudaFree(d_lnp);
         cudaFree(d_acc); cudaFree(d_status);
         if (ev0) cudaEventDestroy(ev0);
@@ -245,7 +247,7 @@ template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool pla
     if (l == 5) return plain ? k_pass<LCF_DEV_ONLY_MODEL, R, 5, true> : k_pass<LCF_DEV_ONLY_MODEL, R, 5, false>;
     return k_pass<LCF_DEV_ONLY_MODEL, R, -1, false>;
 }
-template <typename R> ChainKernel chain_kernel_for(int) { return nullptr; }
+template <typename R> ChainKernel chain_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_chain<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 template <typename R> RingKernel ring_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_ring<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 #else
 // l = walkers-per-CTA exponent of the launch: 5 (32 walkers, every large ensemble) has its own instantiation
@@ -1849,9 +1851,16 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
     // shape: walkers per CTA pass = smallest power of two covering a half-ensemble: <= 32 (narrow groups), or 64..256
     // ("wide" groups: wpb/32 walker columns of warps, one proposal phase for the whole half-ensemble) when the model
     // has no per-walker weight table and the per-CTA tables still let four CTAs share an SM
+    // Look-ahead rounds (k_chain): when the n0 + 2 n1 virtual walkers of a step fit ONE narrow group (W <= 21), a step is one
+    // log-posterior pass plus two accept phases instead of two dependent half-steps; LCF_CHAIN_LA=0 keeps the half-steps.
+    const long long n1 = nwalkers - b->n0, NV = b->n0 + 2 * n1;
+    {
+        const char *env = getenv("LCF_CHAIN_LA");
+        b->spec = (n1 > 0 && NV <= 32 && g_tune_wpb <= 0 && !(env && env[0] == '0')) ? 1 : 0;
+    }
     int l = 0;
     if (g_tune_wpb > 0) { while ((1 << l) < g_tune_wpb && l < 5) ++l; }
-    else { while ((1 << l) < b->n0 && l < 8) ++l; }
+    else { while ((1 << l) < (b->spec ? NV : b->n0) && l < 8) ++l; }
     if (p0->dev.model == 3) l = std::min(l, 5);
     size_t smem = 0;
     int max_tiles = 1;
@@ -1861,6 +1870,11 @@ int lcf_batch_create(int64_t nproblems, lcf_problem *const *problems, int64_t nw
         // four (wide groups) / two CTAs per SM, counting the 1 KB the driver reserves per CTA and the kernel's static 0.8 KB
         if (smem + 2048 <= (l > 5 ? kSmemMax / 4 : kSmemMax / 2) || l == 0) break;
         --l;
+    }
+    if (b->spec && (1 << l) < NV) {                       // the group no longer holds the whole step: back to half-steps
+        b->spec = 0;
+        l = 0;
+        while ((1 << l) < b->n0 && l < 8) ++l;
     }
     // split-K for narrow groups of small problems (an SED epoch has 3-9 points, one per filter): with 2^ks lanes per (walker, point
     // pair) a warp is full of short loops instead of a quarter full of long ones.  Chosen from the mean number of points that
@@ -1977,6 +1991,8 @@ int lcf_batch_run(lcf_batch *b, int64_t nburn, int64_t nsteps) {
     B.W = b->W; B.n0 = b->n0; B.nproblems = b->nprob;
     B.nburn = nburn; B.nsteps = nsteps; B.iter0 = b->iteration;
     B.seed = b->seed; B.wpb_log2 = b->wpb_log2; B.ks = b->ks; B.init_logp = b->need_init_logp ? 1 : 0;
+    if (!b->d_spec) CUDA_TRY(cudaMalloc(&b->d_spec, sizeof(double) * (32 * (size_t)b->nprob + 1)));
+    B.spec = b->spec; B.spec_nlp = b->d_spec; B.nan_scratch = reinterpret_cast<int *>(b->d_spec + 32 * (size_t)b->nprob);
     ChainKernel k = (b->precision == LCF_PRECISION_FP32) ? chain_kernel_for<float>(b->model) : chain_kernel_for<double>(b->model);
     if (!k) return fail(LCF_ERR_ARG, "unknown model");
     { int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), b->smem); if (rc) return rc; }

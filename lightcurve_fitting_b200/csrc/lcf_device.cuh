@@ -1511,7 +1511,10 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
                     for (int d = 0; d < D; ++d) crd[d] = s_q[tid * D + d];
                     Mv.logp[row] = nlp;
                     if (Mv.accepted) Mv.accepted[j] += 1ull;
-                    for (int p = 0; p < Mv.npeers; ++p) {            // the same update in every peer's replica (NVLink stores)
+#pragma unroll
+                    for (int p = 0; p < kMaxPeers; ++p) {            // the same update in every peer's replica (NVLink stores)
+                        // (compile-time indices into Mv's peer arrays: a run-time index kept the whole MoveDev of k_chain / k_ring in local memory)
+                        if (p >= Mv.npeers) break;
                         double *pc = Mv.peer_coords[p] + row * D;
                         for (int d = 0; d < D; ++d) pc[d] = s_q[tid * D + d];
                         Mv.peer_logp[p][row] = nlp;
@@ -1603,6 +1606,9 @@ struct BatchDev {
     long long nburn, nsteps, iter0;
     unsigned long long seed;
     int wpb_log2, init_logp, ks;
+    int spec;                        // look-ahead rounds (W small: all n0 + 2 n1 virtual walkers of a step in ONE pass, see k_chain)
+    double *spec_nlp;                // [nproblems][32] log-posteriors of the round's virtual walkers
+    int *nan_scratch;                // NaN counter of the evaluation passes (only SELECTED evaluations count)
 };
 
 // at most 8 warps per CTA; FP32: 64 registers so that four CTAs (32 warps) share an SM, as in k_pass
@@ -1632,7 +1638,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     MoveDev Mv;
     Mv.coords = B.coords + prob * B.W * D;
     Mv.logp = B.logp + prob * B.W;
-    unsigned long long *acc_ptr = B.accepted + prob * B.W;
+    unsigned long long *acc_ptr0 = B.accepted + prob * B.W;
     Mv.accepted = nullptr;
     Mv.nanflag = B.status + prob;
     Mv.W = B.W; Mv.n0 = B.n0;
@@ -1644,31 +1650,128 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 4 ? LCF_CHAIN_MINBLOCKS : 2
     Mv.seed = B.seed ^ ((unsigned long long)(prob + 1) * 0x9E3779B97F4A7C15ull);
     Mv.qin = nullptr; Mv.out = nullptr; Mv.qstride = 0;
     bool first = true;
-    if (B.init_logp) {                                   // log-prob of the initial positions
-        Mv.mode = MODE_LOGPOST;
-        Mv.Ns = B.W; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0;
-        Mv.qin = Mv.coords; Mv.out = Mv.logp;
-        Mv.chain_step = nullptr; Mv.lnp_step = nullptr; Mv.ctr = 0;
-        const long long ng = (B.W + wpb - 1) / wpb;
-        for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
-        Mv.qin = nullptr; Mv.out = nullptr;
-    }
-    Mv.mode = MODE_MOVE;
     const long long n1 = B.W - B.n0;
-    for (long long it = 0; it < B.nburn + B.nsteps; ++it) {
-        const bool store = it >= B.nburn;
-        Mv.accepted = store ? acc_ptr : nullptr;          // acceptance counts cover the stored phase only
-        Mv.chain_step = store ? B.chain + ((prob * B.nsteps + (it - B.nburn)) * B.W) * D : nullptr;
-        Mv.lnp_step = store ? B.lnp + (prob * B.nsteps + (it - B.nburn)) * B.W : nullptr;
-        for (int half = 0; half < 2; ++half) {
-            Mv.ctr = (unsigned int)(2 * (B.iter0 + it) + half);
+    unsigned long long *const acc_ptr = acc_ptr0;
+    // Passes: the initial log-probabilities, then per step either two half-steps (MODE_MOVE) or -- look-ahead rounds, small
+    // ensembles (B.spec) -- ONE log-posterior pass over the n0 + 2 n1 virtual walkers of the step: the proposals of the first colour
+    // and, for every second-colour walker, its proposal against its partner's old position AND against its partner's proposal
+    // (k_ring's look-ahead, with CTA barriers in place of the grid barrier and nothing deferred: the accept phases follow the
+    // pass directly).  An SED epoch of 10 walkers is latency-bound like cfg1: half as many dependent passes per step.
+    const bool spec = B.spec != 0;
+    const int NV = (int)(B.n0 + 2 * n1), n0 = (int)B.n0;
+    __shared__ double s_lz[32], s_lu[32];                  // ln z, ln u of the step's moves (by physical row)
+    __shared__ int s_acc[32];                              // accept flags of the first colour
+    double *s_q = reinterpret_cast<double *>(smem + L.off_q);
+    double *nlp_out = B.spec_nlp + prob * 32;
+    long long it = B.init_logp ? -1 : 0;
+    int half = 0;
+    while (it < B.nburn + B.nsteps) {
+        const bool init = it < 0, round = spec && !init;
+        const bool store = !init && it >= B.nburn;
+        const unsigned int ctr0 = (unsigned int)(2 * (B.iter0 + (init ? 0 : it)));
+        Mv.accepted = nullptr; Mv.chain_step = nullptr; Mv.lnp_step = nullptr;
+        Mv.qin = nullptr; Mv.out = nullptr; Mv.nanflag = B.status + prob;
+        if (init) {                                        // log-prob of the initial positions
+            Mv.mode = MODE_LOGPOST;
+            Mv.Ns = B.W; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0;
+            Mv.qin = Mv.coords; Mv.out = Mv.logp; Mv.ctr = 0;
+        } else if (round) {
+            // proposals: one thread per virtual walker; a second warp takes the logarithms of the W moves
+            const int tid = threadIdx.x;
+            if (tid < NV) {
+                const int v = tid;
+                int row, sel = 0;
+                long long j, Nc, comp_base;
+                unsigned int ctr;
+                if (v < n0) { row = v; j = 2 * v; ctr = ctr0; Nc = n1; comp_base = n0; }
+                else {
+                    const int k = (v - n0) % (int)n1;
+                    sel = (v - n0) / (int)n1;
+                    row = n0 + k; j = 2 * k + 1; ctr = ctr0 + 1u; Nc = n0; comp_base = 0;
+                }
+                double z, u, za = 0., ua;
+                long long pr, pra = 0;
+                stretch_draw(Mv.seed, ctr, j, Nc, z, pr, u);
+                const int prow = (int)(comp_base + pr);
+                if (sel == 1) stretch_draw(Mv.seed, ctr0, 2 * prow, n1, za, pra, ua);   // the partner's own move of this step
+                const double *own = Mv.coords + row * D, *cp = Mv.coords + prow * D, *cpp = Mv.coords + (n0 + pra) * D;
+                for (int d = 0; d < D; ++d) {
+                    double c = cp[d];
+                    if (sel == 1) c = __dsub_rn(cpp[d], __dmul_rn(__dsub_rn(cpp[d], c), za));   // ... its proposal
+                    s_q[v * D + d] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, own[d]), z));         // q = c - (c - s) z, numpy op order, no FMA
+                }
+            }
+            const bool two_warps = blockDim.x >= 64;
+            if (two_warps ? (tid >= 32 && tid < 32 + (int)B.W) : tid < (int)B.W) {
+                const int row = two_warps ? tid - 32 : tid;
+                double z, u;
+                long long pr;
+                if (row < n0) stretch_draw(Mv.seed, ctr0, 2 * row, n1, z, pr, u);
+                else stretch_draw(Mv.seed, ctr0 + 1u, 2 * (row - n0) + 1, B.n0, z, pr, u);
+                s_lz[row] = log(z);
+                s_lu[row] = log(u);
+            }
+            __syncthreads();
+            Mv.mode = MODE_LOGPOST;
+            Mv.Ns = NV; Mv.act_base = 0; Mv.Nc = 0; Mv.comp_base = 0;
+            Mv.out = nlp_out; Mv.nanflag = B.nan_scratch; Mv.ctr = ctr0;
+        } else {
+            Mv.mode = MODE_MOVE;
+            Mv.accepted = store ? acc_ptr : nullptr;          // acceptance counts cover the stored phase only
+            Mv.chain_step = store ? B.chain + ((prob * B.nsteps + (it - B.nburn)) * B.W) * D : nullptr;
+            Mv.lnp_step = store ? B.lnp + (prob * B.nsteps + (it - B.nburn)) * B.W : nullptr;
+            Mv.ctr = ctr0 + (unsigned int)half;
             Mv.Ns = half ? n1 : B.n0;
             Mv.act_base = half ? B.n0 : 0;
             Mv.Nc = half ? B.n0 : n1;
             Mv.comp_base = half ? 0 : B.n0;
-            const long long ng = (Mv.Ns + wpb - 1) / wpb;
+        }
+        // two call sites, each with the mode known at compile time (one shared site with a run-time mode cost the half-step path 10-14 %)
+        const long long ng = (Mv.Ns + wpb - 1) / wpb;
+        if (init || round) {
+            Mv.mode = MODE_LOGPOST;
+            for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
+        } else {
+            Mv.mode = MODE_MOVE;
             for (long long g = 0; g < ng; ++g) { group_pass<MODEL, R>(sP, sT, Mv, g, smem, L, first, 0, 1); first = false; }
         }
+        if (round) {
+            // accept phases: first colour, then second colour with the evaluation that matches its partner's outcome
+            double *cs = store ? B.chain + ((prob * B.nsteps + (it - B.nburn)) * B.W) * D : nullptr;
+            double *ls = store ? B.lnp + (prob * B.nsteps + (it - B.nburn)) * B.W : nullptr;
+            const int tid = threadIdx.x;
+            for (int colour = 0; colour < 2; ++colour) {
+                if (tid < (colour ? (int)n1 : n0)) {
+                    const int row = colour ? n0 + tid : tid;
+                    const long long j = colour ? 2 * tid + 1 : 2 * tid;
+                    int v = row;
+                    if (colour) {
+                        double z, u;
+                        long long pr;
+                        stretch_draw(Mv.seed, ctr0 + 1u, j, B.n0, z, pr, u);
+                        v = row + (s_acc[pr] ? (int)n1 : 0);
+                    }
+                    const double nlp = nlp_out[v], old = Mv.logp[row];
+                    const bool acc = accept_test(D, s_lz[row], nlp, old, s_lu[row]);
+                    if (nlp != nlp) atomicAdd(B.status + prob, 1);   // emcee: "Probability function returned NaN"
+                    if (!colour) s_acc[row] = acc ? 1 : 0;
+                    double *crd = Mv.coords + row * D;
+                    if (acc) {
+                        for (int d = 0; d < D; ++d) crd[d] = s_q[v * D + d];
+                        Mv.logp[row] = nlp;
+                        if (store) acc_ptr[j] += 1ull;
+                    }
+                    if (store) {
+                        for (int d = 0; d < D; ++d) cs[j * D + d] = crd[d];
+                        ls[j] = acc ? nlp : old;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (init) it = 0;
+        else if (round || half == 1) { ++it; half = 0; }
+        else half = 1;
     }
 }
 

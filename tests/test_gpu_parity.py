@@ -288,6 +288,35 @@ def test_batched_ensembles_match_single():
     assert 0.05 < b.acceptance_fraction.mean() < 0.95
 
 
+@pytest.mark.parametrize('nw', [8, 10, 21, 22])
+def test_batched_ensembles_look_ahead_rounds_match_half_steps(nw, monkeypatch):
+    """Small batched ensembles (n0 + 2 n1 <= 32 virtual walkers: W <= 21) run every step as ONE log-posterior pass over the proposals
+    of the first colour and BOTH candidate proposals of every second-colour walker, followed by the two accept phases (k_chain's
+    look-ahead rounds); LCF_CHAIN_LA=0 keeps two dependent half-steps per step.  Same draws, same proposals, same accept test: the
+    chains and the acceptance counts must be identical (the stored log-posteriors only to rounding: the two schedules evaluate
+    with different walkers-per-CTA shapes), in both precisions; 22 walkers no longer fit and both settings run half-steps."""
+    from lightcurve_fitting_b200.bolometric import BatchSampler
+    for precision, rtol in (('fp64', 1e-13), ('fp32', 1e-6)):
+        rng = np.random.default_rng(3)
+        wls = [W.sed_epoch(rng) for _ in range(7)]
+        probs = [w.device_problem(precision) for w in wls]
+        p0 = np.stack([w.start(nw, rng) for w in wls])
+        out = {}
+        for la in ('0', '1'):
+            monkeypatch.setenv('LCF_CHAIN_LA', la)
+            b = BatchSampler(probs, nw, seed=9).run(p0, 20, 15)
+            assert np.all(b.status == 0)
+            out[la] = (b.get_chain(), b.get_log_prob(), b.acceptance_fraction)
+        np.testing.assert_array_equal(out['1'][0], out['0'][0])
+        np.testing.assert_array_equal(out['1'][2], out['0'][2])
+        np.testing.assert_allclose(out['1'][1], out['0'][1], rtol=rtol)
+        assert not np.array_equal(out['1'][0][:, 0], out['1'][0][:, -1])
+        if nw == 22:
+            np.testing.assert_array_equal(out['1'][1], out['0'][1])
+        for i in range(7):                       # every stored position carries its own log-posterior
+            np.testing.assert_allclose(probs[i].log_posterior(out['1'][0][i].reshape(-1, 2)), out['1'][1][i].reshape(-1), rtol=1e-12 if precision == 'fp64' else 2e-5)
+
+
 @pytest.mark.parametrize('nw', [70, 150, 256, 300])
 def test_batched_ensembles_wide_walker_groups(nw):
     """Half-ensembles of 35 / 75 / 150 walkers run as ONE wide group (64 / 128 / 256 walkers, several warp columns) per
