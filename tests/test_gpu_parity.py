@@ -1141,6 +1141,36 @@ def test_persistent_chain_kernel_matches_half_step_launches(shape, monkeypatch):
         check(lib().lcf_set_tuning_ex(0, 0, 0))
 
 
+@pytest.mark.parametrize('case', ['sc3_odd', 'cs3', 'sed', 'sc4_sigma_small'])
+def test_look_ahead_rounds_other_models_and_odd_ensembles(case, monkeypatch):
+    """The look-ahead rounds of the persistent kernel (LCF_RING=2) against one k_pass launch per half-step (LCF_RING=0) on ensembles
+    whose colours differ in size (odd walker counts), on the other model families (per-walker weight table, SiFTO spline, bare SED)
+    and with the intrinsic-scatter parameter: chains, log-probabilities, acceptance counts and final states must be bit-identical."""
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    rng = np.random.default_rng(11)
+    if case == 'sc3_odd':
+        wl, nwalk, precision = W.synthetic_sc3(npoints=120), 51, 'fp32'
+    elif case == 'cs3':
+        wl, nwalk, precision = W.synthetic_cs3(npoints=90), 40, 'fp32'
+    elif case == 'sed':
+        wl, nwalk, precision = W.sed_epoch(rng), 33, 'fp64'
+    else:
+        wl, nwalk, precision = W.example_sc4(use_sigma=True, npoints=60), 17, 'fp32'
+    prob = wl.device_problem(precision)
+    p0 = wl.start(nwalk, np.random.default_rng(2))
+    out = {}
+    for ring in ('0', '2'):
+        monkeypatch.setenv('LCF_RING', ring)
+        s = EnsembleSampler(nwalk, wl.ndim, prob, seed=77)
+        s.run_mcmc(p0, 5, store=False, skip_initial_state_check=True)
+        st = s.run_mcmc(None, 11)
+        out[ring] = (s.get_chain(), s.get_log_prob(), s.acceptance_fraction, np.array(st.coords), np.array(st.log_prob), prob.last_launch()['kernel'])
+    assert out['2'][5] == 'k_ring<look-ahead>' and out['0'][5].startswith('k_pass')
+    for k in range(5):
+        np.testing.assert_array_equal(out['2'][k], out['0'][k])
+    assert not np.array_equal(out['2'][0][0], out['2'][0][-1])
+
+
 def test_native_sampler_posterior_matches_a_long_reference_run():
     """Statistical parity on a light-curve model: the reference's own lightcurve_mcmc (its closure and driver under the emcee
     stand-in; 32 walkers, 600 + 1200 steps, ShockCooling2 on a 45-point synthetic light curve) froze the posterior
