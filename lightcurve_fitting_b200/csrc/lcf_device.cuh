@@ -234,6 +234,14 @@ __device__ __forceinline__ bool accept_test(int D, double lnz, double nlp, doubl
 // reduction and a degree-12 polynomial.  ~65 dependent operations.  Anything unusual (non-positive, subnormal or
 // non-finite base, huge result) goes to libm, so the special-case semantics are libm's.
 // ---------------------------------------------------------------------------------------
+// 1/x for a positive normal double: MUFU.RCP64H seed (20 bits) + two Newton steps; no special-case handling
+__device__ __forceinline__ double rcp_f64(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
 __device__ __forceinline__ double exp2_core(double t) {               // |t| < 1000
     const double magic = 6755399441055744.0;                           // 1.5 * 2^52
     const double r = t + magic;
@@ -259,7 +267,9 @@ __device__ __forceinline__ double log2_normal(double x) {             // x posit
     int e = (hi >> 20) - 1023;
     double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
     if (m > 1.4142135623730951) { m *= 0.5; e += 1; }                   // [sqrt(1/2), sqrt 2)
-    const double s = (m - 1.0) / (m + 1.0), s2 = s * s;                  // |s| <= 0.1716
+    // (m + 1 is in [1.7, 2.42]: MUFU.RCP64H + two Newton steps instead of an IEEE division -- 5 dependent operations for ~25 on the
+    //  critical chain of every per-walker constant; the quotient is good to 2e-16)
+    const double s = (m - 1.0) * rcp_f64(m + 1.0), s2 = s * s;           // |s| <= 0.1716
     double p = 1. / 23.;
     p = fma(p, s2, 1. / 21.);
     p = fma(p, s2, 1. / 19.);
@@ -314,8 +324,8 @@ struct WalkerSetup {
 // them one per THREAD (walker_term, k < kTerms) instead of one walker per thread (a double-precision pow is a
 // ~300-instruction dependent chain: ten of them back to back used to be the serial prologue of every CTA), and
 // setup_walker then only combines them with a few multiplications.
-constexpr int kMaxTerms = 8;
-template <int MODEL> struct ModelTerms { static constexpr int value = (MODEL == 1 || MODEL == 3) ? 4 : (MODEL == 4 ? 8 : ((MODEL >= 5 && MODEL <= 7) ? 3 : 0)); };
+constexpr int kMaxTerms = 9;
+template <int MODEL> struct ModelTerms { static constexpr int value = (MODEL == 1 || MODEL == 3) ? 4 : (MODEL == 4 ? 9 : ((MODEL >= 5 && MODEL <= 7) ? 3 : 0)); };
 
 // term k of a walker = pow(base, expo) [or power(): 0 for a non-positive base, models.py:42-48] [or cos(base)]:
 // ONE pow call per thread whatever k is, so the lanes of a warp never diverge into different pow instances.
@@ -335,6 +345,11 @@ __device__ inline double walker_term(const ProblemDev &P, const double *p, int k
         // ShockCooling4.temperature_radius, models.py:584-587 (kappa = 1)
         const double v = p[0], f = p[2], Rr = p[3];
         const double ex[8] = {1.26, -1.13, -0.13, 0.78, 2.11, 0.11, -0.32, 0.03};
+        // Terms 7 and 8 are whole dependent chains of the constants, walked by their own warps NEXT TO the other powers instead of
+        // after them in setup_walker (where they were 1 700 of its 2 660 clocks on the 100-walker ensembles): the right-associative
+        // tower v_s ** (0.58 ** (f_rho_M ** 0.03)) of models.py:586, and log2(a / t_tr) with t_tr = t_tr_0 sqrt(M_env / v_s).
+        if (k == 7) return pow_fast(v, pow_fast(0.58, pow_fast(f, 0.03)));
+        if (k == 8) { const double b = mc[1] / (mc[6] * sqrt(p[1] / v)); return (b > 0.) ? log2_fast(b) : -Mth<double>::inf(); }
         const int which = (0x20210210 >> (4 * k)) & 3;       // k -> 0: R, 1: v, 2: f   (R v f R v f R f)
         base = which == 0 ? Rr : (which == 1 ? v : f);
         expo = ex[k];
@@ -382,17 +397,14 @@ __device__ inline void setup_walker(const ProblemDev &P, const double *p, const 
         s.t0 = p[3];
     } else if (MODEL == 4) {
         // mc: A, a, alpha, L_br_0, T_col_br_0, t_br_0, t_tr_0
-        double v = p[0], Menv = p[1];
         double t_br = mc[5] * term[0] * term[1] * term[2];
         double L_br = mc[3] * term[3] * term[4] * term[5];
-        // models.py:586 as written: v_s ** 0.58 ** f_rho_M ** 0.03 is right-associative
-        double T_br = mc[4] * term[6] * pow_fast(v, pow_fast(0.58, term[7]));
-        double t_tr = mc[6] * sqrt(Menv / v);
-        double base = mc[1] / t_tr;
+        // models.py:586 as written: v_s ** 0.58 ** f_rho_M ** 0.03 is right-associative (term 7, walker_term)
+        double T_br = mc[4] * term[6] * term[7];
         s.wc[0] = T_br / k_kB;
         s.wc[1] = c3sq * L_br;
         s.wc[2] = (t_br > 0.) ? -log2_fast(t_br) : Mth<double>::nan();   // log2(ttilde) = log2(t) + wc2
-        s.wc[3] = (base > 0.) ? log2_fast(base) : -Mth<double>::inf();
+        s.wc[3] = term[8];                                               // log2(a / t_tr) | -inf
         s.wc[4] = 1. / (0.97 * s.wc[0]);                    // 1/T on the early branch: wc4 ttilde^(1/3)
         s.wc[5] = 1. / s.wc[0];                             // 1/T on the late branch:  wc5 ttilde^0.45
         s.t0 = p[4];
@@ -724,14 +736,6 @@ __device__ __forceinline__ double ex2m1_f64(double x, const double *__restrict__
     return __hiloint2double(__double2hiint(p) + ((k >> kE2TabBits) << 20), __double2loint(p)) - 1.0;
 }
 
-// 1/x for a positive normal double: MUFU.RCP64H seed (20 bits) + two Newton steps; no special-case handling
-__device__ __forceinline__ double rcp_f64(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
 
 template <bool TAB>
 __device__ __forceinline__ void planck_quad_f64(const double4 *__restrict__ b4, int K2, double iA, double iB,
