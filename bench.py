@@ -73,6 +73,10 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi needs 0.1-1 s to attach on a fresh box: wait for its first line, or a short timed region sees "no samples"
+            deadline = time.perf_counter() + 5.
+            while not self.rows and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.01)
             time.sleep(settle)
         except OSError:
             self.proc = None

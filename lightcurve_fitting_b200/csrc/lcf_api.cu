@@ -448,7 +448,7 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const double K = std::max(1., p->mean_samples) * nbb;            // Planck samples per (walker, point)
     const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
     const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
-    double best = 1e300;
+    double best = 1e300, best_rank = 1e300;
     Shape bs = {5, 16, 1, 0, 0., 0, 1, 0};
     for (int l = 5; l >= 0; --l) {
         if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
@@ -513,7 +513,17 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                             flat = slots;
                         }
                     }
-                    if (cost < best * 0.97) { best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; bs.ks = ks; bs.nq = nq; bs.flat = flat; }
+                    // Look-ahead rounds of the persistent kernel (try_ring): a shape whose grid of ~3 Ns virtual walkers is co-resident with at
+                    // most two CTAs per SM runs a whole step in about the time of one half-step (measured on cfg1: 0.5-0.55 of two half-steps),
+                    // so among the shapes of a small ensemble it is worth more than its half-step cost says -- e.g. FP64, 100 walkers: one walker
+                    // x 8 warps (150 CTAs, two per SM) 6.2 M walker-steps/s with look-ahead rounds against 4.0 M for the half-step optimum
+                    // (clusters of two 8-warp CTAs: 300 CTAs do not fit).  A function of (problem, Ns) only, like the rest of the model.
+                    double rank = cost;
+                    {
+                        const long long ctas3 = ((3 * Ns + (1LL << l) - 1) >> l) * S;
+                        if (cost <= 120000. && ctas3 <= (long long)occ * sms && ctas3 <= 2LL * sms && !flat) rank *= 0.55;
+                    }
+                    if (rank < best_rank * 0.97) { best_rank = rank; best = cost; bs.l = l; bs.nw = nw; bs.cluster = S; bs.smem = sm; bs.ks = ks; bs.nq = nq; bs.flat = flat; }
                 }
             }
         }
