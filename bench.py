@@ -19,7 +19,7 @@ scaling); the accept epilogue of the half-step kernel stores accepted walkers in
 `cpu_baseline`  the oracle (numpy restatement of the reference) run the way the reference runs: a serial emcee-order
             stretch-move chain on one host core, bounded to ~15 s.
 `extras`    the rest of what BASELINE.json / north_star name, each with its own CUDA-event timing and clock sample:
-            fp64 (cfg2 in FP64 mode), sc4 (ShockCooling4 on the cfg2 shape), cfg1 (SN 2016bkv, 100 walkers), cfg3
+            fp64 (cfg2 in FP64 mode), sc4 (ShockCooling4 on the cfg2 shape), cfg1 (SN 2016bkv, 100 walkers; FP32 and FP64), cfg3
             (calculate_bolometric end to end, 500 epochs), cfg4 (CompanionShocking3, 10^4 walkers), cfg5 (survey batch);
             N > 1: multigpu_bit_identical (12-step chain against a single-GPU ensemble), strong scaling of cfg2 at 10^5
             walkers in total, cfg5 sharded over the GPUs with no collective.
@@ -506,9 +506,11 @@ def measure_small_configs(ctx):
     out = {}
     rng = np.random.default_rng(0)
     # cfg1: the reference's default use -- SN 2016bkv, ShockCooling4, 100 walkers x (1000 + 1000) steps
-    for window, tag in (((57468., 57485.), 'cfg1_early_window'), (None, 'cfg1_full')):
+    # (FP32 first; the *_fp64 entries are the same runs in the drop-in's default precision = the reference's arithmetic)
+    for window, tag, precision in (((57468., 57485.), 'cfg1_early_window', 'fp32'), (None, 'cfg1_full', 'fp32'),
+                                   ((57468., 57485.), 'cfg1_early_window_fp64', 'fp64'), (None, 'cfg1_full_fp64', 'fp64')):
         wl = synthetic.example_sc4(window=window)
-        prob = wl.device_problem('fp32')
+        prob = wl.device_problem(precision)
         s = EnsembleSampler(100, wl.ndim, prob, seed=1)
         p0 = wl.start(100, rng)
         s.run_mcmc(p0, 50, store=False)
@@ -524,11 +526,12 @@ def measure_small_configs(ctx):
         sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
         spe = wl.planck_samples_per_eval()
         v = 100 * 1000 / (ms * 1e-3)
-        out[tag] = {'workload': '%s: SN 2016bkv, ShockCooling4, N=%d points, 100 walkers, 1000+1000 steps' % (tag, len(wl.t)),
-                    'value': v, 'unit': 'walker-steps/s', 'us_per_half_step': 1e3 * ms / 2000., 'gpu_launches': s.last_launches,
+        out[tag] = {'workload': '%s: SN 2016bkv, ShockCooling4, N=%d points, 100 walkers, 1000+1000 steps, %s' % (tag, len(wl.t), precision),
+                    'dtype': 'f64' if precision == 'fp64' else 'f32', 'value': v, 'unit': 'walker-steps/s', 'us_per_half_step': 1e3 * ms / 2000., 'gpu_launches': s.last_launches,
                     'e2e': {'value': 100 * 2000 / dt, 'unit': 'walker-steps/s',
                             'includes': 'lightcurve_mcmc-shaped call: H2D start, burn-in, reset, sampling, flatchain D2H'},
-                    'roofline_frac': v * spe / (MUFU_LANES_PER_CLK_SM * SMS * sm_mhz * 1e6), 'launch': prob.last_launch(),
+                    'roofline_frac': v * spe / ((FP64_LANES_PER_CLK_SM / FP64_OPS_PER_SAMPLE if precision == 'fp64' else MUFU_LANES_PER_CLK_SM)
+                                                * SMS * sm_mhz * 1e6), 'launch': prob.last_launch(),
                     'acceptance': float(s.acceptance_fraction.mean()), 'finite': bool(np.isfinite(flat).all()), 'clocks': clk}
     # cfg4: CompanionShocking3, N = 1000, 10^4 walkers
     wl = synthetic.synthetic_cs3(kasen_sifto_truth, npoints=1000)
