@@ -459,7 +459,9 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
             const int ntiles = count_tiles(p, l + ks);
             const double Kc = K / (double)(1 << ks);
             const double pipe_tile = 64. * (f32 ? (Kc + 5.) / 14.5 : 0.9 * Kc + 4.);   // SM clocks per tile at full pipe rate
-            const double lat_tile = (f32 ? 70. : 600.) * Kc + 500. + (ks ? 60. * ks : 0.);   // clocks one warp needs for a tile on its own
+            // clocks one warp needs for a tile on its own.  FP64 from the split-K sweep of the look-ahead shape (cfg1, 1 walker x 8 warps:
+            // 2 / 4 / 8 sample chunks at 17.4 / 16.3 / 18.2 us per step): ~55 clocks per sample and ~4 300 per tile (its FP64 front end)
+            const double lat_tile = (f32 ? 70. * Kc + 500. : 60. * Kc + 4000.) + (ks ? 60. * ks : 0.);
             const int nw_cand[5] = {16, 8, 4, 2, g_tune_nw};   // candidates; the last entry is the override
             for (int ci = (g_tune_nw > 0 ? 4 : 0); ci < (g_tune_nw > 0 ? 5 : 4); ++ci) {
                 const int nw = nw_cand[ci];
