@@ -256,7 +256,9 @@ int  lcf_blackbody_lstsq_batch(int64_t nepochs, const int32_t *offsets, const do
    warps per CTA, cluster size, grid size in CTAs, and the kernel instantiation: 0 = generic k_pass<MODEL, real, -1, false>,
    1 = k_pass<MODEL, real, 5, false> (32 walkers per CTA at compile time), 2 = k_pass<MODEL, real, 5, true> (32 walkers, no
    intrinsic-scatter / model-grid branches), 3 = k_ring (persistent cooperative kernel for one small ensemble),
-   4 = k_ring with look-ahead rounds (one grid barrier per step: both outcomes of the partner's move are evaluated).      */
+   4 = k_ring with look-ahead rounds (one grid barrier per step: both outcomes of the partner's move are evaluated),
+   5 = k_pass_seg (a filter bank larger than shared memory, streamed through it in segments of consecutive filters; also forced,
+   for tests, by LCF_SEG_SAMPLES=<samples per segment> in the environment when the problem's first launch is shaped).      */
 int  lcf_problem_last_launch(lcf_problem *p, int *walkers_per_cta, int *warps_per_cta, int *cluster_size, int64_t *grid,
                              int *kernel_variant);
 

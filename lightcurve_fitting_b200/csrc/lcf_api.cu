@@ -128,7 +128,9 @@ struct lcf_problem {
     std::vector<int> h_point_filter;            // grouped by filter
     std::map<int, TileDev> tile_tabs;           // key = lanes-per-point exponent * 1024 + dealing period (0: natural order), see get_tiles
     std::vector<int> h_filter_records;          // pair records of every filter (tile cost)
-    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0, nq = 1; long long flat = 0; size_t smem = 0; double cost = 0.; } shape_cache;
+    struct { long long Ns = -1; int l = 0, nw = 0, cluster = 1, tune = -1, ks = 0, nq = 1, seg = 0; long long flat = 0; size_t smem = 0; double cost = 0.; } shape_cache;
+    int4 *d_segs = nullptr;                     // bank segments of a bank larger than shared memory (build_segments), else NULL
+    int nseg = 0, seg_samples = 0, seg_wpb = 0;  // segments, samples of the largest one, walkers per CTA they were sized for
     double mean_samples = 0.;                   // mean transmission samples per photometry point
     struct { int wpb = 0, nw = 0, cluster = 0, variant = -1, ks = 0, nq = 1, ppl = 2; long long grid = 0, groups = 0; } last_launch;   // lcf_problem_last_launch
     double *d_eval_q = nullptr, *d_eval_out = nullptr;   // evaluation scratch, grow-only (no cudaMalloc / cudaFree per call)
@@ -235,6 +237,7 @@ namespace {
 // kernel dispatch
 // -----------------------------------------------------------------------------------------
 typedef void (*PassKernel)(const ProblemDev, const TileDev, const MoveDev);
+typedef void (*SegKernel)(const ProblemDev, const TileDev, const MoveDev, const SegDev);
 typedef void (*ChainKernel)(const BatchDev);
 typedef void (*RingKernel)(const ProblemDev, const TileDev, const RingDev);
 
@@ -247,6 +250,7 @@ template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool pla
     if (l == 5) return plain ? k_pass<LCF_DEV_ONLY_MODEL, R, 5, true> : k_pass<LCF_DEV_ONLY_MODEL, R, 5, false>;
     return k_pass<LCF_DEV_ONLY_MODEL, R, -1, false>;
 }
+template <typename R> SegKernel seg_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_pass_seg<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 template <typename R> ChainKernel chain_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_chain<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 template <typename R> RingKernel ring_kernel_for(int model) { return model == LCF_DEV_ONLY_MODEL ? k_ring<LCF_DEV_ONLY_MODEL, R> : nullptr; }
 #else
@@ -264,6 +268,19 @@ template <typename R> PassKernel pass_kernel_for(int model, int l = -1, bool pla
         LCF_PASS_CASE(5) LCF_PASS_CASE(6) LCF_PASS_CASE(7) LCF_PASS_CASE(8)
     }
 #undef LCF_PASS_CASE
+    return nullptr;
+}
+template <typename R> SegKernel seg_kernel_for(int model) {           // bank streamed in segments (larger than shared memory)
+    switch (model) {
+        case 1: return k_pass_seg<1, R>;
+        case 2: return k_pass_seg<2, R>;
+        case 3: return k_pass_seg<3, R>;
+        case 4: return k_pass_seg<4, R>;
+        case 5: return k_pass_seg<5, R>;
+        case 6: return k_pass_seg<6, R>;
+        case 7: return k_pass_seg<7, R>;
+        case 8: return k_pass_seg<8, R>;
+    }
     return nullptr;
 }
 template <typename R> ChainKernel chain_kernel_for(int model) {
@@ -294,11 +311,13 @@ template <typename R> RingKernel ring_kernel_for(int model) {
 }
 #endif
 
-size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxCluster, int nq = 1) {
+// nsamples >= 0: bank slice of that many samples staged at a time (segmented launches) instead of the whole bank
+size_t smem_bytes(const lcf_problem *p, int wpb, int nw, int ncluster = kMaxCluster, int nq = 1, int nsamples = -1) {
     const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
+    const int ns = nsamples >= 0 ? nsamples : p->dev.nsamples;
     if (p->precision == LCF_PRECISION_FP32)
-        return SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
-    return SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
+        return SmemLayout<float>(ns, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
+    return SmemLayout<double>(ns, p->dev.nfilters, wpb, nw, p->dev.ndim, p->dev.model == 3, nspl, ncluster, nq).total;
 }
 
 constexpr int kSplitUnits = 8;        // units of the structured chi-square sums (MoveDev::nq) of the shapes that use them
@@ -420,6 +439,7 @@ struct Shape {
     int l, nw, cluster; size_t smem; double cost; int ks;
     int nq;             // units of the structured chi-square sums: kSplitUnits for unsplit shapes whose warps have >= 2 nq tile rows, else 1
     long long flat;     // > 0: launch this many CTAs, each with the same share of the (group, unit) space (needs the caller's scratch)
+    int seg;            // > 0: the bank is streamed through shared memory in segments of at most this many samples (k_pass_seg)
 };
 
 bool sum_units_enabled() {                 // LCF_SUM_UNITS=1 (experiments): plain per-warp sums everywhere, no flat split
@@ -433,14 +453,60 @@ int flat_mode() {                          // lcf_set_tuning_flat, else LCF_FLAT
     return env;
 }
 
+// A filter bank larger than shared memory (FP64: ~14 000 transmission samples, e.g. a light curve through many JWST / GALEX
+// filters) is streamed: runs of consecutive filters whose pair records (and, ShockCooling3, per-walker weight table) fit next to
+// the per-walker state of a fixed small shape (8 walkers x 8 warps; ShockCooling3: 4 walkers).  `force` (LCF_SEG_SAMPLES, tests):
+// at most that many samples per segment whatever fits.  Built once per problem.
+int build_segments(lcf_problem *p, int force, Shape *bs) {
+    const bool f32 = p->precision == LCF_PRECISION_FP32;
+    const int l = p->dev.model == 3 ? 2 : 3, nw = 8, wpb = 1 << l;
+    if (!p->d_segs) {
+        const size_t fixed = smem_bytes(p, wpb, nw, kMaxCluster, 1, 0);
+        const size_t per_sample = (f32 ? 4 : 8) * (size_t)(2 + (p->dev.model == 3 ? wpb : 0));
+        if (fixed + 256 > kSmemMax) return fail(LCF_ERR_ARG, "too many filters for shared memory");
+        long long cap = (long long)((kSmemMax - fixed - 256) / per_sample) & ~1LL;     // samples per segment (256 B: alignment of the carve-up)
+        int widest = 0;
+        for (int r : p->h_filter_records) widest = std::max(widest, 2 * r);
+        if (force > 0) cap = std::min<long long>(cap, std::max(force & ~1, widest));
+        if (widest > cap)
+            return fail(LCF_ERR_ARG, "one filter has %d transmission samples, more than the %lld that fit in shared memory", widest, cap);
+        std::vector<int4> segs;
+        int f0 = 0, pair0 = 0, pairs = 0, most = 0;
+        const int F = (int)p->h_filter_records.size();
+        for (int f = 0; f < F; ++f) {
+            const int r = p->h_filter_records[f];
+            if (f > f0 && 2LL * (pairs + r) > cap) {
+                segs.push_back(make_int4(f0, f, pair0, pairs));
+                f0 = f; pair0 += pairs; pairs = 0;
+            }
+            pairs += r;
+            most = std::max(most, 2 * pairs);
+        }
+        segs.push_back(make_int4(f0, F, pair0, pairs));
+        int4 *d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, segs.size() * sizeof(int4)));
+        p->allocs.push_back(d);
+        CUDA_TRY(cudaMemcpy(d, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        p->d_segs = d; p->nseg = (int)segs.size(); p->seg_samples = most; p->seg_wpb = wpb;
+    }
+    bs->l = l; bs->nw = nw; bs->cluster = 1; bs->ks = 0; bs->nq = 1; bs->flat = 0; bs->seg = p->seg_samples;
+    bs->smem = smem_bytes(p, wpb, nw, kMaxCluster, 1, p->seg_samples);
+    bs->cost = 1e12;                                       // never a candidate for the persistent / look-ahead kernels
+    if (bs->smem > kSmemMax) return fail(LCF_ERR_STATE, "segmented bank does not fit (%zu bytes)", bs->smem);
+    return 0;
+}
+
 int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const int g_flat = flat_mode();
     const int tune = (((g_tune_wpb * 64 + g_tune_nw) * 16 + g_tune_cluster) * 8 + (g_tune_ks + 1)) * 4 + (g_flat + 1);
     if (p->shape_cache.Ns == Ns && p->shape_cache.tune == tune) {
         out->l = p->shape_cache.l; out->nw = p->shape_cache.nw; out->cluster = p->shape_cache.cluster; out->smem = p->shape_cache.smem;
         out->cost = p->shape_cache.cost; out->ks = p->shape_cache.ks; out->nq = p->shape_cache.nq; out->flat = p->shape_cache.flat;
+        out->seg = p->shape_cache.seg;
         return 0;
     }
+    int force_seg = 0;
+    if (const char *e = getenv("LCF_SEG_SAMPLES")) force_seg = atoi(e);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     const bool f32 = p->precision == LCF_PRECISION_FP32;
@@ -449,8 +515,8 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     const double pipe_tile = 64. * (f32 ? (K + 5.) / 14.5 : 0.9 * K);    // SM clocks per tile at full pipe rate
     const double lat_tile = (f32 ? 70. : 600.) * K + 500.;           // clocks one warp needs for a tile on its own
     double best = 1e300, best_rank = 1e300;
-    Shape bs = {5, 16, 1, 0, 0., 0, 1, 0};
-    for (int l = 5; l >= 0; --l) {
+    Shape bs = {5, 16, 1, 0, 0., 0, 1, 0, 0};
+    for (int l = 5; l >= 0 && force_seg <= 0; --l) {
         if (g_tune_wpb > 0 && (1 << l) != g_tune_wpb) continue;
         const long long groups = (Ns + (1 << l) - 1) >> l;
         // split-K: 2^ks lanes share a (walker, point pair) and each sweeps 1/2^ks of the filter's samples (front end repeated)
@@ -530,12 +596,17 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
             }
         }
     }
+    int rc = 0;
     if (best >= 1e300) {
         if (g_tune_nw > 16 || g_tune_wpb > 32) return fail(LCF_ERR_ARG, "bad tuning override");
-        return fail(LCF_ERR_ARG, "filter bank needs more than %zu bytes of shared memory: too many transmission samples", kSmemMax);
+        if ((rc = build_segments(p, force_seg, &bs))) return rc;      // the bank does not fit in shared memory: stream it
+        best = bs.cost;
+        const bool f32s = p->precision == LCF_PRECISION_FP32;
+        SegKernel k = f32s ? seg_kernel_for<float>(p->dev.model) : seg_kernel_for<double>(p->dev.model);
+        if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
+        if ((rc = ensure_dynamic_smem(reinterpret_cast<const void *>(k), bs.smem))) return rc;
     }
-    int rc = 0;
-    for (int plain = 0; plain < 2; ++plain) {
+    for (int plain = 0; plain < 2 && !bs.seg; ++plain) {
         const int ppl = points_per_lane(p, bs.l, plain != 0);
         PassKernel k = f32 ? pass_kernel_for<float>(p->dev.model, bs.l, plain, ppl) : pass_kernel_for<double>(p->dev.model, bs.l, plain, ppl);
         if (!k) return fail(LCF_ERR_ARG, "unknown model id %d", p->dev.model);
@@ -543,11 +614,11 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
     }
     p->shape_cache.Ns = Ns; p->shape_cache.l = bs.l; p->shape_cache.nw = bs.nw; p->shape_cache.cluster = bs.cluster;
     p->shape_cache.smem = bs.smem; p->shape_cache.tune = tune; p->shape_cache.cost = best; p->shape_cache.ks = bs.ks;
-    p->shape_cache.nq = bs.nq; p->shape_cache.flat = bs.flat;
+    p->shape_cache.nq = bs.nq; p->shape_cache.flat = bs.flat; p->shape_cache.seg = bs.seg;
     bs.cost = best;
     if (getenv("LCF_DEBUG_SHAPE"))
-        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, split-K %d, %d sum units, flat grid %lld, %zu B smem (model %d, modelled %.0f clk)\n",
-                Ns, 1 << bs.l, bs.nw, bs.cluster, 1 << bs.ks, bs.nq, bs.flat, bs.smem, p->dev.model, best);
+        fprintf(stderr, "[lcf] launch shape for %lld walkers: %d walkers/CTA, %d warps, cluster %d, split-K %d, %d sum units, flat grid %lld, %zu B smem, %d bank segment(s) (model %d, modelled %.0f clk)\n",
+                Ns, 1 << bs.l, bs.nw, bs.cluster, 1 << bs.ks, bs.nq, bs.flat, bs.smem, bs.seg ? p->nseg : 1, p->dev.model, best);
     *out = bs;
     return 0;
 }
@@ -563,14 +634,15 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     mv.nq = sh.nq;
     {
         const int nspl = (p->dev.model >= 5 && p->dev.model <= 7) ? p->dev.nfilters * p->dev.spl_nint : 0;
+        const int ns = sh.seg ? sh.seg : p->dev.nsamples;
         if (p->precision == LCF_PRECISION_FP32)
-            mv.lay = SmemLayout<float>(p->dev.nsamples, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
+            mv.lay = SmemLayout<float>(ns, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
         else
-            mv.lay = SmemLayout<double>(p->dev.nsamples, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
+            mv.lay = SmemLayout<double>(ns, p->dev.nfilters, 1 << sh.l, sh.nw, p->dev.ndim, p->dev.model == 3, nspl, kMaxCluster, sh.nq);
         if (mv.lay.total != sh.smem) return fail(LCF_ERR_STATE, "shared-memory layout mismatch");
     }
-    const bool plain = mv.mode != MODE_MODEL && !p->dev.use_sigma;
-    const int ppl = points_per_lane(p, sh.l, plain);
+    const bool plain = !sh.seg && mv.mode != MODE_MODEL && !p->dev.use_sigma;
+    const int ppl = sh.seg ? 2 : points_per_lane(p, sh.l, plain);
     PassKernel k = (p->precision == LCF_PRECISION_FP32) ? pass_kernel_for<float>(p->dev.model, sh.l, plain, ppl)
                                                         : pass_kernel_for<double>(p->dev.model, sh.l, plain, ppl);
     const long long ngroups = (mv.Ns + (1 << sh.l) - 1) / (1 << sh.l);
@@ -602,9 +674,15 @@ int launch_pass(lcf_problem *p, const MoveDev &mv_in, cudaStream_t stream, long 
     cfg.numAttrs = na;
     TileDev tiles;
     if ((rc = get_tiles(p, sh.l + sh.ks, sh.nw * sh.cluster, &tiles, ppl))) return rc;
+    if (sh.seg) {
+        SegKernel ksg = (p->precision == LCF_PRECISION_FP32) ? seg_kernel_for<float>(p->dev.model) : seg_kernel_for<double>(p->dev.model);
+        SegDev sd;
+        sd.segs = p->d_segs; sd.nseg = p->nseg;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ksg, p->dev, tiles, mv, sd));
+    } else
     CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p->dev, tiles, mv));
     p->last_launch.wpb = 1 << sh.l; p->last_launch.nw = sh.nw; p->last_launch.cluster = sh.cluster; p->last_launch.ks = sh.ks;
-    p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.l == 5 ? (plain ? 2 : 1) : 0;
+    p->last_launch.grid = clusters * sh.cluster; p->last_launch.variant = sh.seg ? 5 : (sh.l == 5 ? (plain ? 2 : 1) : 0);
     p->last_launch.nq = sh.nq; p->last_launch.groups = ngroups; p->last_launch.ppl = ppl;
     if (launches) ++*launches;
     return 0;
@@ -1380,6 +1458,7 @@ static int try_ring(lcf_ensemble *e, long long nsteps, int store, bool *used) {
     Shape sh;
     int rc = choose_shape(p, std::max(e->n0, e->n1), &sh);
     if (rc) return rc;
+    if (sh.seg) return 0;                                                    // segmented bank: half-step launches only
     if (sh.flat > 0) return 0;                                               // a flat split is a large ensemble by construction
     if (points_per_lane(p, sh.l, !p->dev.use_sigma) != 2) return 0;          // k_ring runs the two-points-per-lane code: same arithmetic as the launches it replaces
     if (!(env && (env[0] == '1' || env[0] == '2')) && sh.cost > 120000.) return 0;   // > ~60 us per half-step: launch latency is already hidden

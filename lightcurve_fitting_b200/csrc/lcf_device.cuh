@@ -1170,10 +1170,14 @@ template <typename R> struct SmemLayout : SmemOffsets {
 // PLAIN: the launch is a move / log-posterior / log-likelihood pass without the intrinsic-scatter term (the reference's default):
 // the per-tile mode and use_sigma branches are compiled out.
 // PPL: photometry points per lane and tile (2; 4 in the 32-walker plain FP32 kernels of the one-blackbody models, see planck_quad4_f32).
-template <int MODEL, typename R, int WL = -1, bool PLAIN = false, int PPL = 2>
+// SEG: the filter bank does not fit in shared memory (k_pass_seg): `segs` lists runs of consecutive filters, (first filter, end filter,
+// first pair record, pair records), whose slices of the bank do; the group sweeps the light curve once per segment with that slice
+// (and, ShockCooling3, its weight table) staged, taking the tiles of the segment's filters.  Each warp still meets its tiles in table
+// order, so the chi-square sums are those of an unsegmented launch of the same shape, bit for bit.
+template <int MODEL, typename R, int WL = -1, bool PLAIN = false, int PPL = 2, bool SEG = false>
 __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &TL, const MoveDev &Mv, long long g,
                                            unsigned char *smem, const SmemLayout<R> &L, bool need_stage, int crank, int csize,
-                                           int q_lo = 0, int q_hi = 1) {
+                                           int q_lo = 0, int q_hi = 1, const int4 *segs = nullptr, int nseg = 1) {
     typedef typename Vec2<R>::type R2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int wl2 = WL >= 0 ? WL : Mv.wpb_log2;
@@ -1201,10 +1205,10 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     // ---- phase 0: stage the packed filter bank with one TMA bulk copy -------------------
     if (need_stage) {
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)((size_t)(P.nsamples >> 1) * sizeof(R4));
+            const uint32_t bytes = SEG ? 0u : (uint32_t)((size_t)(P.nsamples >> 1) * sizeof(R4));
             const uint32_t sbytes = (MODEL >= 5 && MODEL <= 7) ? (uint32_t)((size_t)P.nfilters * P.spl_nint * sizeof(R4)) : 0u;
             mbar_expect_tx(s_bar, bytes + sbytes);
-            tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
+            if (!SEG) tma_bulk_g2s(s_bank, P.bank, bytes, s_bar);
             if (sbytes) tma_bulk_g2s(smem + L.off_spl, P.spl, sbytes, s_bar);
         }
         for (int i = tid; i < P.nfilters; i += blockDim.x) s_finfo[i] = P.finfo[i];
@@ -1300,9 +1304,9 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
 
     const int tstride = WL == 5 ? kTabStride : (wpb < 32 ? wpb : 32);     // weight-table columns
     // ShockCooling3: per-walker reddened weights  w_k 10^(-0.4 ebv kappa_k)  (filters.py:32-33), pair layout
-    if (MODEL == 3) {
-        const R *kap = reinterpret_cast<const R *>(P.kappa);
-        const int n = (P.nsamples >> 1) * wpb;
+    auto build_tab = [&](int npairs, int pair0) {          // pair0: first pair record of the staged slice (0: the whole bank)
+        const R *kap = reinterpret_cast<const R *>(P.kappa) + 2 * (size_t)pair0;
+        const int n = npairs * wpb;
         for (int idx = tid; idx < n; idx += blockDim.x) {
             const int kp = idx >> wl2, wl = idx & (wpb - 1);
             const R ebv = s_wc[wl * kNumWC + 3];
@@ -1313,7 +1317,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             s_tab[kp * tstride + wl] = v;
         }
         __syncthreads();
-    }
+    };
+    if (MODEL == 3 && !SEG) build_tab(P.nsamples >> 1, 0);
     LCF_TICK(2);
 
     // ---- phase 2: tiles (each lane: up to two points of the tile's filter) ----------------
@@ -1340,10 +1345,22 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
     const int nq = Mv.nq > 1 ? Mv.nq : 1;
     R *s_qpart = reinterpret_cast<R *>(smem + L.off_part);
     R chi = 0;
+    int seg_f0 = 0, seg_f1 = 0, seg_pair0 = 0;
+    for (int sg = 0; sg < (SEG ? nseg : 1); ++sg) {
+    if constexpr (SEG) {                                   // stage the bank slice of segment sg (fallback path: a plain cooperative copy)
+        const int4 s = __ldg(segs + sg);
+        __syncthreads();                                   // every warp is done with the previous slice
+        const R4 *gb = reinterpret_cast<const R4 *>(P.bank) + s.z;
+        for (int i = tid; i < s.w; i += blockDim.x) s_bank[i] = gb[i];
+        seg_f0 = s.x; seg_f1 = s.y; seg_pair0 = s.z;
+        __syncthreads();
+        if (MODEL == 3) build_tab(s.w, s.z);
+    }
     for (int q = q_lo; q < q_hi; ++q) {
     if (nq > 1) chi = 0;
     for (int tile = (q * csize + crank) * nstripes + stripe; tile < TL.ntiles; tile += nstripes * csize * nq) {
         const int4 tl = __ldg(tiles + tile);                 // (first point, count, filter, -)
+        if (SEG && (tl.z < seg_f0 || tl.z >= seg_f1)) continue;    // (warp-uniform)
         const bool active = !skip && slot < tl.y;
         const unsigned amask = ks ? __ballot_sync(0xffffffffu, active) : 0u;    // the chunk lanes of a point pair are active together
         if constexpr (PPL == 4 && sizeof(R) == 4) {
@@ -1384,7 +1401,8 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
             const int pb = two ? pa + ppt : pa;
             // observed values first: their (L1-resident) loads overlap the front end and the inner loop
             const R4 oa = pobs[pa], ob = pobs[pb];
-            const int4 fi = s_finfo[tl.z];
+            int4 fi = s_finfo[tl.z];
+            if (SEG) fi.x -= seg_pair0;                          // pair records are addressed within the staged slice
             PointFE<R> fa, fb;
             R adda, addb;
             front_end<MODEL, R>(P, lw, pa, fa.invT, fa.amp, adda, s_spl, s_e2t);      // branch-free: the two MUFU chains interleave
@@ -1433,6 +1451,7 @@ __device__ __forceinline__ void group_pass(const ProblemDev &P, const TileDev &T
         double cq = (double)chi;
         for (int off = 16; off >= wpb; off >>= 1) cq += __shfl_xor_sync(0xffffffffu, cq, off);
         if (lane < wpb) s_qpart[((q - q_lo) * nw + warp) * wpb + lane] = (R)cq;
+    }
     }
     }
     LCF_TICK(3);
@@ -1589,6 +1608,37 @@ __global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass(const Pr
 #ifdef LCF_X_TIMING
     if (threadIdx.x == 0 && blockIdx.x < 4096) { g_cta_log[3 * blockIdx.x] = t_cta0; g_cta_log[3 * blockIdx.x + 1] = gtimer(); g_cta_log[3 * blockIdx.x + 2] = smid(); }
 #endif
+    if (Mv.npeers) peers_publish(Mv);
+}
+
+// ---------------------------------------------------------------------------------------
+// Kernel A', the fallback of kernel A for a filter bank larger than shared memory (many densely sampled JWST / GALEX curves in one
+// light curve, FP64): the bank is streamed through shared memory in segments of consecutive filters (group_pass<SEG>).  Same
+// parameter block, same proposal / accept code and peer exchange as k_pass; one CTA per walker group, no cluster, plain sums.
+// ---------------------------------------------------------------------------------------
+struct SegDev {
+    const int4 *segs;                // [nseg] (first filter, end filter, first pair record, pair records)
+    int nseg;
+};
+
+template <int MODEL, typename R>
+__global__ void __launch_bounds__(512, (sizeof(R) == 4 ? 2 : 1)) k_pass_seg(const ProblemDev P, const TileDev TL, const MoveDev Mv, const SegDev S) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wpb = 1 << Mv.wpb_log2;
+    const SmemLayout<R> L(Mv.lay);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (sizeof(R) == 8) stage_e2tab(reinterpret_cast<double *>(smem + L.off_e2t));
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    const long long ngroups = (Mv.Ns + wpb - 1) / wpb;
+    if (Mv.npeers) peers_wait(Mv);
+    bool first = true;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        group_pass<MODEL, R, -1, false, 2, true>(P, TL, Mv, g, smem, L, first, 0, 1, 0, 1, S.segs, S.nseg);
+        first = false;
+    }
     if (Mv.npeers) peers_publish(Mv);
 }
 

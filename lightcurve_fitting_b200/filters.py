@@ -74,7 +74,8 @@ def fitzpatrick99(wave, a_v, r_v=3.1):
     uv = x >= 1e4 / 2700.
     k = np.empty_like(x)
     k[uv] = _f99_uv(x[uv], c1_, c2_)
-    k[~uv] = splev(x[~uv], _f99_cache[r_v])
+    if not uv.all():                       # fitpack rejects an empty array (a curve entirely below 2700 A: GALEX FUV)
+        k[~uv] = splev(x[~uv], _f99_cache[r_v])
     return a_v / r_v * (k + r_v)
 
 

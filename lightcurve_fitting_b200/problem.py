@@ -166,7 +166,7 @@ class DeviceProblem:
         check(lib().lcf_problem_last_launch_ex(self.handle, C.byref(ng), C.byref(nq), C.byref(ppl)))
         return {'walkers_per_cta': a.value, 'warps_per_cta': b.value, 'cluster': c.value, 'grid': g.value,
                 'groups': ng.value, 'sum_units': nq.value, 'points_per_lane': ppl.value, 'flat': v.value != 3 and g.value != ng.value * c.value,
-                'kernel': {0: 'k_pass<generic>', 1: 'k_pass<32 walkers>', 2: 'k_pass<32 walkers, plain>', 3: 'k_ring', 4: 'k_ring<look-ahead>'}[v.value]}
+                'kernel': {0: 'k_pass<generic>', 1: 'k_pass<32 walkers>', 2: 'k_pass<32 walkers, plain>', 3: 'k_ring', 4: 'k_ring<look-ahead>', 5: 'k_pass_seg'}[v.value]}
 
     # -- evaluation entry points ----------------------------------------------------------
     def model_eval(self, params):

@@ -1373,3 +1373,98 @@ def test_flat_split_chains_are_bit_identical_to_one_group_per_cta(name, nw, shap
     for a, b in zip(out[0], out[1]):
         np.testing.assert_array_equal(a, b)
     _check_chain_rows_against_oracle(wl, out[1][0], out[1][1], precision, 8, 3)
+
+
+# ---- filter banks larger than shared memory: streamed in segments of consecutive filters (k_pass_seg) ------------------------------
+_SEG_CASES = {
+    'sc4_example': ('fp32', 120), 'sc4_example_sigma_abs': ('fp64', 64), 'sc3_synth_sigma': ('fp32', 100), 'sc3_synth': ('fp64', 150),
+    'cs3_synth': ('fp64', 90), 'sed': ('fp32', 50),
+}
+
+
+@pytest.mark.parametrize('name', sorted(_SEG_CASES))
+def test_segmented_bank_is_bit_identical_to_the_unsegmented_launch(name, monkeypatch):
+    """LCF_SEG_SAMPLES forces the fallback of a bank larger than shared memory on an ordinary problem: the bank slices of a few
+    filters at a time are staged in turn and every warp still meets its tiles in table order, so log-posteriors, model grids and
+    whole chains are those of the unsegmented launch of the same shape bit for bit -- and the oracle's within the tolerance."""
+    from lightcurve_fitting_b200._capi import lib, check
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    precision, cap = _SEG_CASES[name]
+    wl = WORKLOADS[name]()
+    shape = (4, 8, 1) if wl.model_name == 'ShockCooling3' else (8, 8, 1)       # the fixed shape of the segmented launches
+    P = _params(wl, 37, 3, widen=0.1)
+    p0 = wl.start(50, np.random.default_rng(2))
+    monkeypatch.setenv('LCF_RING', '0')                                          # half-step launches on both sides
+    out = {}
+    for seg in (True, False):
+        if seg:
+            monkeypatch.setenv('LCF_SEG_SAMPLES', str(cap))
+        else:
+            monkeypatch.delenv('LCF_SEG_SAMPLES')
+            check(lib().lcf_set_tuning_ex(*shape))
+            check(lib().lcf_set_tuning_split(1))
+        try:
+            prob = wl.device_problem(precision)
+            lp = prob.log_posterior(P)
+            ll = prob.last_launch()
+            grid = prob.model_eval(P[:5, :prob.nmodel] if hasattr(prob, 'nmodel') else P[:5])
+            s = EnsembleSampler(50, wl.ndim, prob, seed=17)
+            s.run_mcmc(p0, 6)
+            out[seg] = (lp, grid, s.get_chain(), s.get_log_prob(), s.acceptance_fraction, ll, prob.last_launch())
+        finally:
+            check(lib().lcf_set_tuning_ex(0, 0, 0))
+            check(lib().lcf_set_tuning_split(0))
+    assert out[True][5]['kernel'] == 'k_pass_seg' and out[True][6]['kernel'] == 'k_pass_seg'
+    assert out[False][5]['kernel'] == 'k_pass<generic>'
+    for k in ('walkers_per_cta', 'warps_per_cta', 'cluster', 'sum_units'):
+        assert out[True][5][k] == out[False][5][k], k
+    for k in range(5):
+        np.testing.assert_array_equal(out[True][k], out[False][k])
+    lpo = W.oracle_log_posterior(wl)
+    want = np.array([lpo(p) for p in P])
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(want), np.isneginf(out[True][0]))
+    np.testing.assert_allclose(out[True][0][fin], want[fin], rtol=RTOL[precision])
+
+
+@pytest.mark.parametrize('model', ['ShockCooling4', 'ShockCooling3'])
+def test_filter_bank_larger_than_shared_memory_fp64(model):
+    """A light curve through the 30 most densely sampled filters of the registry (JWST MIRI / NIRCam, GALEX, Flamingos-2 ...:
+    > 17 000 transmission samples, 16 B each in FP64) does not fit in the 227 KB of shared memory of an SM: the reference has
+    no such limit (filters.py:296-335 integrates whatever it is given), so the library streams the bank (round 1: LCF_ERR_ARG)."""
+    from lightcurve_fitting_b200.synthetic import Workload
+    from lightcurve_fitting_b200.sampler import EnsembleSampler
+    names = ['F2550W', 'F2100W', 'NUV', 'F1800W', 'F444W', 'Itagaki', 'F356W', 'F1500W', 'F277W', 'K', 'H', 'Kepler', 'F200W', 'F1280W',
+             'TESS', 'F335M', 'F360M', 'F770W', 'F1000W', 'FUV', 'w', 'F300M', 'F150W', 'UVW1', 'J', 'r-DECam', 'U', 'B', 'g', 'i']
+    rng = np.random.default_rng(21)
+    n = 2 * len(names) + 7
+    t0 = 59000.
+    t = np.sort(rng.uniform(t0 + 0.3, t0 + 12., n))
+    fn = [names[i % len(names)] for i in range(n)]
+    if model == 'ShockCooling3':
+        p_true = np.array([1., 1., 1., 3., 20., 0.1, t0])
+        pri = [('uniform', 0., 10.), ('uniform', 0., 10.), ('uniform', 0., 100.), ('uniform', 0., 100.), ('uniform', 5., 50.),
+               ('uniform', 0., 1.), ('uniform', t0 - 2., t0 + 0.3)]
+        tcol = 6
+    else:
+        p_true = np.array([1., 1., 1., 3., t0])
+        pri = [('uniform', 0., 10.), ('uniform', 0., 10.), ('uniform', 0., 100.), ('uniform', 0., 100.), ('uniform', t0 - 2., t0 + 0.3)]
+        tcol = 4
+    ytrue = W.oracle_truth(model, t, fn, p_true, 0.005)
+    dy = 0.05 * ytrue
+    y = ytrue + dy * rng.normal(size=n)
+    lo, hi = p_true * 0.9, p_true * 1.1
+    lo[tcol], hi[tcol] = t0 - 0.1, t0 + 0.1
+    wl = Workload('large-bank-' + model, model, t, fn, y, dy, pri, lo, hi, z=0.005, truth=p_true)
+    prob = wl.device_problem('fp64')
+    _check_logpost(wl, 'fp64', n=24, seed=6, widen=0.05)
+    got = prob.log_posterior(_params(wl, 24, 6, 0.05))
+    assert prob.last_launch()['kernel'] == 'k_pass_seg'
+    lpo = W.oracle_log_posterior(wl)
+    s = EnsembleSampler(64, wl.ndim, prob, seed=4)
+    s.run_mcmc(wl.start(64, rng), 5)
+    assert prob.last_launch()['kernel'] == 'k_pass_seg'
+    chain, lnp = s.get_chain(), s.get_log_prob()
+    for (i, j) in ((0, 3), (2, 40), (4, 63), (4, 0)):
+        np.testing.assert_allclose(lnp[i, j], lpo(chain[i, j]), rtol=RTOL['fp64'])
+    assert (s.acceptance_fraction > 0).any()

@@ -87,6 +87,10 @@ def test_extinction_law_matches_oracle():
     assert np.all(np.diff(F.fitzpatrick99(wave[wave > 2300.], 1.)) < 0)         # monotonic redward of the bump
     # known answer at the 5470 A spline knot: A = a_v + (-5.13540e-2 + 1.00216 r_v - 7.35778e-5 r_v^2 - r_v) for r_v = a_v = 3.1
     np.testing.assert_allclose(F.fitzpatrick99(np.array([5470.]), 3.1), 3.1 + (-5.13540e-2 + 1.00216 * 3.1 - 7.35778e-5 * 9.61 - 3.1), rtol=1e-12)
+    # a curve entirely in the ultraviolet (GALEX FUV, 1340-1810 A) or entirely redward of 2700 A: no empty array reaches fitpack
+    fuv = np.linspace(1340., 1810., 7)
+    np.testing.assert_allclose(F.fitzpatrick99(fuv, 0.31), rp.fitzpatrick99(fuv, 0.31), rtol=1e-14)
+    assert np.all(F.fitzpatrick99(fuv, 0.31) > 0.6) and np.all(F.fitzpatrick99(np.array([2.5e5]), 0.31) < 0.01)
     freq = np.array([400., 600., 900.])
     np.testing.assert_allclose(F.extinction_law(freq, 0.), 1.)
 
