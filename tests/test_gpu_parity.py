@@ -598,13 +598,18 @@ def test_sharded_ensemble_emulated_two_ranks_matches_single():
     check(lib().lcf_set_tuning(0, 0))
 
 
-def test_fused_peer_exchange_two_ranks_one_device_matches_single():
+@pytest.mark.parametrize('segmented', [False, True])
+def test_fused_peer_exchange_two_ranks_one_device_matches_single(segmented, monkeypatch):
     """The fused exchange (accept epilogue stores into the peer replica, device-side half-step flags) on two
-    rank-ensembles of one process: chains bit-identical to the single-ensemble run, replicas identical at the end."""
+    rank-ensembles of one process: chains bit-identical to the single-ensemble run, replicas identical at the end.
+    segmented: the same through k_pass_seg (bank streamed in segments, forced with LCF_SEG_SAMPLES), which shares the protocol."""
     import ctypes as C
     from lightcurve_fitting_b200._capi import lib, check
     from lightcurve_fitting_b200.sampler import EnsembleSampler
     wl = W.synthetic_sc3(npoints=96)
+    if segmented:
+        monkeypatch.setenv('LCF_SEG_SAMPLES', '100')
+        monkeypatch.setenv('LCF_RING', '0')
     prob = wl.device_problem('fp32')
     nw, nsteps = 64, 8
     check(lib().lcf_set_tuning_ex(8, 4, 1))
@@ -612,6 +617,7 @@ def test_fused_peer_exchange_two_ranks_one_device_matches_single():
         p0 = wl.start(nw, np.random.default_rng(2))
         single = EnsembleSampler(nw, wl.ndim, prob, seed=42)
         single.run_mcmc(p0, nsteps, skip_initial_state_check=True)
+        assert (prob.last_launch()['kernel'] == 'k_pass_seg') == segmented
         ranks = [EnsembleSampler(nw, wl.ndim, prob, seed=42, rank=r, world=2) for r in range(2)]
         coords, logps, flags = (C.c_void_p * 2)(), (C.c_void_p * 2)(), (C.c_void_p * 2)()
         for r, s in enumerate(ranks):
