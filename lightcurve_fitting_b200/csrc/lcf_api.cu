@@ -455,11 +455,12 @@ int flat_mode() {                          // lcf_set_tuning_flat, else LCF_FLAT
 
 // A filter bank larger than shared memory (FP64: ~14 000 transmission samples, e.g. a light curve through many JWST / GALEX
 // filters) is streamed: runs of consecutive filters whose pair records (and, ShockCooling3, per-walker weight table) fit next to
-// the per-walker state of a fixed small shape (8 walkers x 8 warps; ShockCooling3: 4 walkers).  `force` (LCF_SEG_SAMPLES, tests):
+// the per-walker state of a fixed small shape (8 walkers x 16 warps; ShockCooling3: 4 walkers).  `force` (LCF_SEG_SAMPLES, tests):
 // at most that many samples per segment whatever fits.  Built once per problem.
 int build_segments(lcf_problem *p, int force, Shape *bs) {
     const bool f32 = p->precision == LCF_PRECISION_FP32;
-    const int l = p->dev.model == 3 ? 2 : 3, nw = 8, wpb = 1 << l;
+    static const int env_nw = [] { const char *e = getenv("LCF_SEG_WARPS"); const int v = e ? atoi(e) : 0; return v == 4 || v == 8 || v == 16 ? v : 0; }();   // (experiments)
+    const int l = p->dev.model == 3 ? 2 : 3, nw = env_nw ? env_nw : 16, wpb = 1 << l;   // (16 warps: +18 % over 8 on the 30-filter FP64 case)
     if (!p->d_segs) {
         const size_t fixed = smem_bytes(p, wpb, nw, kMaxCluster, 1, 0);
         const size_t per_sample = (f32 ? 4 : 8) * (size_t)(2 + (p->dev.model == 3 ? wpb : 0));

@@ -1397,7 +1397,7 @@ def test_segmented_bank_is_bit_identical_to_the_unsegmented_launch(name, monkeyp
     from lightcurve_fitting_b200.sampler import EnsembleSampler
     precision, cap = _SEG_CASES[name]
     wl = WORKLOADS[name]()
-    shape = (4, 8, 1) if wl.model_name == 'ShockCooling3' else (8, 8, 1)       # the fixed shape of the segmented launches
+    shape = (4, 16, 1) if wl.model_name == 'ShockCooling3' else (8, 16, 1)     # the fixed shape of the segmented launches
     P = _params(wl, 37, 3, widen=0.1)
     p0 = wl.start(50, np.random.default_rng(2))
     monkeypatch.setenv('LCF_RING', '0')                                          # half-step launches on both sides
