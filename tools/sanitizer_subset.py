@@ -42,6 +42,15 @@ def main():
     s.get_autocorr_time(tol=0, quiet=True)
     s.get_split_rhat()
     print('ok chain kernel, diagnostics', flush=True)
+    # segmented bank (k_pass_seg): slices of ~2 filters staged in turn, ShockCooling3's weight table rebuilt per slice
+    os.environ['LCF_SEG_SAMPLES'] = '100'
+    os.environ['LCF_RING'] = '0'
+    for wl, prec in ((W.synthetic_sc3(npoints=64), 'fp32'), (W.synthetic_cs3(npoints=60), 'fp64')):
+        prob = wl.device_problem(prec)
+        s = EnsembleSampler(24, wl.ndim, prob, seed=5)
+        s.run_mcmc(wl.start(24, rng), 3)
+        assert prob.last_launch()['kernel'] == 'k_pass_seg'
+    print('ok segmented bank', flush=True)
 
 
 if __name__ == '__main__':
