@@ -562,6 +562,10 @@ int choose_shape(lcf_problem *p, long long Ns, Shape *out) {
                     for (int s2 = S; s2 > 1; s2 >>= 1) cost *= 1.15;
                     if (nw < 8) cost *= 1.15;
                     if (ctas < sms) cost *= 1. + 0.25 * (1. - (double)ctas / sms);  // measured (cfg1 sweep): idle SMs cost more than the chain model says
+                    // measured (cfg2 at 25 000 / 50 000 walkers, profiles/round2_shape_model_vs_sweep.jsonl): with several waves of CTAs per SM a CTA of
+                    // fewer walkers repeats its prologue and the per-point front end more often -- 1 / 2 / 4-8 / 16 walkers per CTA cost
+                    // +20 / +7 / +4 / +2.5 % per walker against 32; without it the model took one walker per CTA for 12 500 walkers (+22 %)
+                    if (f32 && Ns >= 64LL * sms) { static const double few[6] = {1.20, 1.07, 1.04, 1.04, 1.025, 1.}; cost *= few[l]; }
                     // Flat split (one CTA per co-resident slot, each with groups / slots of the work) against the plain launch of the same
                     // shape, in units of the time two co-resident CTAs need for a group each.  Measured on B200 (profiles/round2_flat_split.txt):
                     // a CTA alone on its SM runs at 0.69 of the paired rate; the warp schedulers favour the older of two co-resident CTAs,

@@ -28,8 +28,12 @@ def main():
         ('cfg2 ShockCooling3 N=2000, 2e4 walkers', bench.workload(bench.device_truth, 2000, 'sc3'), 20_000, 10,
          [(32, 16, 1, 0), (32, 8, 1, 0), (16, 16, 1, 0), (16, 8, 1, 0), (8, 8, 1, 0), (32, 16, 2, 0)]),
     ]
+    strong = [(32, 16, 1, 0), (16, 16, 1, 0), (8, 16, 1, 0), (8, 8, 1, 0), (4, 16, 1, 0), (4, 8, 1, 0), (2, 8, 1, 0), (1, 8, 1, 0), (32, 16, 2, 0), (16, 16, 2, 0)]
+    for nw_s, gpus in ((50_000, 2), (25_000, 4), (12_500, 8)):        # the per-GPU share of the strong-scaling runs of bench.py (10^5 walkers in total)
+        cases.append(('cfg2 ShockCooling3 N=2000, %d walkers (strong scaling on %d GPUs)' % (nw_s, gpus), bench.workload(bench.device_truth, 2000, 'sc3'), nw_s, 10, strong))
+    only = sys.argv[1] if len(sys.argv) > 1 else ''
     for name, wl, nw, steps, shapes in cases:
-        if wl is None:
+        if wl is None or only not in name:
             continue
         prob = wl.device_problem('fp32')
         p0 = wl.start(nw, rng)
