@@ -282,6 +282,13 @@ int  lcf_set_tuning_flat(int mode);
    grid != groups x cluster_size was a flat split.                                                                               */
 int  lcf_problem_last_launch_ex(lcf_problem *p, int64_t *groups, int *sum_units, int *points_per_lane);
 
+/* Plan of a segmented launch (kernel variant 5; host only, no device needed).  A filter bank larger than shared memory is cut into
+   runs of consecutive filters of at most `cap_samples` transmission samples (two per pair record): greedy, each run as long as
+   fits.  segs_out[4 i .. 4 i + 3] = (first filter, end filter, first pair record, pair records) of run i; returns the number of
+   runs, or -1 when one filter alone exceeds `cap_samples` / `max_segs` runs are not enough.  The reference has no counterpart:
+   Filter.synthesize (filters.py:288-310) integrates one transmission curve at a time from host memory.                       */
+int  lcf_plan_bank_segments(const int *pair_records, int nfilters, int64_t cap_samples, int *segs_out, int max_segs);
+
 #ifdef __cplusplus
 }
 #endif

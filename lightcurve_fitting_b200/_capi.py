@@ -51,6 +51,7 @@ SYMBOLS = [
     ('lcf_set_tuning_ex', C.c_int, [C.c_int, C.c_int, C.c_int]),
     ('lcf_set_tuning_split', C.c_int, [C.c_int]),
     ('lcf_set_tuning_flat', C.c_int, [C.c_int]),
+    ('lcf_plan_bank_segments', C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int]),
     ('lcf_problem_last_launch_ex', C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ('lcf_blackbody_lstsq_batch', C.c_int, [C.c_int64, C.POINTER(C.c_int32), _pd, _pd, C.c_double, C.c_double, C.c_double, _pd, _pd,
                                             _pd, _pd, _pd, C.POINTER(C.c_int32)]),

@@ -471,19 +471,13 @@ int build_segments(lcf_problem *p, int force, Shape *bs) {
         if (force > 0) cap = std::min<long long>(cap, std::max(force & ~1, widest));
         if (widest > cap)
             return fail(LCF_ERR_ARG, "one filter has %d transmission samples, more than the %lld that fit in shared memory", widest, cap);
-        std::vector<int4> segs;
-        int f0 = 0, pair0 = 0, pairs = 0, most = 0;
         const int F = (int)p->h_filter_records.size();
-        for (int f = 0; f < F; ++f) {
-            const int r = p->h_filter_records[f];
-            if (f > f0 && 2LL * (pairs + r) > cap) {
-                segs.push_back(make_int4(f0, f, pair0, pairs));
-                f0 = f; pair0 += pairs; pairs = 0;
-            }
-            pairs += r;
-            most = std::max(most, 2 * pairs);
-        }
-        segs.push_back(make_int4(f0, F, pair0, pairs));
+        std::vector<int4> segs(F);
+        const int ns = lcf_plan_bank_segments(p->h_filter_records.data(), F, cap, reinterpret_cast<int *>(segs.data()), F);
+        if (ns < 1) return fail(LCF_ERR_STATE, "bank segmentation failed");
+        segs.resize(ns);
+        int most = 0;
+        for (const int4 &sg : segs) most = std::max(most, 2 * sg.w);
         int4 *d = nullptr;
         CUDA_TRY(cudaMalloc(&d, segs.size() * sizeof(int4)));
         p->allocs.push_back(d);
@@ -862,6 +856,30 @@ int lcf_set_tuning_split(int sample_chunks) {
     g_tune_ks = -1;
     for (int k = 0; sample_chunks && k <= 5; ++k) if ((1 << k) == sample_chunks) g_tune_ks = k;
     return 0;
+}
+
+// Host-only planner of the segmented launches (no device needed; build_segments uses it, tests call it on the CPU).
+int lcf_plan_bank_segments(const int *pair_records, int nfilters, int64_t cap_samples, int *segs_out, int max_segs) {
+    if (!pair_records || !segs_out || nfilters <= 0 || max_segs <= 0) return -1;
+    int n = 0, f0 = 0;
+    long long pair0 = 0, pairs = 0;
+    auto emit = [&](int f1) {
+        if (n >= max_segs) return false;
+        segs_out[4 * n] = f0; segs_out[4 * n + 1] = f1; segs_out[4 * n + 2] = (int)pair0; segs_out[4 * n + 3] = (int)pairs;
+        ++n;
+        return true;
+    };
+    for (int f = 0; f < nfilters; ++f) {
+        const long long r = pair_records[f];
+        if (r < 0 || 2 * r > cap_samples) return -1;                  // one filter alone exceeds the capacity
+        if (f > f0 && 2 * (pairs + r) > cap_samples) {
+            if (!emit(f)) return -1;
+            f0 = f; pair0 += pairs; pairs = 0;
+        }
+        pairs += r;
+    }
+    if (!emit(nfilters)) return -1;
+    return n;
 }
 
 int lcf_set_tuning_flat(int mode) {

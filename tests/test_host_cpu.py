@@ -352,3 +352,38 @@ def test_every_product_filter_curve_matches_reference_moments():
         got = [len(nu), nu[0], nu[-1], nu.sum(), tn.sum(), (nu * tn).sum(), (nu * nu * tn).sum(), np.abs(np.diff(tn)).sum(),
                f.freq_eff, f.dfreq, f.wl_eff, f.m0, f.M0]
         np.testing.assert_allclose(got, row, rtol=1e-11, err_msg=str(n))
+
+
+def test_bank_segment_planner_covers_every_filter_within_the_capacity():
+    """Host logic of the segmented launches (k_pass_seg; no device needed): runs of consecutive filters, each as long as fits."""
+    import ctypes as C
+    from lightcurve_fitting_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(4)
+
+    def plan(rec, cap, max_segs=None):
+        rec = np.ascontiguousarray(rec, np.int32)
+        out = np.zeros((len(rec) if max_segs is None else max_segs, 4), np.int32)
+        n = L.lcf_plan_bank_segments(rec.ctypes.data_as(C.POINTER(C.c_int)), len(rec), C.c_int64(cap),
+                                     out.ctypes.data_as(C.POINTER(C.c_int)), len(out))
+        return n, out[:max(n, 0)]
+
+    for _ in range(200):
+        rec = rng.integers(1, 800, rng.integers(1, 40))
+        cap = int(2 * rec.max() + rng.integers(0, 6000))
+        n, segs = plan(rec, cap)
+        assert n >= 1
+        assert segs[0, 0] == 0 and segs[-1, 1] == len(rec) and np.array_equal(segs[1:, 0], segs[:-1, 1])     # consecutive, complete
+        off = np.concatenate([[0], np.cumsum(rec)])
+        np.testing.assert_array_equal(segs[:, 2], off[segs[:, 0]])                                             # first pair record
+        np.testing.assert_array_equal(segs[:, 3], off[segs[:, 1]] - off[segs[:, 0]])                           # pair records
+        assert np.all(2 * segs[:, 3] <= cap)
+        for i in range(n - 1):                                                                                 # greedy: the next filter did not fit
+            assert 2 * (segs[i, 3] + rec[segs[i, 1]]) > cap
+    # everything fits: one run; one filter alone too large, or too few output rows: -1
+    assert plan([10, 20, 30], 1000)[0] == 1 and plan([10, 20, 30], 1000)[1].tolist() == [[0, 3, 0, 60]]
+    assert plan([10, 600, 30], 1000)[0] == -1
+    assert plan([100, 100, 100, 100], 200)[0] == 4 and plan([100, 100, 100, 100], 200, max_segs=3)[0] == -1
+    # the 30-filter FP64 case of the GPU test (pair records of the largest registry curves, ~14 000 samples of capacity)
+    n, segs = plan([741, 728, 661, 518, 514, 476, 458, 409, 402, 401, 352, 312, 305, 305, 281, 279, 277, 270, 240, 236], 14000)
+    assert n == 2 and 2 * segs[:, 3].sum() == 2 * 8165
