@@ -78,6 +78,16 @@ def test_packed_bank_reproduces_reference_synthesis():
     got = np.array([R ** 2 * np.sum(w[off[i]:off[i + 1]] * 10 ** (-0.4 * 0.35 * kappa[off[i]:off[i + 1]])
                                     / np.expm1(alpha[off[i]:off[i + 1]] / T)) for i, (T, R) in enumerate(zip(Tb, Rb))])
     np.testing.assert_allclose(got, G['bb/point_zebv'], rtol=1e-11)
+    # curves entirely in the ultraviolet / the mid-infrared (GALEX, JWST MIRI: outside the golden set) against the oracle's synthesis;
+    # pack_bank evaluates F99 for every filter, so an all-UV curve used to fail here whatever E(B-V) was
+    names = ['FUV', 'NUV', 'F2550W', 'F444W']
+    Tb, Rb = np.array([30., 12., 1.5, 4.]), np.array([1., 2., 30., 10.])
+    for kw in ({}, {'z': 0.02, 'ebv': 0.15}):
+        off, alpha, w, kappa = pack_bank([filtdict[n] for n in names], **kw)
+        got = np.array([R ** 2 * np.sum(w[off[i]:off[i + 1]] / np.expm1(alpha[off[i]:off[i + 1]] / T))
+                        for i, (T, R) in enumerate(zip(Tb, Rb))])
+        want = rp.blackbody_to_filters([rp.filtdict[n] for n in names], Tb, Rb, **kw)
+        np.testing.assert_allclose(got, want, rtol=1e-11)
 
 
 def test_extinction_law_matches_oracle():
